@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/liboracle.so (the plain-C restatement,
+oracle/spade_oracle.c). Built on demand with gcc (a few seconds)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+from .ref import RefCfg, make_cfg  # same struct layout (spo_cfg == ref_cfg)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "spade_oracle.c")
+    hdr = os.path.join(_HERE, "spade_oracle.h")
+    if (force or not os.path.exists(LIB_PATH)
+            or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        subprocess.check_call(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-o", LIB_PATH, src, "-lm"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.spo_array_size.restype = C.c_int64
+        _lib.spo_offset.restype = C.c_int64
+        _lib.spo_offset.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def array_size(cfg):
+    return int(lib().spo_array_size(C.byref(cfg)))
+
+
+def offset(cfg, v, i, j, k, lb):
+    return int(lib().spo_offset(C.byref(cfg), v, i, j, k, lb))
+
+
+def flux_div(cfg, q, rhs=None, increment=False):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.zeros_like(q) if rhs is None else np.array(rhs, dtype=np.float64, copy=True)
+    assert lib().spo_flux_div(C.byref(cfg), _ptr(q), _ptr(out), int(increment)) == 0
+    return out
+
+
+def exchange(cfg, q):
+    out = np.array(q, dtype=np.float64, copy=True)
+    assert lib().spo_exchange(C.byref(cfg), _ptr(out)) == 0
+    return out
+
+
+def reduce_umax(cfg, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = C.c_double(0.0)
+    assert lib().spo_reduce_umax(C.byref(cfg), _ptr(q), C.byref(out)) == 0
+    return out.value
+
+
+def advance(cfg, q, dt, nsteps):
+    out = np.array(q, dtype=np.float64, copy=True)
+    assert lib().spo_advance(C.byref(cfg), _ptr(out), C.c_double(dt), int(nsteps)) == 0
+    return out
+
+
+def exchange_tables(cfg, rank, cap=1 << 16):
+    send = np.zeros((cap, 16), dtype=np.int64)
+    recv = np.zeros((cap, 16), dtype=np.int64)
+    ns, nr = C.c_int64(0), C.c_int64(0)
+    offs = np.zeros((cfg.nranks, 6), dtype=np.int64)
+    i64 = C.POINTER(C.c_int64)
+    assert lib().spo_exchange_tables(C.byref(cfg), int(rank), send.ctypes.data_as(i64), recv.ctypes.data_as(i64),
+                                     C.c_int64(cap), C.byref(ns), C.byref(nr), offs.ctypes.data_as(i64)) == 0
+    assert ns.value <= cap and nr.value <= cap
+    return send[:ns.value].copy(), recv[:nr.value].copy(), offs
+
+
+def partition(nglob, nranks):
+    g2r = np.zeros(nglob, dtype=np.int64)
+    g2l = np.zeros(nglob, dtype=np.int64)
+    i64 = C.POINTER(C.c_int64)
+    lib().spo_partition(C.c_int64(nglob), int(nranks), g2r.ctypes.data_as(i64), g2l.ctypes.data_as(i64))
+    return g2r, g2l
+
+
+def prim2cons(gamma, R, p):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    w = np.zeros(5)
+    lib().spo_prim2cons(C.c_double(gamma), C.c_double(R), _ptr(p), _ptr(w))
+    return w
+
+
+def cons2prim(gamma, R, w):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    p = np.zeros(5)
+    lib().spo_cons2prim(C.c_double(gamma), C.c_double(R), _ptr(w), _ptr(p))
+    return p

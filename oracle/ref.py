@@ -1,0 +1,115 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/_ref/libspade_ref.so (the unmodified
+SPADE reference, built by oracle/Makefile from /root/reference/src + oracle/ref_driver.cc)."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libspade_ref.so")
+
+
+class RefCfg(C.Structure):
+    _fields_ = [("nblocks", C.c_int * 3), ("ncells", C.c_int * 3), ("ng", C.c_int),
+                ("bounds", C.c_double * 6), ("periodic", C.c_int * 3), ("scheme", C.c_int),
+                ("gamma", C.c_double), ("R", C.c_double), ("mu", C.c_double),
+                ("prandtl", C.c_double), ("sensor_eps", C.c_double), ("nranks", C.c_int),
+                ("integrator", C.c_int)]
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ref_last_error.restype = C.c_char_p
+        _lib.ref_array_size.restype = C.c_int64
+    return _lib
+
+
+def make_cfg(nblocks, ncells, ng=2, bounds=None, periodic=(1, 1, 1), scheme=0, gamma=1.4, R=287.15,
+             mu=1.0e-3, prandtl=0.72, sensor_eps=1e-2, nranks=1, integrator=0):
+    c = RefCfg()
+    c.nblocks[:] = list(nblocks)
+    c.ncells[:] = list(ncells)
+    c.ng = ng
+    if bounds is None:
+        bounds = [0.0, 2 * np.pi] * 3
+    c.bounds[:] = list(bounds)
+    c.periodic[:] = [int(p) for p in periodic]
+    c.scheme = scheme
+    c.gamma, c.R, c.mu, c.prandtl, c.sensor_eps = gamma, R, mu, prandtl, sensor_eps
+    c.nranks = nranks
+    c.integrator = integrator
+    return c
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("reference driver failed: " + lib().ref_last_error().decode())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def array_size(cfg):
+    return int(lib().ref_array_size(C.byref(cfg)))
+
+
+def flux_div(cfg, q, rhs=None, increment=False):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.zeros_like(q) if rhs is None else np.array(rhs, dtype=np.float64, copy=True)
+    _check(lib().ref_flux_div(C.byref(cfg), _ptr(q), _ptr(out), int(increment)))
+    return out
+
+
+def exchange(cfg, q):
+    out = np.array(q, dtype=np.float64, copy=True)
+    _check(lib().ref_exchange(C.byref(cfg), _ptr(out)))
+    return out
+
+
+def reduce_umax(cfg, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = C.c_double(0.0)
+    _check(lib().ref_reduce_umax(C.byref(cfg), _ptr(q), C.byref(out)))
+    return out.value
+
+
+def advance(cfg, q, dt, nsteps):
+    out = np.array(q, dtype=np.float64, copy=True)
+    sec = C.c_double(0.0)
+    _check(lib().ref_advance(C.byref(cfg), _ptr(out), C.c_double(dt), int(nsteps), C.byref(sec)))
+    return out, sec.value
+
+
+def exchange_tables(cfg, rank, cap=1 << 16):
+    send = np.zeros((cap, 16), dtype=np.int64)
+    recv = np.zeros((cap, 16), dtype=np.int64)
+    ns, nr = C.c_int64(0), C.c_int64(0)
+    offs = np.zeros((cfg.nranks, 6), dtype=np.int64)
+    i64 = C.POINTER(C.c_int64)
+    _check(lib().ref_exchange_tables(C.byref(cfg), int(rank), send.ctypes.data_as(i64), recv.ctypes.data_as(i64),
+                                     C.c_int64(cap), C.byref(ns), C.byref(nr), offs.ctypes.data_as(i64)))
+    assert ns.value <= cap and nr.value <= cap
+    return send[:ns.value].copy(), recv[:nr.value].copy(), offs
+
+
+def prim2cons(gamma, R, p):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    w = np.zeros(5)
+    lib().ref_prim2cons(C.c_double(gamma), C.c_double(R), _ptr(p), _ptr(w))
+    return w
+
+
+def cons2prim(gamma, R, w):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    p = np.zeros(5)
+    lib().ref_cons2prim(C.c_double(gamma), C.c_double(R), _ptr(w), _ptr(p))
+    return p
