@@ -1,0 +1,160 @@
+/* spade_b200.h — C ABI of libspade_b200.so: the B200 (sm_100a) implementation of SPADE's RHS hot
+ * path (flux_div + ghost exchange + RK stage update + reductions).
+ *
+ * Every entry point takes plain pointers and sizes. Device memory is owned by the caller (SPADE's
+ * grid_array / device_vector, or a torch tensor): the library never allocates persistent state
+ * except inside the opaque handles created and destroyed here. There is NO CPU fallback: every
+ * compute entry point launches hand-written CUDA kernels and returns an error if no device is
+ * present.
+ *
+ * Array layout (bit-exact with the reference's default mem_map::linear_t, reference
+ * src/core/mem_map.h:484-496, src/grid/grid_array.h:252-257):
+ *     off(v,i,j,k,lb) = v + 5*((i+g0) + (n0+2*g0)*((j+g1) + (n1+2*g1)*((k+g2) + (n2+2*g2)*lb)))
+ * v: 0..4 = (p,T,u,v,w) for primitive arrays, (continuity, energy, x/y/z momentum) for residuals
+ * (reference src/navier-stokes/fluid_state.h:11-77); i,j,k may run over [-g, n+g).
+ *
+ * Error convention: 0 = success; nonzero = failure (cudaError_t value or SPB_ERR_*), message from
+ * spb_last_error(). The reference throws except::sp_exception after a failed CUDA call
+ * (reference src/dispatch/execute.h:86-96); the C++ shim (include/spade_b200_shim.hpp) turns a
+ * nonzero return into that exception.
+ *
+ * Threading: one host thread (or process) per GPU, each having selected its device; calls on
+ * different devices are independent (reference src/parallel/compute_pool.h:497-514).
+ * Streams: `stream` is a cudaStream_t passed as void* (NULL = default stream). All calls are
+ * asynchronous with respect to the host unless stated otherwise; the reference's synchronous
+ * semantics (src/dispatch/execute.h:85) are recovered with spb_sync().
+ */
+#ifndef SPADE_B200_H
+#define SPADE_B200_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_NVAR 5
+
+enum {
+    SPB_ERR_BAD_ARG      = 10001,
+    SPB_ERR_UNSUPPORTED  = 10002,
+    SPB_ERR_NO_DEVICE    = 10003,
+    SPB_ERR_DRIVER       = 10004
+};
+
+/* ---- flux functor description -------------------------------------------------------------
+ * Closed set of the reference functor types the kernels implement; the C++ shim recognises the
+ * composed functor type at compile time and fills this POD from its by-value members.
+ *   conv: convective scheme          reference src/navier-stokes/convective.h
+ *   diss: dissipative scheme blended by the sensor (hybrid_scheme_t), reference hybrid_scheme.h:15-47
+ *   visc: viscous::visc_lr with viscous_laws::constant_viscosity_t, reference viscous.h:14-113 */
+enum { SPB_CONV_NONE = 0, SPB_CONV_TOTANI = 1 /* totani_lr, convective.h:54-94 */,
+       SPB_CONV_CENT_KEEP4 = 2 /* cent_keep<4>, convective.h:97-192 */,
+       SPB_CONV_FWENO = 3 /* fweno_t alone, convective.h:336-497 */ };
+enum { SPB_DISS_NONE = 0, SPB_DISS_FWENO = 1 /* hybrid_scheme_t(conv, fweno_t, ducros_t, tag) */ };
+enum { SPB_BLEND_FULL_FLUX = 0 /* (1-a)F0 + a F1 */, SPB_BLEND_DISS_FLUX = 1 /* F0 + a F1 */ };
+
+typedef struct spb_flux_desc
+{
+    int    conv;        /* SPB_CONV_*  */
+    int    diss;        /* SPB_DISS_*  */
+    int    blend;       /* SPB_BLEND_* (used when diss != NONE) */
+    int    visc;        /* 0 / 1 : add viscous::visc_lr */
+    double gamma, R;    /* fluid_state::ideal_gas_t, reference src/navier-stokes/gas.h:35-49 */
+    double mu;          /* constant_viscosity_t::visc */
+    double beta;        /* constant_viscosity_t::beta   (= -2 mu/3 as stored by the reference) */
+    double prandtl_inv; /* constant_viscosity_t::prandtl_inv */
+    double sensor_eps;  /* state_sensor::ducros_t::epsilon, reference state_sensor.h:21-43 */
+} spb_flux_desc;
+
+/* ---- grid ------------------------------------------------------------------------------------
+ * Local (per-rank) block geometry, replacing the device image of grid_geometry_t
+ * (reference src/grid/grid_geometry.h:16-100, src/grid/cartesian_grid.h:114-165).
+ * bbox: host array [nlb][6] = xmin,xmax,ymin,ymax,zmin,zmax of each local block in computational
+ * coordinates; dx = (max-min)/nx and inv_dx = 1.0/dx are formed exactly as the reference does. */
+typedef struct spb_grid spb_grid;
+int  spb_grid_create(spb_grid** out, const int nx[3], const int ng[3], int64_t nlb, const double* bbox_host);
+void spb_grid_destroy(spb_grid* g);
+int64_t spb_grid_array_size(const spb_grid* g);                    /* doubles in one 5-variable array */
+int64_t spb_grid_offset(const spb_grid* g, int v, int i, int j, int k, int64_t lb);
+
+/* ---- RHS: replaces pde_algs::flux_div(q, rhs, flux_func, traits) ------------------------------
+ * reference src/pde-algs/flux-div/flux_div.h:23-41, flux_div_basic.h:17-77.
+ * rhs(cell) (+)= sum_dir (F_lowerface - F_upperface) / dx_dir on interior cells (identity coords,
+ * Jacobian 1). increment = 0 is the `overwrite` trait: interior cells are overwritten (the ghost
+ * cells of rhs, which the reference zero-fills, are left untouched — they are never read).
+ * q must have its ghost cells filled (exchange) to the stencil depth of the scheme. */
+int spb_flux_div(const spb_grid* g, const double* q_dev, double* rhs_dev, const spb_flux_desc* flux,
+                 int increment, void* stream);
+/* Same, restricted to local blocks [lb_begin, lb_end): used to overlap the exchange of rank-boundary
+ * blocks with the RHS of interior blocks. */
+int spb_flux_div_blocks(const spb_grid* g, const double* q_dev, double* rhs_dev, const spb_flux_desc* flux,
+                        int increment, int64_t lb_begin, int64_t lb_end, void* stream);
+
+/* ---- RK stage update: replaces detail::transform_advance_to -----------------------------------
+ * reference src/time-integration/advance.h:57-102: per interior cell
+ *   w = cons(q); w += sum_j coeff[j]*k_j  (only j with coeff[j] != 0, in order); q = prim(w)
+ * coeff[j] = (a_ij - a_{i-1,j})*dt as formed by the caller (the shim forms it like advance.h:84-92). */
+int spb_rk_update(const spb_grid* g, double* q_dev, const double* const* k_dev, int nk, const double* coeff,
+                  double gamma, double R, void* stream);
+/* 2-register SSPRK3 stages opt_rk3_s0/s1/s2, reference src/time-integration/advance.h:286-354.
+ * stage 1 overwrites r0 with (dt/6)(r0+r1) exactly like the reference. */
+int spb_ssprk3_stage(const spb_grid* g, int stage, double* q_dev, double* r0_dev, const double* r1_dev,
+                     double dt, double gamma, double R, void* stream);
+
+/* ---- reduction: replaces algs::transform_reduce(array, make_reduction(array, f, op)) ----------
+ * reference src/algs/transform_reduce.h:43-191. Closed set of element kernels `f`. */
+enum { SPB_RED_MAX = 0, SPB_RED_SUM = 1 };
+enum { SPB_FN_WAVESPEED = 0 /* sqrt(gamma R T) + |u|  (CFL, development/cuda-tgv/main.cc:152-161) */,
+       SPB_FN_VAR = 1 /* q[ivar] */, SPB_FN_ABSVAR = 2 /* |q[ivar]| */, SPB_FN_KINETIC = 3 /* 0.5 rho |u|^2 */ };
+/* Synchronous: returns the reduced value over the interior cells of all local blocks in *out_host. */
+int spb_reduce(const spb_grid* g, const double* q_dev, int op, int fn, int ivar, double gamma, double R,
+               double* out_host, void* stream);
+
+/* ---- ghost exchange: replaces make_exchange / arr_exchange_t::exchange -------------------------
+ * reference src/grid/make_exchange.h:111-421, exchange_config.h:286-419, get_transaction.h:11-97.
+ * A plan holds this rank's sorted send and receive transaction lists; lists are bit-identical to
+ * exchange_config_t::send_data[0] / recv_data[0] of the reference (same order, boxes and tags). */
+typedef struct spb_exchange spb_exchange;
+/* Uniform cartesian block lattice partitioned like partition::block_partition_t
+ * (reference src/grid/partition.h:27-84, src/grid/cartesian_blocks.h:40-105). Host-only, no GPU needed. */
+int  spb_exchange_create(spb_exchange** out, const int nblocks[3], const int nx[3], const int ng[3],
+                         const int periodic[3], int rank, int nranks);
+/* From transaction tables produced elsewhere (e.g. marshalled from SPADE's exchange_config_t by the shim);
+ * each transaction is 16 int64: tag, rank_send, rank_recv, glob_src_blk, glob_dst_blk,
+ * src.min[0..3], src.size[0..2], dst.min[0..3]   (index 3 = local block id, -1 if not owned). */
+int  spb_exchange_create_from_tables(spb_exchange** out, const int nx[3], const int ng[3], int rank, int nranks,
+                                     const int64_t* send, int64_t nsend, const int64_t* recv, int64_t nrecv);
+void spb_exchange_destroy(spb_exchange* e);
+int64_t spb_exchange_num_send(const spb_exchange* e);
+int64_t spb_exchange_num_recv(const spb_exchange* e);
+/* copies the tables out (host); offs gets 6 int64 per peer: send_message_size, recv_message_size,
+ * send_rank_offsets, send_rank_sizes, recv_rank_offsets, recv_rank_sizes (cells / transactions). */
+int  spb_exchange_tables(const spb_exchange* e, int64_t* send, int64_t* recv, int64_t* offs);
+int64_t spb_exchange_local_blocks(const spb_exchange* e);          /* blocks owned by this rank */
+int64_t spb_exchange_first_block(const spb_exchange* e);           /* global id of local block 0 */
+/* cells this rank sends to / receives from `peer` (message sizes in cells; x5 doubles). Element
+ * order inside the message is the reference's: transaction order, ix + nx*(iy + ny*iz), v fastest. */
+int64_t spb_exchange_send_cells(const spb_exchange* e, int peer);
+int64_t spb_exchange_recv_cells(const spb_exchange* e, int peer);
+/* same-rank transactions: q(dst) = q(src) on the device (make_exchange.h:166-203). */
+int spb_exchange_local(spb_exchange* e, double* q_dev, void* stream);
+/* pack q into the contiguous message for `peer` (make_exchange.h:136-164) / unpack (340-369). */
+int spb_exchange_pack(spb_exchange* e, const double* q_dev, int peer, double* sendbuf_dev, void* stream);
+int spb_exchange_unpack(spb_exchange* e, double* q_dev, int peer, const double* recvbuf_dev, void* stream);
+/* One-sided variant over NVLink peer memory: pack straight into the peer's receive buffer
+ * (peer_recvbuf_dev is a pointer into the peer GPU's memory, mapped with cudaIpcOpenMemHandle or
+ * cudaDeviceEnablePeerAccess). Same element order as spb_exchange_pack. */
+int spb_exchange_pack_peer(spb_exchange* e, const double* q_dev, int peer, double* peer_recvbuf_dev, void* stream);
+
+/* ---- utilities ---------------------------------------------------------------------------------- */
+const char* spb_last_error(void);
+int  spb_device_count(void);
+int  spb_sync(void* stream);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+int64_t spb_launch_count(void);
+const char* spb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,89 @@
+"""ctypes loader of libspade_b200.so (the C ABI declared in include/spade_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import of any compute entry point
+fails loudly, and every compute call fails if no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspade_b200.so")
+
+
+class FluxDesc(C.Structure):
+    """spb_flux_desc (include/spade_b200.h)."""
+    _fields_ = [("conv", C.c_int), ("diss", C.c_int), ("blend", C.c_int), ("visc", C.c_int),
+                ("gamma", C.c_double), ("R", C.c_double), ("mu", C.c_double), ("beta", C.c_double),
+                ("prandtl_inv", C.c_double), ("sensor_eps", C.c_double)]
+
+
+class SpbError(RuntimeError):
+    pass
+
+
+_lib = None
+_i64p = C.POINTER(C.c_int64)
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); every symbol include/spade_b200.h declares
+SYMBOLS = {
+    "spb_grid_create": (C.c_int, [C.POINTER(C.c_void_p), _ip, _ip, C.c_int64, _dp]),
+    "spb_grid_destroy": (None, [C.c_void_p]),
+    "spb_grid_array_size": (C.c_int64, [C.c_void_p]),
+    "spb_grid_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
+    "spb_flux_div": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.c_int, C.c_void_p]),
+    "spb_flux_div_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.c_int,
+                                      C.c_int64, C.c_int64, C.c_void_p]),
+    "spb_rk_update": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, _dp, C.c_double,
+                                C.c_double, C.c_void_p]),
+    "spb_ssprk3_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                   C.c_double, C.c_double, C.c_void_p]),
+    "spb_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp,
+                             C.c_void_p]),
+    "spb_exchange_create": (C.c_int, [C.POINTER(C.c_void_p), _ip, _ip, _ip, _ip, C.c_int, C.c_int]),
+    "spb_exchange_create_from_tables": (C.c_int, [C.POINTER(C.c_void_p), _ip, _ip, C.c_int, C.c_int, _i64p,
+                                                  C.c_int64, _i64p, C.c_int64]),
+    "spb_exchange_destroy": (None, [C.c_void_p]),
+    "spb_exchange_num_send": (C.c_int64, [C.c_void_p]),
+    "spb_exchange_num_recv": (C.c_int64, [C.c_void_p]),
+    "spb_exchange_tables": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p]),
+    "spb_exchange_local_blocks": (C.c_int64, [C.c_void_p]),
+    "spb_exchange_first_block": (C.c_int64, [C.c_void_p]),
+    "spb_exchange_send_cells": (C.c_int64, [C.c_void_p, C.c_int]),
+    "spb_exchange_recv_cells": (C.c_int64, [C.c_void_p, C.c_int]),
+    "spb_exchange_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "spb_exchange_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "spb_exchange_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "spb_exchange_pack_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "spb_last_error": (C.c_char_p, []),
+    "spb_device_count": (C.c_int, []),
+    "spb_sync": (C.c_int, [C.c_void_p]),
+    "spb_launch_count": (C.c_int64, []),
+    "spb_version": (C.c_char_p, []),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SpbError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(spade_b200 has no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SpbError(f"libspade_b200 error {rc}: {lib().spb_last_error().decode()}")
+
+
+def int3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])

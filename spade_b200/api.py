@@ -1,0 +1,578 @@
+"""Host-side mirror of the SPADE operator API for the RHS hot path, on top of the C ABI.
+
+Names, argument meaning and error behaviour follow the reference (wvannoordt/spade, C++20 headers):
+    cartesian_blocks_t / cartesian_grid_t   src/grid/cartesian_blocks.h:24-117, cartesian_grid.h:55-384
+    grid_array                              src/grid/grid_array.h:182-422
+    make_exchange / arr_exchange_t.exchange src/grid/make_exchange.h:111-421
+    pde_algs.flux_div                       src/pde-algs/flux-div/flux_div.h:23-56
+    time_integration.integrator_t, rk_t     src/time-integration/integrator.h:25-59, explicit.h:27-116,
+                                            advance.h:236-280, 359-402
+    algs.transform_reduce                   src/algs/transform_reduce.h:43-191
+    flux functors                           src/navier-stokes/*.h
+The C++ shim (include/spade_b200_shim.hpp) is the drop-in for an existing SPADE solver; this module is
+the same thing for Python drivers, the tests and bench.py. torch supplies device memory, streams and
+torch.distributed — every kernel is in libspade_b200.so.
+"""
+import ctypes as C
+from fractions import Fraction
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FluxDesc, SpbError, check, int3, lib
+
+NVAR = 5
+
+# ---- enums of include/spade_b200.h ---------------------------------------------------------------
+CONV_NONE, CONV_TOTANI, CONV_CENT_KEEP4, CONV_FWENO = 0, 1, 2, 3
+DISS_NONE, DISS_FWENO = 0, 1
+BLEND_FULL_FLUX, BLEND_DISS_FLUX = 0, 1
+RED_MAX, RED_SUM = 0, 1
+FN_WAVESPEED, FN_VAR, FN_ABSVAR, FN_KINETIC = 0, 1, 2, 3
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+# ---- parallel group (reference parallel::pool_t, src/parallel/compute_pool.h:141-365) --------------
+class pool_t:
+    """rank/size view of the process group; one process per GPU (torch.distributed) instead of the
+    reference's one std::thread per GPU."""
+
+    def __init__(self, rank=0, size=1, group=None):
+        self._rank, self._size, self.group = int(rank), int(size), group
+
+    @staticmethod
+    def from_torch(group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return pool_t(dist.get_rank(group), dist.get_world_size(group), group)
+        return pool_t()
+
+    def rank(self):
+        return self._rank
+
+    def size(self):
+        return self._size
+
+    def isroot(self):
+        return self._rank == 0
+
+    def sync(self):
+        if self._size > 1:
+            import torch.distributed as dist
+            dist.barrier(self.group)
+
+    def reduce(self, value, op):
+        """pool_t::reduce (compute_pool.h:247-284): all ranks get the reduced scalar."""
+        if self._size == 1:
+            return value
+        import torch.distributed as dist
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.tensor([value], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == RED_MAX else dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
+
+# ---- grid ---------------------------------------------------------------------------------------------
+class cartesian_blocks_t:
+    """Uniform lattice of blocks; global id lb = bi + nb0*(bj + nb1*bk) (cartesian_blocks.h:54-55,96)."""
+
+    def __init__(self, num_blocks, bounds):
+        self.num_blocks = [int(x) for x in num_blocks]
+        self.bounds = [float(x) for x in bounds]            # xmin xmax ymin ymax zmin zmax
+        assert len(self.num_blocks) == 3 and len(self.bounds) == 6
+        self.total_blocks = self.num_blocks[0] * self.num_blocks[1] * self.num_blocks[2]
+
+    def total_num_blocks(self):
+        return self.total_blocks
+
+    def block_index(self, lb):
+        nb = self.num_blocks
+        return (lb % nb[0], (lb // nb[0]) % nb[1], lb // (nb[0] * nb[1]))
+
+    def get_block_box(self, lb):
+        """cartesian_blocks.h:49,66-71: min = bounds.min + b*bsize; max = min + bsize."""
+        b = self.block_index(lb)
+        out = []
+        for d in range(3):
+            bsize = (self.bounds[2 * d + 1] - self.bounds[2 * d]) / self.num_blocks[d]
+            lo = self.bounds[2 * d] + b[d] * bsize
+            out += [lo, lo + bsize]
+        return out
+
+
+class identity:
+    """coords::identity (core/coord_system.h:51): the only coordinate system the reference's
+    gradient-based fluxes accept (info_gradient.h:83)."""
+
+
+class cartesian_grid_t:
+    """cartesian_grid_t(cells_in_block, blocks, coords, group), cartesian_grid.h:84-89."""
+
+    def __init__(self, cells_in_block, blocks, coords=None, group=None):
+        if coords is not None and not isinstance(coords, identity):
+            raise SpbError("cartesian_grid_t: only coords.identity is implemented (as in the reference's flux path)")
+        self.num_cell = [int(x) for x in cells_in_block]
+        self.blocks = blocks
+        self._group = group if group is not None else pool_t()
+        # partition::block_partition_t (partition.h:27-84) — taken from the library's own plan builder
+        plan = C.c_void_p()
+        check(lib().spb_exchange_create(C.byref(plan), int3(blocks.num_blocks), int3(self.num_cell), int3([1, 1, 1]),
+                                        int3([1, 1, 1]), self._group.rank(), self._group.size()))
+        self.num_local_blocks = int(lib().spb_exchange_local_blocks(plan))
+        self.first_block = int(lib().spb_exchange_first_block(plan))
+        lib().spb_exchange_destroy(plan)
+        self._bbox = np.array([blocks.get_block_box(self.first_block + l) for l in range(self.num_local_blocks)],
+                              dtype=np.float64).reshape(-1)
+        self._handles = {}
+
+    def handle(self, num_exch):
+        """spb_grid for arrays with `num_exch` exchange cells (device image of grid_geometry_t)."""
+        key = tuple(int(x) for x in num_exch)
+        if key not in self._handles:
+            h = C.c_void_p()
+            check(lib().spb_grid_create(C.byref(h), int3(self.num_cell), int3(key), self.num_local_blocks,
+                                        self._bbox.ctypes.data_as(C.POINTER(C.c_double))))
+            self._handles[key] = h
+        return self._handles[key]
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                lib().spb_grid_destroy(h)
+            self._handles = {}
+        except Exception:
+            pass
+
+    def group(self):
+        return self._group
+
+    def get_num_local_blocks(self):
+        return self.num_local_blocks
+
+    def get_num_global_blocks(self):
+        return self.blocks.total_blocks
+
+    def get_num_cells(self, d=None):
+        return self.num_cell if d is None else self.num_cell[d]
+
+    def get_dx(self, d, lb=0):
+        box = self.blocks.get_block_box(self.first_block + lb)
+        return (box[2 * d + 1] - box[2 * d]) / self.num_cell[d]
+
+    def get_grid_size(self):
+        return self.num_cell[0] * self.num_cell[1] * self.num_cell[2] * self.blocks.total_blocks
+
+    def local_cells(self):
+        return self.num_cell[0] * self.num_cell[1] * self.num_cell[2] * self.num_local_blocks
+
+    def cell_centers(self, lb, num_exch):
+        """x,y,z of all padded cells of local block lb (grid_geometry.h:58-70), numpy arrays."""
+        box = self.blocks.get_block_box(self.first_block + lb)
+        out = []
+        for d in range(3):
+            dx = (box[2 * d + 1] - box[2 * d]) / self.num_cell[d]
+            idx = np.arange(-num_exch[d], self.num_cell[d] + num_exch[d])
+            out.append(box[2 * d] + (idx + 0.5) * dx)
+        return out
+
+
+class grid_array:
+    """grid_array(grid, fill, num_exch, device) — 5-variable cell-centred array on the device in the
+    reference's memory order off = v + 5*(i' + ni*(j' + nj*(k' + nk*lb))) (mem_map.h:484-496): a contiguous
+    float64 cuda tensor of shape [nlb, nk', nj', ni', 5]."""
+
+    def __init__(self, grid, fill=0.0, num_exch=(2, 2, 2), data=None):
+        self.grid = grid
+        self.num_exch = [int(x) for x in num_exch]
+        self.h = grid.handle(self.num_exch)
+        p = [n + 2 * g for n, g in zip(grid.num_cell, self.num_exch)]
+        self.shape = (grid.num_local_blocks, p[2], p[1], p[0], NVAR)
+        if data is None:
+            self.data = torch.full(self.shape, float(fill), dtype=torch.float64, device="cuda")
+        else:
+            assert tuple(data.shape) == self.shape and data.dtype == torch.float64 and data.is_cuda
+            self.data = data.contiguous()
+
+    @staticmethod
+    def from_host(grid, host, num_exch=(2, 2, 2)):
+        """host: numpy array in reference order; copied through pinned memory."""
+        p = [n + 2 * g for n, g in zip(grid.num_cell, num_exch)]
+        shape = (grid.num_local_blocks, p[2], p[1], p[0], NVAR)
+        h = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float64).reshape(shape))
+        return grid_array(grid, num_exch=num_exch, data=h.pin_memory().to("cuda", non_blocking=True))
+
+    def to_host(self):
+        return self.data.cpu().numpy()
+
+    def get_grid(self):
+        return self.grid
+
+    def get_num_exchange(self):
+        return self.num_exch
+
+    def interior(self):
+        g, n = self.num_exch, self.grid.num_cell
+        return self.data[:, g[2]:g[2] + n[2], g[1]:g[1] + n[1], g[0]:g[0] + n[0], :]
+
+    def clone(self):
+        return grid_array(self.grid, num_exch=self.num_exch, data=self.data.clone())
+
+
+# ---- flux functors (closed set; each mirrors a reference type) ---------------------------------------------
+class ideal_gas_t:
+    """fluid_state::ideal_gas_t(gamma, R), gas.h:35-49"""
+
+    def __init__(self, gamma, R):
+        self.gamma, self.R = float(gamma), float(R)
+
+
+class constant_viscosity_t:
+    """viscous_laws::constant_viscosity_t(visc, prandtl), viscous_laws.h:62-100"""
+
+    def __init__(self, visc, prandtl):
+        self.visc = float(visc)
+        self.beta = -2.0 * self.visc / 3.0
+        self.prandtl_inv = 1.0 / float(prandtl)
+
+
+class _functor:
+    def desc(self):
+        raise NotImplementedError
+
+
+class totani_lr(_functor):
+    """convective::totani_lr, convective.h:54-94"""
+
+    def __init__(self, gas):
+        self.gas = gas
+
+    def _fill(self, d):
+        d.conv = CONV_TOTANI
+        d.gamma, d.R = self.gas.gamma, self.gas.R
+
+
+class cent_keep(_functor):
+    """convective::cent_keep<order>(gas), convective.h:97-192; order 2 == totani_lr arithmetic."""
+
+    def __init__(self, order, gas):
+        if order not in (2, 4):
+            raise SpbError("cent_keep: only orders 2 and 4 fit two exchange cells")
+        self.order, self.gas = order, gas
+
+    def _fill(self, d):
+        d.conv = CONV_TOTANI if self.order == 2 else CONV_CENT_KEEP4
+        d.gamma, d.R = self.gas.gamma, self.gas.R
+
+
+class fweno_t(_functor):
+    """convective::fweno_t<gas, enable_smooth>, convective.h:336-497"""
+
+    def __init__(self, gas):
+        self.gas = gas
+
+    def _fill(self, d):
+        d.conv = CONV_FWENO
+        d.gamma, d.R = self.gas.gamma, self.gas.R
+
+
+class ducros_t:
+    """state_sensor::ducros_t(epsilon), state_sensor.h:21-43"""
+
+    def __init__(self, epsilon):
+        self.epsilon = float(epsilon)
+
+
+full_flux, diss_flux = BLEND_FULL_FLUX, BLEND_DISS_FLUX
+
+
+class hybrid_scheme_t(_functor):
+    """convective::hybrid_scheme_t(scheme0, scheme1, blender, tag), hybrid_scheme.h:15-47"""
+
+    def __init__(self, scheme0, scheme1, blender, tag=full_flux):
+        if not isinstance(scheme1, fweno_t) or not isinstance(blender, ducros_t) or isinstance(scheme0, fweno_t):
+            raise SpbError("hybrid_scheme_t: implemented for (totani_lr|cent_keep, fweno_t, ducros_t)")
+        self.scheme0, self.scheme1, self.blender, self.tag = scheme0, scheme1, blender, tag
+
+    def _fill(self, d):
+        self.scheme0._fill(d)
+        d.diss = DISS_FWENO
+        d.blend = self.tag
+        d.sensor_eps = self.blender.epsilon
+
+
+class visc_lr(_functor):
+    """viscous::visc_lr(vlaw, gas), viscous.h:14-113"""
+
+    def __init__(self, vlaw, gas):
+        if not isinstance(vlaw, constant_viscosity_t):
+            raise SpbError("visc_lr: only constant_viscosity_t has get_all() in the reference (viscous_laws.h:102-135)")
+        self.vlaw, self.gas = vlaw, gas
+
+    def _fill(self, d):
+        d.visc = 1
+        d.mu, d.beta, d.prandtl_inv = self.vlaw.visc, self.vlaw.beta, self.vlaw.prandtl_inv
+        d.gamma, d.R = self.gas.gamma, self.gas.R
+
+
+class composite_kernel_t(_functor):
+    """omni::compose(k0, k1, ...), omni/compose.h:11-45: the sum of the kernels on the union stencil."""
+
+    def __init__(self, *kernels):
+        self.kernels = kernels
+        nconv = sum(1 for k in kernels if not isinstance(k, visc_lr))
+        nvisc = sum(1 for k in kernels if isinstance(k, visc_lr))
+        if nconv > 1 or nvisc > 1:
+            raise SpbError("compose: at most one convective and one viscous functor")
+
+    def _fill(self, d):
+        for k in self.kernels:
+            k._fill(d)
+
+
+def compose(*kernels):
+    return composite_kernel_t(*kernels)
+
+
+def flux_desc(flux_func):
+    d = FluxDesc()
+    d.conv, d.diss, d.blend, d.visc = CONV_NONE, DISS_NONE, BLEND_FULL_FLUX, 0
+    d.gamma, d.R, d.mu, d.beta, d.prandtl_inv, d.sensor_eps = 1.4, 287.15, 0.0, 0.0, 1.0, 0.0
+    flux_func._fill(d)
+    return d
+
+
+# ---- pde_algs ------------------------------------------------------------------------------------------------
+overwrite, increment = 0, 1
+
+
+def flux_div(prims, rhs, flux_func, traits=increment, blocks=None):
+    """pde_algs::flux_div(prims, rhs, flux_func, traits); default trait is `increment` like
+    flux_div_basic.h:32-35. `blocks=(b0,b1)` restricts to a local block range."""
+    d = flux_func if isinstance(flux_func, FluxDesc) else flux_desc(flux_func)
+    if blocks is None:
+        check(lib().spb_flux_div(prims.h, _dptr(prims.data), _dptr(rhs.data), C.byref(d), int(traits), _stream_ptr()))
+    else:
+        check(lib().spb_flux_div_blocks(prims.h, _dptr(prims.data), _dptr(rhs.data), C.byref(d), int(traits),
+                                        int(blocks[0]), int(blocks[1]), _stream_ptr()))
+
+
+# ---- exchange ------------------------------------------------------------------------------------------------
+class arr_exchange_t:
+    """make_exchange(array, periodic) -> handle; handle.exchange(array, pool) (make_exchange.h:111-421)."""
+
+    def __init__(self, grid, num_exch, periodic):
+        self.grid = grid
+        self.pool = grid.group()
+        self._h = C.c_void_p()
+        check(lib().spb_exchange_create(C.byref(self._h), int3(grid.blocks.num_blocks), int3(grid.num_cell),
+                                        int3(num_exch), int3([int(bool(p)) for p in periodic]),
+                                        self.pool.rank(), self.pool.size()))
+        self.send_cells = [int(lib().spb_exchange_send_cells(self._h, p)) for p in range(self.pool.size())]
+        self.recv_cells = [int(lib().spb_exchange_recv_cells(self._h, p)) for p in range(self.pool.size())]
+        self._sendbuf, self._recvbuf = {}, {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().spb_exchange_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def tables(self):
+        ns, nr = int(lib().spb_exchange_num_send(self._h)), int(lib().spb_exchange_num_recv(self._h))
+        send = np.zeros((ns, 16), dtype=np.int64)
+        recv = np.zeros((nr, 16), dtype=np.int64)
+        offs = np.zeros((self.pool.size(), 6), dtype=np.int64)
+        i64 = C.POINTER(C.c_int64)
+        check(lib().spb_exchange_tables(self._h, send.ctypes.data_as(i64), recv.ctypes.data_as(i64), offs.ctypes.data_as(i64)))
+        return send, recv, offs
+
+    def _buffers(self):
+        me = self.pool.rank()
+        for p in range(self.pool.size()):
+            if p == me:
+                continue
+            if self.send_cells[p] and p not in self._sendbuf:
+                self._sendbuf[p] = torch.empty(NVAR * self.send_cells[p], dtype=torch.float64, device="cuda")
+            if self.recv_cells[p] and p not in self._recvbuf:
+                self._recvbuf[p] = torch.empty(NVAR * self.recv_cells[p], dtype=torch.float64, device="cuda")
+
+    def exchange(self, array, pool=None):
+        st = _stream_ptr()
+        me = self.pool.rank()
+        if self.pool.size() > 1:
+            import torch.distributed as dist
+            self._buffers()
+            ops = []
+            for p, buf in self._recvbuf.items():
+                ops.append(dist.P2POp(dist.irecv, buf, p, group=self.pool.group))
+            for p, buf in self._sendbuf.items():
+                check(lib().spb_exchange_pack(self._h, _dptr(array.data), p, _dptr(buf), st))
+                ops.append(dist.P2POp(dist.isend, buf, p, group=self.pool.group))
+            reqs = dist.batch_isend_irecv(ops) if ops else []
+            check(lib().spb_exchange_local(self._h, _dptr(array.data), st))      # overlaps the NVLink transfers
+            for r in reqs:
+                r.wait()
+            for p, buf in self._recvbuf.items():
+                check(lib().spb_exchange_unpack(self._h, _dptr(array.data), p, _dptr(buf), st))
+        else:
+            check(lib().spb_exchange_local(self._h, _dptr(array.data), st))
+
+
+def make_exchange(array, periodic):
+    return arr_exchange_t(array.grid, array.num_exch, periodic)
+
+
+# ---- algs ----------------------------------------------------------------------------------------------------
+def transform_reduce(array, fn=FN_WAVESPEED, op=RED_MAX, gas=None, ivar=0):
+    """algs::transform_reduce(array, make_reduction(array, f, op)) incl. the cross-rank pool.reduce
+    (transform_reduce.h:171-190)."""
+    gas = gas or ideal_gas_t(1.4, 287.15)
+    out = C.c_double(0.0)
+    check(lib().spb_reduce(array.h, _dptr(array.data), int(op), int(fn), int(ivar), gas.gamma, gas.R,
+                           C.byref(out), _stream_ptr()))
+    return array.grid.group().reduce(out.value, op)
+
+
+# ---- time integration ---------------------------------------------------------------------------------------------
+class rk_t:
+    """Butcher table as exact ratios, explicit.h:27-116."""
+
+    def __init__(self, table, accum, dt, name):
+        self.table = [[Fraction(x) for x in row] for row in table]
+        self.accum = [Fraction(x) for x in accum]
+        self.dt = [Fraction(x) for x in dt]
+        self.name = name
+
+    def rhs_size(self):
+        return len(self.table[0])
+
+    def rows(self):
+        return len(self.table)
+
+
+F = Fraction
+rk2_t = rk_t([[0, 0], [F(1, 2), 0]], [0, 1], [0, F(1, 2)], "rk2")
+rk4_t = rk_t([[0, 0, 0, 0], [F(1, 2), 0, 0, 0], [0, F(1, 2), 0, 0], [0, 0, 1, 0]],
+             [F(1, 6), F(1, 3), F(1, 3), F(1, 6)], [0, F(1, 2), F(1, 2), 1], "rk4")
+ssprk3_t = rk_t([[0, 0, 0], [1, 0, 0], [F(1, 4), F(1, 4), 0]], [F(1, 6), F(1, 6), F(2, 3)], [0, 1, F(1, 2)], "ssprk3")
+ssprk34_t = rk_t([[0, 0, 0, 0], [F(1, 2), 0, 0, 0], [F(1, 2), F(1, 2), 0, 0], [F(1, 6), F(1, 6), F(1, 6), 0]],
+                 [F(1, 6), F(1, 6), F(1, 6), F(1, 2)], [0, F(1, 2), 1, F(1, 2)], "ssprk34")
+rk38r_t = rk_t([[0, 0, 0, 0], [F(1, 3), 0, 0, 0], [F(-1, 3), 1, 0, 0], [1, -1, 1, 0]],
+               [F(1, 8), F(3, 8), F(3, 8), F(1, 8)], [0, F(1, 3), F(2, 3), 1], "rk38r")
+
+
+class tspecial_rk3_t:
+    name = "ssprk3_opt"
+
+    @staticmethod
+    def rhs_size():
+        return 2
+
+
+ssprk3_opt = tspecial_rk3_t()
+
+
+def _ratio_diff_value(a, b):
+    """ratio_diff_t + coeff_value_t (advance.h:47-55): (d1*n0 - d0*n1)/(d0*d1) evaluated in double."""
+    n0, d0, n1, d1 = a.numerator, a.denominator, b.numerator, b.denominator
+    num, den = d1 * n0 - d0 * n1, d0 * d1
+    return float(num) / float(den) if num != 0 else 0.0
+
+
+class time_axis_t:
+    def __init__(self, t0, dt):
+        self.t, self.dt = float(t0), float(dt)
+
+    def time(self):
+        return self.t
+
+    def timestep(self):
+        return self.dt
+
+
+class integrator_data_t:
+    """integrator_data_t(q, rhs, scheme): one solution array and rhs_size() residual registers."""
+
+    def __init__(self, q, rhs, scheme):
+        self.solution_data = [q]
+        self.residual_data = [rhs] + [rhs.clone() for _ in range(scheme.rhs_size() - 1)]
+
+    def solution(self, i=0):
+        return self.solution_data[i]
+
+    def residual(self, i=0):
+        return self.residual_data[i]
+
+
+class state_transform_t:
+    """fluid_state::state_transform_t(cons_t(), gas): selects the fused prim<->cons update."""
+
+    def __init__(self, gas):
+        self.gas = gas
+
+
+class integrator_t:
+    """integrator_t(axis, scheme, data, rhs_calc, boundary_cond, trans).advance()
+    — the fused prim/cons path of advance.h:236-280 and the ssprk3_opt path of advance.h:359-402."""
+
+    def __init__(self, axis, scheme, data, rhs_calc, boundary_cond, trans):
+        self.axis, self.scheme, self.data = axis, scheme, data
+        self.rhs_calc, self.boundary_cond, self.trans = rhs_calc, boundary_cond, trans
+
+    def solution(self):
+        return self.data.solution(0)
+
+    def time(self):
+        return self.axis.t
+
+    def _update(self, prev_row, curr_row):
+        q = self.data.solution(0)
+        dt = self.axis.dt
+        nk = len(curr_row)
+        coeff = (C.c_double * nk)(*[_ratio_diff_value(c, p) * dt for c, p in zip(curr_row, prev_row)])
+        ks = (C.c_void_p * nk)(*[r.data.data_ptr() for r in self.data.residual_data[:nk]])
+        check(lib().spb_rk_update(q.h, _dptr(q.data), ks, nk, coeff, self.trans.gas.gamma, self.trans.gas.R, _stream_ptr()))
+
+    def advance(self):
+        ax, q, dt = self.axis, self.data.solution(0), self.axis.dt
+        gas = self.trans.gas
+        if isinstance(self.scheme, tspecial_rk3_t):
+            r0, r1 = self.data.residual(0), self.data.residual(1)
+            tc = [0.0, 1.0, 0.5]
+            self.rhs_calc(r0, q, ax.t + tc[0] * dt)
+            for stage in range(3):
+                check(lib().spb_ssprk3_stage(q.h, stage, _dptr(q.data), _dptr(r0.data), _dptr(r1.data), dt,
+                                             gas.gamma, gas.R, _stream_ptr()))
+                if stage < 2:
+                    self.boundary_cond(q, ax.t + tc[stage + 1] * dt)
+                    self.rhs_calc(r1, q, ax.t + tc[stage + 1] * dt)
+            ax.t += dt
+            self.boundary_cond(q, ax.t)
+            return
+        s = self.scheme
+        self.rhs_calc(self.data.residual(0), q, ax.t + float(s.dt[0]) * dt)
+        for i in range(1, s.rows()):
+            self._update(s.table[i - 1], s.table[i])
+            self.boundary_cond(q, ax.t + float(s.dt[i]) * dt)
+            self.rhs_calc(self.data.residual(i), q, ax.t + float(s.dt[i]) * dt)
+        self._update(s.table[s.rows() - 1], s.accum)
+        ax.t += dt
+        self.boundary_cond(q, ax.t)
+
+
+def launch_count():
+    return int(lib().spb_launch_count())
+
+
+def device_count():
+    return int(lib().spb_device_count())

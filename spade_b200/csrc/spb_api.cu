@@ -1,0 +1,89 @@
+// Grid handle, error string, utilities of the C ABI (include/spade_b200.h).
+#include "spb_common.cuh"
+#include <mutex>
+
+namespace spb
+{
+    static thread_local std::string t_error;
+    std::atomic<int64_t> g_launches{0};
+    void set_error(const std::string& msg) { t_error = msg; }
+
+    encode_tiled_fn get_encode_tiled()
+    {
+        static encode_tiled_fn fn = nullptr;
+        static std::once_flag once;
+        std::call_once(once, []
+        {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess
+                && qres == cudaDriverEntryPointSuccess)
+                fn = (encode_tiled_fn)p;
+        });
+        return fn;
+    }
+}
+
+extern "C"
+{
+    const char* spb_last_error(void) { return spb::t_error.c_str(); }
+    const char* spb_version(void) { return "spade_b200 0.1 (sm_100a)"; }
+    int64_t spb_launch_count(void) { return spb::g_launches.load(); }
+
+    int spb_device_count(void)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return n;
+    }
+
+    int spb_sync(void* stream)
+    {
+        SPB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        return 0;
+    }
+
+    // reference: src/grid/cartesian_grid.h:114-136 (dx = box.size/num_cell; inv_dx = 1.0/dx)
+    int spb_grid_create(spb_grid** out, const int nx[3], const int ng[3], int64_t nlb, const double* bbox_host)
+    {
+        if (!out || !nx || !ng || nlb < 0 || (nlb > 0 && !bbox_host)) { spb::set_error("spb_grid_create: bad argument"); return SPB_ERR_BAD_ARG; }
+        for (int d = 0; d < 3; ++d) if (nx[d] < 1 || ng[d] < 0) { spb::set_error("spb_grid_create: bad extents"); return SPB_ERR_BAD_ARG; }
+        if (spb_device_count() < 1) { spb::set_error("spb_grid_create: no CUDA device (this library has no CPU path)"); return SPB_ERR_NO_DEVICE; }
+        spb_grid* g = new spb_grid();
+        for (int d = 0; d < 3; ++d) { g->nx[d] = nx[d]; g->ng[d] = ng[d]; g->np[d] = nx[d] + 2*ng[d]; }
+        g->nlb = nlb;
+        g->block_stride = (int64_t)SPB_NVAR*g->np[0]*g->np[1]*g->np[2];
+        g->dx_host.resize(3*nlb); g->inv_dx_host.resize(3*nlb);
+        for (int64_t lb = 0; lb < nlb; ++lb)
+            for (int d = 0; d < 3; ++d)
+            {
+                const double size = bbox_host[6*lb + 2*d + 1] - bbox_host[6*lb + 2*d];
+                const double dx = size/nx[d];
+                g->dx_host[3*lb+d] = dx;
+                g->inv_dx_host[3*lb+d] = 1.0/dx;
+            }
+        g->inv_dx_dev = nullptr;
+        cudaError_t e = cudaGetDevice(&g->device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);
+        if (e == cudaSuccess && nlb > 0) e = cudaMalloc(&g->inv_dx_dev, sizeof(double)*3*nlb);
+        if (e == cudaSuccess && nlb > 0) e = cudaMemcpy(g->inv_dx_dev, g->inv_dx_host.data(), sizeof(double)*3*nlb, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { delete g; return spb::cuda_fail(e, "spb_grid_create", __FILE__, __LINE__); }
+        *out = g;
+        return 0;
+    }
+
+    void spb_grid_destroy(spb_grid* g)
+    {
+        if (!g) return;
+        if (g->inv_dx_dev) cudaFree(g->inv_dx_dev);
+        delete g;
+    }
+
+    int64_t spb_grid_array_size(const spb_grid* g) { return g->block_stride*g->nlb; }
+
+    // reference: src/core/mem_map.h:484-496
+    int64_t spb_grid_offset(const spb_grid* g, int v, int i, int j, int k, int64_t lb)
+    {
+        return v + (int64_t)SPB_NVAR*((i + g->ng[0]) + (int64_t)g->np[0]*((j + g->ng[1]) + (int64_t)g->np[1]*((k + g->ng[2]) + (int64_t)g->np[2]*lb)));
+    }
+}

@@ -1,0 +1,46 @@
+// Internal declarations shared by the translation units of libspade_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <atomic>
+#include "../../include/spade_b200.h"
+
+namespace spb
+{
+    void set_error(const std::string& msg);
+    extern std::atomic<int64_t> g_launches;
+
+    inline int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+    {
+        set_error(std::string(what) + ": " + cudaGetErrorString(e) + " (" + file + ":" + std::to_string(line) + ")");
+        return int(e);
+    }
+
+    // Resolved through the runtime (cudaGetDriverEntryPoint) so the library links without libcuda.
+    typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    encode_tiled_fn get_encode_tiled();
+}
+
+#define SPB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return spb::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
+#define SPB_LAUNCH_CHECK() do { spb::g_launches.fetch_add(1, std::memory_order_relaxed); cudaError_t e__ = cudaGetLastError(); \
+    if (e__ != cudaSuccess) return spb::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); } while (0)
+
+struct spb_grid
+{
+    int     nx[3];
+    int     ng[3];
+    int     np[3];              // padded extents nx + 2 ng
+    int64_t nlb;
+    int64_t block_stride;       // doubles per block = 5*np0*np1*np2
+    int     device;
+    std::vector<double> dx_host;      // [nlb][3]
+    std::vector<double> inv_dx_host;  // [nlb][3]
+    double* inv_dx_dev;               // [nlb][3]
+    int     num_sms;
+};

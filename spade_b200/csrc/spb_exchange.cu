@@ -1,0 +1,309 @@
+// Ghost-cell exchange: plan construction (host) and the pack / unpack / same-rank copy kernels.
+// Replaces get_exchg_config + arr_exchange_t::exchange of the reference
+// (src/grid/exchange_config.h:286-419, src/grid/get_transaction.h:11-97,
+//  src/grid/cartesian_blocks.h:76-103, src/grid/partition.h:27-84, src/grid/make_exchange.h:111-410).
+//
+// The reference finds the transaction of a buffer element with a 16-way tag search and div/mod per
+// element (make_exchange.h:14-63). Here the plan is flattened once on the host into work items
+// (transaction, element range); a CTA streams one item with contiguous runs along i.
+#include "spb_common.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+struct spb_trans
+{
+    int64_t f[16];   // tag, rank_send, rank_recv, glob_src, glob_dst, src.min[4], src.size[3], dst.min[4]
+    int64_t cells() const { return f[9]*f[10]*f[11]; }
+};
+
+namespace spb
+{
+    struct DevTrans
+    {
+        long long src_off;   // offset (doubles) of the source box origin in q, -1 if not local
+        long long dst_off;   // offset (doubles) of the destination box origin in q, -1 if not local
+        long long buf_off;   // offset (doubles) of this transaction inside its peer message
+        int bx, by, bz;
+    };
+    struct WorkItem { int trans; int begin; };   // element range [begin, begin + ITEM) of a transaction
+
+    constexpr int ITEM = 2048;                   // doubles per work item
+}
+
+struct spb_exchange
+{
+    int nx[3], ng[3], np[3];
+    int rank, nranks;
+    int64_t nlocal, first_block;
+    std::vector<spb_trans> send, recv;                 // sorted like the reference
+    std::vector<int64_t> send_rank_off, send_rank_cnt, recv_rank_off, recv_rank_cnt;
+    std::vector<int64_t> send_cells, recv_cells;       // per peer message size in cells
+    // device side (built lazily on the first device call)
+    bool dev_ready = false;
+    spb::DevTrans* d_send = nullptr; spb::DevTrans* d_recv = nullptr;
+    std::vector<std::vector<spb::WorkItem>> items_send, items_recv;   // per peer
+    std::vector<spb::WorkItem*> d_items_send, d_items_recv;
+};
+
+namespace spb
+{
+    // reference src/grid/partition.h:40-71
+    static void partition_blocks(int64_t nglob, int nranks, std::vector<int64_t>& g2r, std::vector<int64_t>& g2l)
+    {
+        g2r.assign(nglob, 0); g2l.assign(nglob, 0);
+        std::vector<int64_t> partial(nranks, 0);
+        int64_t cur = 0, counter = 0;
+        const int64_t per = nglob/nranks, extra = nglob - per*nranks;
+        for (int64_t lb = 0; lb < nglob; ++lb)
+        {
+            g2r[lb] = cur; g2l[lb] = partial[cur]++;
+            ++counter;
+            const int64_t add = (extra > 0 && cur < extra) ? 1 : 0;
+            if (counter == per + add) { counter = 0; cur = (cur + 1) % nranks; }
+        }
+    }
+
+    static void finish_plan(spb_exchange* e)
+    {
+        // stable sort by (peer asc, tag desc): reference src/grid/exchange_config.h:379-397
+        std::stable_sort(e->send.begin(), e->send.end(), [](const spb_trans& a, const spb_trans& b)
+            { if (a.f[2] != b.f[2]) return a.f[2] < b.f[2]; if (a.f[0] != b.f[0]) return a.f[0] > b.f[0]; return a.cells() < b.cells(); });
+        std::stable_sort(e->recv.begin(), e->recv.end(), [](const spb_trans& a, const spb_trans& b)
+            { if (a.f[1] != b.f[1]) return a.f[1] < b.f[1]; if (a.f[0] != b.f[0]) return a.f[0] > b.f[0]; return a.cells() < b.cells(); });
+        const int n = e->nranks;
+        e->send_rank_off.assign(n, 0); e->send_rank_cnt.assign(n, 0); e->recv_rank_off.assign(n, 0); e->recv_rank_cnt.assign(n, 0);
+        e->send_cells.assign(n, 0); e->recv_cells.assign(n, 0);
+        for (const auto& t: e->send) { e->send_rank_cnt[t.f[2]]++; e->send_cells[t.f[2]] += t.cells(); }
+        for (const auto& t: e->recv) { e->recv_rank_cnt[t.f[1]]++; e->recv_cells[t.f[1]] += t.cells(); }
+        int64_t so = 0, ro = 0;
+        for (int p = 0; p < n; ++p) { e->send_rank_off[p] = so; so += e->send_rank_cnt[p]; e->recv_rank_off[p] = ro; ro += e->recv_rank_cnt[p]; }
+    }
+
+    static long long box_origin(const spb_exchange* e, const int64_t* mn)   // mn = {i, j, k, lb}
+    {
+        if (mn[3] < 0) return -1;
+        return 5ll*((mn[0] + e->ng[0]) + (long long)e->np[0]*((mn[1] + e->ng[1]) + (long long)e->np[1]*((mn[2] + e->ng[2]) + (long long)e->np[2]*mn[3])));
+    }
+
+    static int build_device(spb_exchange* e)
+    {
+        if (e->dev_ready) return 0;
+        const int n = e->nranks;
+        auto build = [&](const std::vector<spb_trans>& list, const std::vector<int64_t>& roff, const std::vector<int64_t>& rcnt, bool peer_is_recv,
+                         DevTrans** d_list, std::vector<std::vector<WorkItem>>& items, std::vector<WorkItem*>& d_items) -> int
+        {
+            std::vector<DevTrans> h(list.size());
+            items.assign(n, {}); d_items.assign(n, nullptr);
+            for (int p = 0; p < n; ++p)
+            {
+                long long boff = 0;
+                for (int64_t t = roff[p]; t < roff[p] + rcnt[p]; ++t)
+                {
+                    const spb_trans& tr = list[t];
+                    DevTrans& d = h[t];
+                    d.src_off = box_origin(e, &tr.f[5]);
+                    d.dst_off = box_origin(e, &tr.f[12]);
+                    d.buf_off = boff;
+                    d.bx = (int)tr.f[9]; d.by = (int)tr.f[10]; d.bz = (int)tr.f[11];
+                    const long long nel = 5ll*tr.cells();
+                    boff += nel;
+                    for (long long b = 0; b < nel; b += ITEM) items[p].push_back(WorkItem{(int)t, (int)b});
+                }
+                if (!items[p].empty())
+                {
+                    SPB_CUDA(cudaMalloc((void**)&d_items[p], sizeof(WorkItem)*items[p].size()));
+                    SPB_CUDA(cudaMemcpy(d_items[p], items[p].data(), sizeof(WorkItem)*items[p].size(), cudaMemcpyHostToDevice));
+                }
+            }
+            (void)peer_is_recv;
+            if (!h.empty())
+            {
+                SPB_CUDA(cudaMalloc((void**)d_list, sizeof(DevTrans)*h.size()));
+                SPB_CUDA(cudaMemcpy(*d_list, h.data(), sizeof(DevTrans)*h.size(), cudaMemcpyHostToDevice));
+            }
+            return 0;
+        };
+        int rc = build(e->send, e->send_rank_off, e->send_rank_cnt, true, &e->d_send, e->items_send, e->d_items_send);
+        if (rc) return rc;
+        rc = build(e->recv, e->recv_rank_off, e->recv_rank_cnt, false, &e->d_recv, e->items_recv, e->d_items_recv);
+        if (rc) return rc;
+        e->dev_ready = true;
+        return 0;
+    }
+
+    // MODE 0: q(dst) = q(src)   MODE 1: buf = q(src)   MODE 2: q(dst) = buf
+    template <int MODE>
+    __global__ void __launch_bounds__(256) exchange_kernel(double* q, const double* qsrc, double* __restrict__ buf,
+        const double* __restrict__ bufsrc, const DevTrans* __restrict__ trans, const WorkItem* __restrict__ items, int np0, int np1)
+    {
+        const WorkItem it = items[blockIdx.x];
+        const DevTrans tr = trans[it.trans];
+        const int nel = 5*tr.bx*tr.by*tr.bz;
+        const int row = 5*tr.bx;                       // contiguous doubles along i
+        const long long pitch_j = 5ll*np0, pitch_k = 5ll*np0*np1;
+        const int end = min(it.begin + ITEM, nel);
+        for (int el = it.begin + threadIdx.x; el < end; el += 256)
+        {
+            const int r = el / row, c = el - r*row;
+            const int iz = r / tr.by, iy = r - iz*tr.by;
+            const long long rel = c + iy*pitch_j + iz*pitch_k;
+            if (MODE == 0) q[tr.dst_off + rel] = qsrc[tr.src_off + rel];
+            if (MODE == 1) buf[tr.buf_off + el] = qsrc[tr.src_off + rel];
+            if (MODE == 2) q[tr.dst_off + rel] = bufsrc[tr.buf_off + el];
+        }
+    }
+}
+
+extern "C"
+{
+    int spb_exchange_create(spb_exchange** out, const int nb[3], const int nx[3], const int ng[3], const int periodic[3], int rank, int nranks)
+    {
+        using namespace spb;
+        if (!out || !nb || !nx || !ng || !periodic || nranks < 1 || rank < 0 || rank >= nranks) { set_error("spb_exchange_create: bad argument"); return SPB_ERR_BAD_ARG; }
+        spb_exchange* e = new spb_exchange();
+        for (int d = 0; d < 3; ++d) { e->nx[d] = nx[d]; e->ng[d] = ng[d]; e->np[d] = nx[d] + 2*ng[d]; }
+        e->rank = rank; e->nranks = nranks;
+        const int64_t nglob = (int64_t)nb[0]*nb[1]*nb[2];
+        std::vector<int64_t> g2r, g2l;
+        partition_blocks(nglob, nranks, g2r, g2l);
+        e->nlocal = 0; e->first_block = -1;
+        for (int64_t lb = 0; lb < nglob; ++lb) if (g2r[lb] == rank) { if (e->first_block < 0) e->first_block = lb; e->nlocal++; }
+        if (e->first_block < 0) e->first_block = 0;
+        // transactions in (global block asc, neighbour-table order): reference exchange_config.h:331-363
+        for (int64_t lb = 0; lb < nglob; ++lb)
+        {
+            const int blk[3] = {(int)(lb % nb[0]), (int)((lb/nb[0]) % nb[1]), (int)(lb/((int64_t)nb[0]*nb[1]))};
+            for (int dk = -1; dk <= 1; ++dk) for (int dj = -1; dj <= 1; ++dj) for (int di = -1; di <= 1; ++di)
+            {
+                if (di == 0 && dj == 0 && dk == 0) continue;
+                const int edge[3] = {di, dj, dk};
+                int nbr[3]; bool ignore = false;
+                for (int d = 0; d < 3; ++d)
+                {
+                    nbr[d] = blk[d] + edge[d];                 // periodic wrap always applied, cartesian_blocks.h:84-92
+                    if (nbr[d] < 0) nbr[d] += nb[d];
+                    if (nbr[d] >= nb[d]) nbr[d] -= nb[d];
+                    const bool is_min = blk[d] == 0, is_max = blk[d] == nb[d] - 1;
+                    if (!periodic[d] && ((is_min && edge[d] == -1) || (is_max && edge[d] == 1))) ignore = true;   // exchange_config.h:336-342
+                }
+                if (ignore) continue;
+                const int64_t lbn = nbr[0] + (int64_t)nb[0]*(nbr[1] + (int64_t)nb[1]*nbr[2]);
+                if (g2r[lb] != rank && g2r[lbn] != rank) continue;
+                spb_trans t;
+                const int dsum = std::abs(di) + std::abs(dj) + std::abs(dk);
+                int tag = dsum == 1 ? 3 : (dsum == 2 ? 12 : 16);  // get_transaction.h:33-51
+                for (int d = 0; d < 3; ++d)
+                {
+                    if (dsum == 1 && edge[d] != 0) tag -= d;
+                    if (dsum == 2 && edge[d] == 0) tag -= d;
+                }
+                t.f[0] = tag; t.f[1] = g2r[lb]; t.f[2] = g2r[lbn]; t.f[3] = lb; t.f[4] = lbn;
+                for (int d = 0; d < 3; ++d)                       // get_transaction.h:54-86
+                {
+                    int smin, smax, dmin;
+                    if (edge[d] == -1)     { smin = 0;             smax = ng[d]; dmin = nx[d]; }
+                    else if (edge[d] == 0) { smin = 0;             smax = nx[d]; dmin = 0; }
+                    else                   { smin = nx[d] - ng[d]; smax = nx[d]; dmin = -ng[d]; }
+                    t.f[5+d] = smin; t.f[9+d] = smax - smin; t.f[12+d] = dmin;
+                }
+                t.f[8]  = g2r[lb]  == rank ? g2l[lb]  : -1;       // partition.h:107-111 (to_local of a foreign block)
+                t.f[15] = g2r[lbn] == rank ? g2l[lbn] : -1;
+                if (g2r[lb]  == rank) e->send.push_back(t);
+                if (g2r[lbn] == rank) e->recv.push_back(t);
+            }
+        }
+        finish_plan(e);
+        *out = e;
+        return 0;
+    }
+
+    int spb_exchange_create_from_tables(spb_exchange** out, const int nx[3], const int ng[3], int rank, int nranks,
+                                        const int64_t* send, int64_t nsend, const int64_t* recv, int64_t nrecv)
+    {
+        using namespace spb;
+        if (!out || !nx || !ng || nranks < 1 || rank < 0 || rank >= nranks || nsend < 0 || nrecv < 0) { set_error("spb_exchange_create_from_tables: bad argument"); return SPB_ERR_BAD_ARG; }
+        spb_exchange* e = new spb_exchange();
+        for (int d = 0; d < 3; ++d) { e->nx[d] = nx[d]; e->ng[d] = ng[d]; e->np[d] = nx[d] + 2*ng[d]; }
+        e->rank = rank; e->nranks = nranks; e->nlocal = -1; e->first_block = -1;
+        e->send.resize(nsend); e->recv.resize(nrecv);
+        for (int64_t i = 0; i < nsend; ++i) std::copy(send + 16*i, send + 16*i + 16, e->send[i].f);
+        for (int64_t i = 0; i < nrecv; ++i) std::copy(recv + 16*i, recv + 16*i + 16, e->recv[i].f);
+        finish_plan(e);
+        *out = e;
+        return 0;
+    }
+
+    void spb_exchange_destroy(spb_exchange* e)
+    {
+        if (!e) return;
+        if (e->d_send) cudaFree(e->d_send);
+        if (e->d_recv) cudaFree(e->d_recv);
+        for (auto p: e->d_items_send) if (p) cudaFree(p);
+        for (auto p: e->d_items_recv) if (p) cudaFree(p);
+        delete e;
+    }
+
+    int64_t spb_exchange_num_send(const spb_exchange* e) { return (int64_t)e->send.size(); }
+    int64_t spb_exchange_num_recv(const spb_exchange* e) { return (int64_t)e->recv.size(); }
+    int64_t spb_exchange_local_blocks(const spb_exchange* e) { return e->nlocal; }
+    int64_t spb_exchange_first_block(const spb_exchange* e) { return e->first_block; }
+    int64_t spb_exchange_send_cells(const spb_exchange* e, int peer) { return (peer < 0 || peer >= e->nranks) ? -1 : e->send_cells[peer]; }
+    int64_t spb_exchange_recv_cells(const spb_exchange* e, int peer) { return (peer < 0 || peer >= e->nranks) ? -1 : e->recv_cells[peer]; }
+
+    int spb_exchange_tables(const spb_exchange* e, int64_t* send, int64_t* recv, int64_t* offs)
+    {
+        if (!e) { spb::set_error("spb_exchange_tables: null plan"); return SPB_ERR_BAD_ARG; }
+        if (send) for (size_t i = 0; i < e->send.size(); ++i) std::copy(e->send[i].f, e->send[i].f + 16, send + 16*i);
+        if (recv) for (size_t i = 0; i < e->recv.size(); ++i) std::copy(e->recv[i].f, e->recv[i].f + 16, recv + 16*i);
+        if (offs) for (int p = 0; p < e->nranks; ++p)
+        {
+            offs[6*p+0] = e->send_cells[p];    offs[6*p+1] = e->recv_cells[p];
+            offs[6*p+2] = e->send_rank_off[p]; offs[6*p+3] = e->send_rank_cnt[p];
+            offs[6*p+4] = e->recv_rank_off[p]; offs[6*p+5] = e->recv_rank_cnt[p];
+        }
+        return 0;
+    }
+
+    int spb_exchange_local(spb_exchange* e, double* q_dev, void* stream)
+    {
+        using namespace spb;
+        if (!e || !q_dev) { set_error("spb_exchange_local: bad argument"); return SPB_ERR_BAD_ARG; }
+        int rc = build_device(e); if (rc) return rc;
+        const auto& items = e->items_send[e->rank];
+        if (items.empty()) return 0;
+        exchange_kernel<0><<<(unsigned)items.size(), 256, 0, (cudaStream_t)stream>>>(q_dev, q_dev, nullptr, nullptr, e->d_send, e->d_items_send[e->rank], e->np[0], e->np[1]);
+        SPB_LAUNCH_CHECK();
+        return 0;
+    }
+
+    int spb_exchange_pack(spb_exchange* e, const double* q_dev, int peer, double* sendbuf_dev, void* stream)
+    {
+        using namespace spb;
+        if (!e || !q_dev || peer < 0 || peer >= e->nranks) { set_error("spb_exchange_pack: bad argument"); return SPB_ERR_BAD_ARG; }
+        int rc = build_device(e); if (rc) return rc;
+        const auto& items = e->items_send[peer];
+        if (items.empty()) return 0;
+        if (!sendbuf_dev) { set_error("spb_exchange_pack: null buffer"); return SPB_ERR_BAD_ARG; }
+        exchange_kernel<1><<<(unsigned)items.size(), 256, 0, (cudaStream_t)stream>>>(nullptr, q_dev, sendbuf_dev, nullptr, e->d_send, e->d_items_send[peer], e->np[0], e->np[1]);
+        SPB_LAUNCH_CHECK();
+        return 0;
+    }
+
+    int spb_exchange_pack_peer(spb_exchange* e, const double* q_dev, int peer, double* peer_recvbuf_dev, void* stream)
+    {
+        return spb_exchange_pack(e, q_dev, peer, peer_recvbuf_dev, stream);
+    }
+
+    int spb_exchange_unpack(spb_exchange* e, double* q_dev, int peer, const double* recvbuf_dev, void* stream)
+    {
+        using namespace spb;
+        if (!e || !q_dev || peer < 0 || peer >= e->nranks) { set_error("spb_exchange_unpack: bad argument"); return SPB_ERR_BAD_ARG; }
+        int rc = build_device(e); if (rc) return rc;
+        const auto& items = e->items_recv[peer];
+        if (items.empty()) return 0;
+        if (!recvbuf_dev) { set_error("spb_exchange_unpack: null buffer"); return SPB_ERR_BAD_ARG; }
+        exchange_kernel<2><<<(unsigned)items.size(), 256, 0, (cudaStream_t)stream>>>(q_dev, nullptr, nullptr, recvbuf_dev, e->d_recv, e->d_items_recv[peer], e->np[0], e->np[1]);
+        SPB_LAUNCH_CHECK();
+        return 0;
+    }
+}

@@ -1,0 +1,231 @@
+// Face-flux device functions of the RHS kernel: the closed set of SPADE flux functors, written
+// for one face of compile-time direction D with every metric term of coords::identity folded away.
+//
+// Reference semantics (file:line in /root/reference/src):
+//   totani_lr                 navier-stokes/convective.h:68-93
+//   cent_keep<4>              navier-stokes/convective.h:118-184, core/finite_diff.h:26-34
+//   fweno_t (enable_smooth)   navier-stokes/convective.h:355-496
+//   hybrid_scheme_t           navier-stokes/hybrid_scheme.h:29-45
+//   ducros_t                  navier-stokes/state_sensor.h:32-42
+//   visc_lr + constant_viscosity_t   navier-stokes/viscous.h:39-80, viscous_laws.h:77-99
+//   face value / face gradient       omni/infos/info_value.h:30-40, info_gradient.h:22-87
+// The arithmetic is re-associated (each face once, unit normals folded, e = R T/(gamma-1) instead
+// of p/(rho (gamma-1)), only the stress row the face needs) — results agree with the reference to
+// round-off (gate: 1e-12 relative L2, tests/test_flux_div_gpu.py), not bit-for-bit.
+#pragma once
+#include "spb_common.cuh"
+
+namespace spb
+{
+    struct FluxParams
+    {
+        double gamma, R, gm1, cv;     // cv = R/(gamma-1)
+        double mu, beta, two_mu, kappa;
+        double eps;
+        int    blend;                 // SPB_BLEND_*
+    };
+
+    // q_v at offset (sD along D, sT1 along (D+1)%3, sT2 along (D+2)%3) from the face's right cell
+    template <int D, class A>
+    __device__ __forceinline__ double qrel(const A& a, int v, int sD, int sT1, int sT2)
+    {
+        constexpr int T1 = (D + 1) % 3, T2 = (D + 2) % 3;
+        int o[3];
+        o[D] = sD; o[T1] = sT1; o[T2] = sT2;
+        return a(v, o[0], o[1], o[2]);
+    }
+
+    // ---- convective::totani_lr -------------------------------------------------------------
+    template <int D>
+    __device__ __forceinline__ void flux_totani(const FluxParams& P, const double (&qL)[5], const double (&qR)[5], double (&F)[5])
+    {
+        const double rhoL = qL[0]/(P.R*qL[1]);
+        const double rhoR = qR[0]/(P.R*qR[1]);
+        const double unL = qL[2+D], unR = qR[2+D];
+        const double C = (rhoL + rhoR)*(unL + unR);                 // 4c
+        double S = P.cv*(qL[1] + qR[1]);                            // e_L + e_R
+        S = fma(qL[2], qR[2], S); S = fma(qL[3], qR[3], S); S = fma(qL[4], qR[4], S);
+        const double C8 = 0.125*C;
+        F[0] = 0.25*C;
+        F[1] = fma(C8, S, 0.5*fma(unL, qR[0], unR*qL[0]));
+        F[2] = C8*(qL[2] + qR[2]);
+        F[3] = C8*(qL[3] + qR[3]);
+        F[4] = C8*(qL[4] + qR[4]);
+        F[2+D] = fma(0.5, qL[0] + qR[0], F[2+D]);
+    }
+
+    // ---- convective::cent_keep<4>: cells c0..c3 at half-offsets -3,-1,+1,+3 -------------------
+    template <int D>
+    __device__ __forceinline__ void flux_cent_keep4(const FluxParams& P, const double (&c0)[5], const double (&c1)[5],
+                                                    const double (&c2)[5], const double (&c3)[5], double (&F)[5])
+    {
+        const double a1 = 2.0/3.0, a2 = -1.0/12.0;
+        const double* q[4] = {c0, c1, c2, c3};
+        double rho[4], eng[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) { rho[i] = q[i][0]/(P.R*q[i][1]); eng[i] = P.cv*q[i][1]; }
+        double cc = 0.0, m[3] = {0.0, 0.0, 0.0}, g = 0.0, k = 0.0, ie = 0.0, pd = 0.0;
+        auto pair = [&](const double a, const int i0, const int i1)
+        {
+            const double c_loc = a*0.25*(rho[i0] + rho[i1])*(q[i0][2+D] + q[i1][2+D]);
+            cc += c_loc;
+            #pragma unroll
+            for (int d = 0; d < 3; ++d) m[d] = fma(c_loc, 0.5*(q[i0][2+d] + q[i1][2+d]), m[d]);
+            g  = fma(a, 0.5*(q[i0][0] + q[i1][0]), g);
+            k  = fma(0.5*c_loc, fma(q[i0][2], q[i1][2], fma(q[i0][3], q[i1][3], q[i0][4]*q[i1][4])), k);
+            ie = fma(c_loc, 0.5*(eng[i0] + eng[i1]), ie);
+            pd = fma(a, 0.5*fma(q[i0][2+D], q[i1][0], q[i1][2+D]*q[i0][0]), pd);
+        };
+        pair(a1, 1, 2);
+        pair(a2, 1, 3);
+        pair(a2, 0, 2);
+        F[0] = 2.0*cc;
+        F[1] = 2.0*(k + ie + pd);
+        F[2] = 2.0*m[0]; F[3] = 2.0*m[1]; F[4] = 2.0*m[2];
+        F[2+D] = fma(2.0, g, F[2+D]);
+    }
+
+    // ---- convective::fweno_t ---------------------------------------------------------------------
+    __device__ __forceinline__ double fweno_apply(const double (&f)[4], const double (&d)[4])
+    {
+        const double f0u = f[0] + d[0];
+        const double f1u = f[1] + d[1], f1d = f[1] - d[1];
+        const double f2u = f[2] + d[2], f2d = f[2] - d[2];
+        const double f3d = f[3] - d[3];
+        const double r0 = fma(1.5, f1u, -0.5*f0u);
+        const double r1 = 0.5*(f1u + f2u);
+        const double r2 = 0.5*(f1d + f2d);
+        const double r3 = fma(1.5, f2d, -0.5*f3d);
+        const double eps = 1e-16;
+        double a0 = f0u - f1u, a1 = f1u - f2u, a2 = f1d - f2d, a3 = f2d - f3d;
+        a0 = fma(a0, a0, eps); a0 *= a0;
+        a1 = fma(a1, a1, eps); a1 *= a1;
+        a2 = fma(a2, a2, eps); a2 *= a2;
+        a3 = fma(a3, a3, eps); a3 *= a3;
+        const double w0 = a1/(a0 + a0 + a1);
+        const double w3 = a2/(a3 + a3 + a2);
+        // w0 r0 + (1-w0) r1 + (1-w3) r2 + w3 r3
+        return fma(w0, r0 - r1, r1) + fma(w3, r3 - r2, r2);
+    }
+
+    template <int D>
+    __device__ __forceinline__ void flux_fweno(const FluxParams& P, const double (&c0)[5], const double (&c1)[5],
+                                               const double (&c2)[5], const double (&c3)[5], double (&F)[5])
+    {
+        const double* q[4] = {c0, c1, c2, c3};
+        double rho[4], hsr[4], a[4], ke[4], fm[4], fl[4], ds[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            a[i]   = P.R*q[i][1];
+            const double u2 = fma(q[i][2], q[i][2], fma(q[i][3], q[i][3], q[i][4]*q[i][4]));
+            ke[i]  = 0.5*u2;
+            rho[i] = q[i][0]/a[i];
+            hsr[i] = 0.5*rho[i]*(sqrt(u2) + sqrt(a[i]*P.gamma));
+            fm[i]  = 0.5*rho[i]*q[i][2+D];
+        }
+        // continuity
+        F[0] = fweno_apply(fm, hsr);
+        // energy
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const double engy = ke[i] + a[i]/P.gm1;
+            fl[i] = fm[i]*(engy + a[i]);
+            ds[i] = hsr[i]*engy;
+        }
+        F[1] = fweno_apply(fl, ds);
+        // momentum
+        #pragma unroll
+        for (int dr = 0; dr < 3; ++dr)
+        {
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                fl[i] = fm[i]*q[i][2+dr];
+                if (dr == D) fl[i] = fma(0.5, q[i][0], fl[i]);
+                ds[i] = hsr[i]*q[i][2+dr];
+            }
+            F[2+dr] = fweno_apply(fl, ds);
+        }
+    }
+
+    // ---- the composed functor on the lower face (direction D) of the cell the accessor is centred on
+    template <int CONV, int DISS, int VISC, int D, class A>
+    __device__ __forceinline__ void face_flux(const A& a, const FluxParams& P, const double (&invdx)[3], double (&F)[5])
+    {
+        constexpr int T1 = (D + 1) % 3, T2 = (D + 2) % 3;
+        constexpr bool WIDE = (CONV == SPB_CONV_CENT_KEEP4) || (CONV == SPB_CONV_FWENO) || (DISS != SPB_DISS_NONE);
+        double qL[5], qR[5], qLL[5], qRR[5];
+        #pragma unroll
+        for (int v = 0; v < 5; ++v) { qL[v] = qrel<D>(a, v, -1, 0, 0); qR[v] = qrel<D>(a, v, 0, 0, 0); }
+        if (WIDE)
+        {
+            #pragma unroll
+            for (int v = 0; v < 5; ++v) { qLL[v] = qrel<D>(a, v, -2, 0, 0); qRR[v] = qrel<D>(a, v, 1, 0, 0); }
+        }
+        #pragma unroll
+        for (int v = 0; v < 5; ++v) F[v] = 0.0;
+
+        if (CONV == SPB_CONV_TOTANI)     flux_totani<D>(P, qL, qR, F);
+        if (CONV == SPB_CONV_CENT_KEEP4) flux_cent_keep4<D>(P, qLL, qL, qR, qRR, F);
+        if (CONV == SPB_CONV_FWENO)      flux_fweno<D>(P, qLL, qL, qR, qRR, F);
+
+        if (VISC || DISS)
+        {
+            // face gradient g[dir][comp] of the velocity; gT = normal derivative of T
+            double g[3][3];
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) g[D][c] = (qR[2+c] - qL[2+c])*invdx[D];
+            const double gT = (qR[1] - qL[1])*invdx[D];
+            const double c1 = 0.25*invdx[T1], c2 = 0.25*invdx[T2];
+            #pragma unroll
+            for (int c = 0; c < 3; ++c)
+            {
+                const bool need1 = DISS || (c == T1) || (c == D);
+                const bool need2 = DISS || (c == T2) || (c == D);
+                g[T1][c] = 0.0; g[T2][c] = 0.0;
+                if (need1)
+                    g[T1][c] = c1*((qrel<D>(a, 2+c, -1,  1, 0) - qrel<D>(a, 2+c, -1, -1, 0))
+                                 + (qrel<D>(a, 2+c,  0,  1, 0) - qrel<D>(a, 2+c,  0, -1, 0)));
+                if (need2)
+                    g[T2][c] = c2*((qrel<D>(a, 2+c, -1, 0,  1) - qrel<D>(a, 2+c, -1, 0, -1))
+                                 + (qrel<D>(a, 2+c,  0, 0,  1) - qrel<D>(a, 2+c,  0, 0, -1)));
+            }
+            const double div = g[0][0] + g[1][1] + g[2][2];
+            if (DISS)
+            {
+                const double th2 = div*div;
+                const double w0 = g[1][2] - g[2][1];
+                const double w1 = g[2][0] - g[0][2];
+                const double w2 = g[0][1] - g[1][0];
+                const double vort = fma(w0, w0, fma(w1, w1, w2*w2));
+                const double alpha = th2/(th2 + vort + P.eps);
+                double F1[5];
+                flux_fweno<D>(P, qLL, qL, qR, qRR, F1);
+                const double coeff0 = (P.blend == SPB_BLEND_FULL_FLUX) ? (1.0 - alpha) : 1.0;
+                #pragma unroll
+                for (int v = 0; v < 5; ++v) F[v] = fma(alpha, F1[v], coeff0*F[v]);
+            }
+            if (VISC)
+            {
+                const double tDD = fma(P.two_mu, g[D][D], P.beta*div);
+                const double tD1 = P.mu*(g[D][T1] + g[T1][D]);
+                const double tD2 = P.mu*(g[D][T2] + g[T2][D]);
+                const double ufD = 0.5*(qL[2+D]  + qR[2+D]);
+                const double uf1 = 0.5*(qL[2+T1] + qR[2+T1]);
+                const double uf2 = 0.5*(qL[2+T2] + qR[2+T2]);
+                const double h = fma(ufD, tDD, fma(uf1, tD1, fma(uf2, tD2, P.kappa*gT)));
+                F[1]    -= h;
+                F[2+D]  -= tDD;
+                F[2+T1] -= tD1;
+                F[2+T2] -= tD2;
+            }
+        }
+    }
+
+    template <int CONV, int DISS> struct stencil_halo
+    {
+        static constexpr int value = ((CONV == SPB_CONV_CENT_KEEP4) || (CONV == SPB_CONV_FWENO) || (DISS != SPB_DISS_NONE)) ? 2 : 1;
+    };
+}

@@ -1,0 +1,127 @@
+"""Parity of the exchange kernels (bit-exact), the fused RK stage update, the reductions and short RK
+trajectories against the oracle (reference src/grid/make_exchange.h:111-410,
+src/time-integration/advance.h:57-102,236-402, src/algs/transform_reduce.h:53-191)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import GAMMA, RGAS, make_state, oracle_cfg, product_flux, product_setup, rel_l2, zero_ghosts, interior
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("periodic", [(1, 1, 1), (1, 0, 1), (0, 0, 0)])
+@pytest.mark.parametrize("nb,n", [((2, 2, 2), (16, 16, 16)), ((1, 3, 2), (8, 4, 12)), ((1, 1, 1), (32, 32, 32))])
+def test_single_rank_exchange_bit_exact(periodic, nb, n):
+    from oracle import port
+    ng = 2
+    q = zero_ghosts(make_state(nb, n, ng, seed=2), ng)
+    cfg = oracle_cfg(nb, n, ng, periodic=periodic)
+    want = port.exchange(cfg, q.ravel()).reshape(q.shape)
+    sp, blocks, grid = product_setup(nb, n, ng)
+    qa = sp.grid_array.from_host(grid, q)
+    sp.make_exchange(qa, periodic).exchange(qa)
+    assert np.array_equal(qa.to_host(), want)
+
+
+@pytest.mark.parametrize("size", [2, 3])
+def test_pack_unpack_between_simulated_ranks_bit_exact(size):
+    """All ranks of a `size`-rank partition are played on one GPU: pack on the sender, hand the message
+    buffer over, unpack on the receiver; the union must equal the oracle's global exchange."""
+    from oracle import port
+    import torch
+    import spade_b200.api as sp
+    nb, n, ng = (2, 2, 3), (8, 8, 8), 2
+    periodic = (1, 1, 0)
+    q = zero_ghosts(make_state(nb, n, ng, seed=4), ng)
+    cfg = oracle_cfg(nb, n, ng, periodic=periodic)
+    want = port.exchange(cfg, q.ravel()).reshape(q.shape)
+    ranks = []
+    for r in range(size):
+        _, blocks, grid = product_setup(nb, n, ng, rank=r, size=size)
+        lo = grid.first_block
+        qa = sp.grid_array.from_host(grid, q[lo:lo + grid.num_local_blocks])
+        ranks.append((grid, qa, sp.make_exchange(qa, periodic)))
+    lib = sp.lib()
+    bufs = {}
+    for r, (grid, qa, ex) in enumerate(ranks):
+        for p in range(size):
+            if p != r and ex.send_cells[p]:
+                b = torch.empty(5 * ex.send_cells[p], dtype=torch.float64, device="cuda")
+                sp.check(lib.spb_exchange_pack(ex._h, C.c_void_p(qa.data.data_ptr()), p, C.c_void_p(b.data_ptr()), None))
+                bufs[(r, p)] = b
+        sp.check(lib.spb_exchange_local(ex._h, C.c_void_p(qa.data.data_ptr()), None))
+    for r, (grid, qa, ex) in enumerate(ranks):
+        for p in range(size):
+            if p != r and ex.recv_cells[p]:
+                assert ex.recv_cells[p] == ranks[p][2].send_cells[r]
+                sp.check(lib.spb_exchange_unpack(ex._h, C.c_void_p(qa.data.data_ptr()), p, C.c_void_p(bufs[(p, r)].data_ptr()), None))
+    torch.cuda.synchronize()
+    got = np.concatenate([qa.to_host() for _, qa, _ in ranks], axis=0)
+    assert np.array_equal(got, want)
+
+
+def test_reductions():
+    from oracle import port
+    nb, n, ng = (2, 1, 2), (16, 8, 12), 2
+    q = make_state(nb, n, ng, seed=9)
+    cfg = oracle_cfg(nb, n, ng)
+    sp, blocks, grid = product_setup(nb, n, ng)
+    qa = sp.grid_array.from_host(grid, q)
+    gas = sp.ideal_gas_t(GAMMA, RGAS)
+    assert sp.transform_reduce(qa, sp.FN_WAVESPEED, sp.RED_MAX, gas) == pytest.approx(port.reduce_umax(cfg, q.ravel()), rel=1e-15)
+    qi = interior(q, ng)
+    assert sp.transform_reduce(qa, sp.FN_VAR, sp.RED_MAX, gas, ivar=3) == qi[..., 3].max()
+    assert sp.transform_reduce(qa, sp.FN_VAR, sp.RED_SUM, gas, ivar=0) == pytest.approx(qi[..., 0].sum(), rel=1e-13)
+    assert sp.transform_reduce(qa, sp.FN_ABSVAR, sp.RED_MAX, gas, ivar=4) == np.abs(qi[..., 4]).max()
+
+
+def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1)):
+    sp, blocks, grid = product_setup(nb, n, ng)
+    gas = sp.ideal_gas_t(GAMMA, RGAS)
+    qa = sp.grid_array.from_host(grid, q)
+    ra = sp.grid_array(grid, 0.0)
+    ex = sp.make_exchange(qa, periodic)
+    flux = sp.flux_desc(product_flux(scheme))
+    alg = {0: sp.rk4_t, 1: sp.ssprk3_opt, 2: sp.ssprk3_t, 3: sp.rk2_t}[integ]
+    data = sp.integrator_data_t(qa, ra, alg)
+    ti = sp.integrator_t(sp.time_axis_t(0.0, dt), alg, data,
+                         lambda r, qq, t: sp.flux_div(qq, r, flux, sp.overwrite),
+                         lambda qq, t: ex.exchange(qq), sp.state_transform_t(gas))
+    for _ in range(nsteps):
+        ti.advance()
+    return ti.solution().to_host()
+
+
+@pytest.mark.parametrize("integ", [0, 1, 2, 3])
+def test_rk_trajectory_matches_oracle(integ):
+    from oracle import port
+    nb, n, ng = (2, 2, 1), (16, 8, 8), 2
+    q0 = make_state(nb, n, ng, seed=13)
+    cfg = oracle_cfg(nb, n, ng, scheme=0, integrator=integ)
+    q0 = port.exchange(cfg, q0.ravel()).reshape(q0.shape)
+    dx = 2 * np.pi / 32
+    dt = 0.2 * dx / port.reduce_umax(cfg, q0.ravel())
+    want = port.advance(cfg, q0.ravel(), dt, 5).reshape(q0.shape)
+    got = _advance_product(nb, n, ng, q0, 0, integ, dt, 5)
+    assert rel_l2(got, want) < 1e-12
+    assert rel_l2(got - q0, want - q0) < 1e-9      # the increment itself, not just the state
+
+
+def test_rk4_hybrid_weno_trajectory_and_conservation():
+    from oracle import port
+    nb, n, ng = (2, 2, 2), (8, 8, 8), 2
+    q0 = make_state(nb, n, ng, seed=17, jump=True)
+    cfg = oracle_cfg(nb, n, ng, scheme=1, integrator=0)
+    q0 = port.exchange(cfg, q0.ravel()).reshape(q0.shape)
+    dx = 2 * np.pi / 16
+    dt = 0.2 * dx / port.reduce_umax(cfg, q0.ravel())
+    want = port.advance(cfg, q0.ravel(), dt, 3).reshape(q0.shape)
+    got = _advance_product(nb, n, ng, q0, 1, 0, dt, 3)
+    assert rel_l2(got, want) < 1e-12
+
+    def total_mass(q):
+        qi = interior(q, ng)
+        return (qi[..., 0] / (RGAS * qi[..., 1])).sum()
+    assert total_mass(got) == pytest.approx(total_mass(q0), rel=1e-12)   # periodic box conserves mass

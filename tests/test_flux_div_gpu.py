@@ -1,0 +1,96 @@
+"""Parity of the CUDA RHS kernel (through the C ABI) with the oracle restatement of
+pde_algs::flux_div / flux_div_basic (reference src/pde-algs/flux-div/flux_div_basic.h:17-77).
+Gate (BASELINE.json north_star): 1e-12 relative L2 in fp64 over the whole 5-vector field."""
+import numpy as np
+import pytest
+
+from util import make_state, oracle_cfg, product_flux, product_setup, rel_l2, interior
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def run_product(nb, n, ng, q, scheme, increment=False, rhs0=None, bounds=None, **kw):
+    sp, blocks, grid = product_setup(nb, n, ng, bounds)
+    qa = sp.grid_array.from_host(grid, q, (ng,) * 3)
+    ra = sp.grid_array(grid, 0.0, (ng,) * 3) if rhs0 is None else sp.grid_array.from_host(grid, rhs0, (ng,) * 3)
+    sp.flux_div(qa, ra, product_flux(scheme, **kw), sp.increment if increment else sp.overwrite)
+    return ra.to_host()
+
+
+@pytest.mark.parametrize("scheme", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+def test_schemes_match_oracle(scheme):
+    from oracle import port
+    nb, n, ng = (2, 1, 2), (32, 16, 8), 2
+    q = make_state(nb, n, ng, seed=scheme, jump=scheme in (1, 6, 8))
+    cfg = oracle_cfg(nb, n, ng, scheme=scheme)
+    want = port.flux_div(cfg, q.ravel()).reshape(q.shape)
+    got = run_product(nb, n, ng, q, scheme)
+    assert rel_l2(got, want) < TOL
+    # ghost cells of rhs are not touched (they started at zero like the reference's overwrite)
+    assert np.array_equal(got[:, 0], np.zeros_like(got[:, 0]))
+
+
+@pytest.mark.parametrize("n", [(16, 16, 16), (40, 12, 4), (8, 20, 6), (64, 8, 8), (4, 4, 4)])
+def test_ragged_block_shapes(n):
+    from oracle import port
+    nb, ng = (1, 2, 1), 2
+    for scheme in (0, 1):
+        q = make_state(nb, n, ng, seed=7)
+        cfg = oracle_cfg(nb, n, ng, scheme=scheme)
+        want = port.flux_div(cfg, q.ravel()).reshape(q.shape)
+        got = run_product(nb, n, ng, q, scheme)
+        assert rel_l2(got, want) < TOL
+
+
+def test_anisotropic_spacing_and_one_ghost():
+    from oracle import port
+    nb, n, ng = (2, 2, 1), (16, 8, 12), 1
+    bounds = [0.0, 6.0, -1.0, 1.0, 0.0, 3.0]
+    q = make_state(nb, n, ng, seed=3, bounds=bounds)
+    cfg = oracle_cfg(nb, n, ng, scheme=0, bounds=bounds)
+    want = port.flux_div(cfg, q.ravel()).reshape(q.shape)
+    got = run_product(nb, n, ng, q, 0, bounds=bounds)
+    assert rel_l2(got, want) < TOL
+
+
+def test_increment_trait():
+    from oracle import port
+    nb, n, ng = (1, 1, 2), (32, 8, 8), 2
+    q = make_state(nb, n, ng, seed=11)
+    rng = np.random.default_rng(5)
+    rhs0 = rng.normal(size=q.shape) * 1e3
+    cfg = oracle_cfg(nb, n, ng, scheme=0)
+    want = port.flux_div(cfg, q.ravel(), rhs=rhs0.ravel(), increment=True).reshape(q.shape)
+    got = run_product(nb, n, ng, q, 0, increment=True, rhs0=rhs0)
+    assert rel_l2(got, want) < TOL
+
+
+def test_uniform_state_has_zero_rhs_and_linearity_of_block_range():
+    sp, blocks, grid = product_setup((2, 2, 2), (32, 32, 32), 2)
+    q = np.zeros((8, 36, 36, 36, 5))
+    q[..., 0], q[..., 1], q[..., 2], q[..., 3], q[..., 4] = 101325.0, 300.0, 10.0, -3.0, 2.0
+    qa = sp.grid_array.from_host(grid, q)
+    ra = sp.grid_array(grid, 1.0)
+    sp.flux_div(qa, ra, product_flux(1), sp.overwrite)
+    r = interior(ra.to_host(), 2)
+    assert np.abs(r).max() < 1e-6 * 101325.0 * 10.0   # pure cancellation
+    # block-range launches tile the full launch exactly
+    qs = make_state((2, 2, 2), (32, 32, 32), 2, seed=1)
+    qa = sp.grid_array.from_host(grid, qs)
+    full = sp.grid_array(grid, 0.0)
+    parts = sp.grid_array(grid, 0.0)
+    sp.flux_div(qa, full, product_flux(0), sp.overwrite)
+    sp.flux_div(qa, parts, product_flux(0), sp.overwrite, blocks=(0, 3))
+    sp.flux_div(qa, parts, product_flux(0), sp.overwrite, blocks=(3, 8))
+    assert np.array_equal(full.to_host(), parts.to_host())
+
+
+def test_matches_reference_library_if_present(ref_lib):
+    nb, n, ng = (2, 2, 2), (16, 16, 16), 2
+    q = make_state(nb, n, ng, seed=21, jump=True)
+    for scheme in (0, 1):
+        cfg = oracle_cfg(nb, n, ng, scheme=scheme)
+        want = ref_lib.flux_div(cfg, q.ravel()).reshape(q.shape)
+        got = run_product(nb, n, ng, q, scheme)
+        assert rel_l2(got, want) < TOL
