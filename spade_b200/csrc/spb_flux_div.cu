@@ -28,7 +28,9 @@ namespace spb
 
     template <int H> struct FdivSmem
     {
-        static constexpr int TIp = TI + 2*H, TJp = TJ + 2*H;
+        // +2: fp64 TMA boxes must start on a 16-byte boundary (measured on B200: an odd first coordinate raises
+        // an illegal-instruction fault), so the box starts one cell early when the halo start is an odd cell
+        static constexpr int TIp = TI + 2*H + 2, TJp = TJ + 2*H;
         static constexpr int NP = H + 3;                                  // ring slots
         static constexpr int PLANE_DOUBLES = TIp*TJp*5;
         static constexpr int PLANE_BYTES = PLANE_DOUBLES*8;
@@ -81,7 +83,8 @@ namespace spb
         const double invdx[3] = {inv_dx_tab[3*lb + 0], inv_dx_tab[3*lb + 1], inv_dx_tab[3*lb + 2]};
 
         // TMA coordinates of the tile (fused (v,i) dimension first)
-        const int c0 = 5*(i0 + G.ng[0] - H);
+        const int ash = (i0 + G.ng[0] - H) & 1;          // alignment shift (cells)
+        const int c0 = 5*(i0 + G.ng[0] - H - ash);
         const int c1 = j0 + G.ng[1] - H;
         const int c2base = G.ng[2] - H;               // plane p -> k = p - H -> coordinate p + ng - H
         const int nplanes = nz + 2*H;
@@ -109,7 +112,7 @@ namespace spb
 
         TileAcc<H> acc;
         acc.ring = ring;
-        acc.cell = ((jl + H)*S::TIp + (il + H))*5;
+        acc.cell = ((jl + H)*S::TIp + (il + H + ash))*5;
 
         // planes p = 0 .. H are needed by step 0 besides plane H+1
         uint32_t parity_bits = 0;                      // bit s = parity to wait for on slot s
@@ -167,7 +170,7 @@ namespace spb
                 if (tid < nj_t)                      // warp 0: x-face i = ni_t of row tid
                 {
                     TileAcc<H> e = acc;
-                    e.cell = ((tid + H)*S::TIp + (ni_t + H))*5;
+                    e.cell = ((tid + H)*S::TIp + (ni_t + H + ash))*5;
                     double F[5];
                     face_flux<CONV, DISS, VISC, 0>(e, P, invdx, F);
                     #pragma unroll
@@ -176,7 +179,7 @@ namespace spb
                 if (tid >= 32 && tid < 32 + ni_t)    // warp 1: y-face j = nj_t of column tid-32
                 {
                     TileAcc<H> e = acc;
-                    e.cell = ((nj_t + H)*S::TIp + (tid - 32 + H))*5;
+                    e.cell = ((nj_t + H)*S::TIp + (tid - 32 + H + ash))*5;
                     double F[5];
                     face_flux<CONV, DISS, VISC, 1>(e, P, invdx, F);
                     #pragma unroll
