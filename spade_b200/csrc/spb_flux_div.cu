@@ -60,9 +60,10 @@ namespace spb
     {
         constexpr int H = stencil_halo<CONV, DISS>::value;
         using S = FdivSmem<H>;
-        extern __shared__ __align__(128) unsigned char smem_raw[];
-        unsigned char* smem_al = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~uintptr_t(127));
-        double*   ring = (double*)smem_al;
+        extern __shared__ __align__(128) double smem_raw[];
+        // pointer arithmetic on the __shared__ symbol (no integer round trip) keeps the address space known
+        // to the compiler: LDS/STS instead of generic LD/ST
+        double*   ring = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
         double*   Fx   = ring + S::NP*S::PLANE_STRIDE;
         double*   Fy   = Fx + S::FX_DOUBLES;
         uint64_t* bars = (uint64_t*)(Fy + S::FY_DOUBLES);
