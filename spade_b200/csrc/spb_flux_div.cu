@@ -255,6 +255,13 @@ namespace spb
     }
 }
 
+namespace spb
+{
+    template <int CONV, int VISC>
+    int launch_fdiv_narrow(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream);     // spb_flux_div_narrow.cu
+}
+
 extern "C"
 {
     int spb_flux_div_blocks(const spb_grid* g, const double* q_dev, double* rhs_dev, const spb_flux_desc* f,
@@ -272,14 +279,17 @@ extern "C"
         cudaStream_t st = (cudaStream_t)stream;
 #define SPB_CASE(C, D, V) if (f->conv == C && f->diss == D && (f->visc != 0) == (V != 0)) \
             return launch_fdiv<C, D, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st)
-        SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_NONE,  1);
+#define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
+            return launch_fdiv_narrow<C, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st)
+        SPB_NARROW(SPB_CONV_TOTANI, 1);
+        SPB_NARROW(SPB_CONV_TOTANI, 0);
+        SPB_NARROW(SPB_CONV_NONE,   1);
+#undef SPB_NARROW
         SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_FWENO, 1);
         SPB_CASE(SPB_CONV_CENT_KEEP4, SPB_DISS_NONE,  1);
         SPB_CASE(SPB_CONV_CENT_KEEP4, SPB_DISS_FWENO, 1);
-        SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_NONE,  0);
         SPB_CASE(SPB_CONV_CENT_KEEP4, SPB_DISS_NONE,  0);
         SPB_CASE(SPB_CONV_FWENO,      SPB_DISS_NONE,  0);
-        SPB_CASE(SPB_CONV_NONE,       SPB_DISS_NONE,  1);
         SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_FWENO, 0);
 #undef SPB_CASE
         set_error("spb_flux_div: this combination of flux functors is not in the implemented set");

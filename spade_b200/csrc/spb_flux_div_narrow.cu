@@ -1,0 +1,542 @@
+// Fused RHS kernel for the one-ghost-cell ("narrow") functor set: totani_lr and/or visc_lr.
+// Replaces pde_algs::flux_div (reference src/pde-algs/flux-div/flux_div_basic.h:17-77) composed with
+// convective::totani_lr (src/navier-stokes/convective.h:68-93) and viscous::visc_lr
+// (src/navier-stokes/viscous.h:39-80; face value/gradient src/omni/infos/info_value.h:30-40,
+// info_gradient.h:22-87) for coords::identity.
+//
+// Design (B200, sm_100a):
+//  * One CTA = TI x TJ column of one block, marching through k. 8 compute warps (one cell per
+//    thread) + 1 edge warp that owns the halo ring (cells i = -1, j = -1) and the faces on the
+//    upper tile edge, so no compute warp does more than three faces per plane.
+//  * Planes of q (reference AoS order) arrive in a 4-slot shared-memory ring through TMA
+//    (cp.async.bulk.tensor.4d + mbarrier), two planes ahead of the compute.
+//  * A thread keeps its own column (k-1, k, k+1) in registers. Everything a neighbour needs from a
+//    cell is published once per plane in SoA shared memory: density and the scaled central
+//    differences D_t = 0.25/dx_t (q(c+e_t) - q(c-e_t)), because the reference's tangential face
+//    gradient is exactly D_t(L) + D_t(R). Every face flux is evaluated once; x/y fluxes are handed
+//    to the neighbour through shared memory, the z flux stays in registers.
+//  * The finished rhs plane is staged in shared memory and written with one TMA tensor store
+//    (hardware clips ragged tiles to the interior), so global stores are fully coalesced.
+#include "spb_common.cuh"
+#include "spb_tma.cuh"
+#include "spb_flux.cuh"
+
+namespace spb
+{
+    namespace nrw
+    {
+        constexpr int TI = 32, TJ = 8;
+        constexpr int NCOMPUTE = TI*TJ;                 // 8 warps
+        constexpr int NTHREADS = NCOMPUTE + 32;         // + edge warp
+        constexpr int TIp = TI + 2 + 2;                 // halo + 16-byte TMA start alignment slack
+        constexpr int TJp = TJ + 2;
+        constexpr int NP = 4;                           // ring slots
+        constexpr int PLANE_DOUBLES = TIp*TJp*5;
+        constexpr int PLANE_BYTES = PLANE_DOUBLES*8;
+        constexpr int PLANE_STRIDE = ((PLANE_BYTES + 127)/128*128)/8;
+        constexpr int PW = TI + 2;                      // published arrays: [NPUB][TJ+2][PW]
+        constexpr int PSZ = (TJ + 2)*PW;
+        constexpr int NPUB = 8;                         // rho, Dx.u, Dx.v, Dy.u, Dy.v, Dz.u, Dz.v, Dz.w
+        constexpr int FX_DOUBLES = TJ*(TI + 1)*5;
+        constexpr int FY_DOUBLES = (TJ + 1)*TI*5;
+        constexpr int STAGE_DOUBLES = TJ*TI*5;
+        constexpr int OFF_P = NP*PLANE_STRIDE;
+        constexpr int OFF_STAGE = (OFF_P + NPUB*PSZ + 15)/16*16;          // 128-byte aligned for the TMA store
+        constexpr int OFF_FX = OFF_STAGE + STAGE_DOUBLES;
+        constexpr int OFF_FY = OFF_FX + FX_DOUBLES;
+        constexpr int OFF_BAR = OFF_FY + FY_DOUBLES;
+        constexpr int SMEM_BYTES = (OFF_BAR + NP)*8 + 128;
+
+        enum { P_RHO = 0, P_DXU, P_DXV, P_DYU, P_DYV, P_DZU, P_DZV, P_DZW };
+
+        struct Dims
+        {
+            int nx[3], ng[3], np[3];
+            int tiles_i, tiles_j;
+            long long block_stride;
+            long long lb0;
+            int increment;
+            int tma_store;
+            double idx[3], cdx[3];          // uniform lattice: 1/dx and 0.25/dx
+        };
+
+        // One face of direction D. s-sums and differences are shared between the convective and the viscous part.
+        //   a = g[T1][u_T1], b = g[T1][u_D], c = g[T2][u_T2], d = g[T2][u_D]   (tangential face gradients)
+        template <int CONV, int VISC, int D>
+        __device__ __forceinline__ void face(const FluxParams& P, const double (&qL)[5], const double (&qR)[5],
+                                             const double rhoL, const double rhoR, const double a, const double b,
+                                             const double c, const double d, const double invdxD, double (&F)[5])
+        {
+            constexpr int T1 = (D + 1) % 3, T2 = (D + 2) % 3;
+            const double s0 = qL[2] + qR[2], s1 = qL[3] + qR[3], s2 = qL[4] + qR[4];
+            const double s[3] = {s0, s1, s2};
+            if (CONV == SPB_CONV_TOTANI)
+            {
+                // reference convective.h:68-93 with n = e_D
+                const double C  = (rhoL + rhoR)*s[D];                                   // 4c
+                double S = P.cv*(qL[1] + qR[1]);                                        // e_L + e_R
+                S = fma(qL[2], qR[2], S); S = fma(qL[3], qR[3], S); S = fma(qL[4], qR[4], S);
+                const double C8 = 0.125*C;
+                F[0] = 0.25*C;
+                F[1] = fma(C8, S, 0.5*fma(qL[2+D], qR[0], qR[2+D]*qL[0]));
+                F[2] = C8*s0; F[3] = C8*s1; F[4] = C8*s2;
+                F[2+D] = fma(0.5, qL[0] + qR[0], F[2+D]);
+            }
+            else
+            {
+                #pragma unroll
+                for (int v = 0; v < 5; ++v) F[v] = 0.0;
+            }
+            if (VISC)
+            {
+                // reference viscous.h:39-80 with n = e_D: only the stress row D is needed
+                const double gD  = (qR[2+D] - qL[2+D])*invdxD;
+                const double div = gD + a + c;
+                const double tDD = fma(P.two_mu, gD, P.beta*div);
+                const double tD1 = P.mu*fma(qR[2+T1] - qL[2+T1], invdxD, b);
+                const double tD2 = P.mu*fma(qR[2+T2] - qL[2+T2], invdxD, d);
+                const double hh  = fma(s[D], tDD, fma(s[T1], tD1, s[T2]*tD2));         // 2 u_f . tau_D
+                F[1] = fma(-0.5, hh, F[1]);
+                F[1] = fma(-(P.kappa*invdxD), qR[1] - qL[1], F[1]);                               // kappa dT/dx_D
+                F[2+D]  -= tDD;
+                F[2+T1] -= tD1;
+                F[2+T2] -= tD2;
+            }
+        }
+
+        // Inverse spacings: for a uniform lattice (all blocks the same dx) they come from the kernel-parameter constant
+        // bank and cost no registers; otherwise (AMR: per-block dx) they are read from the per-block table.
+        template <bool UNIF> struct Spacing
+        {
+            double i0, i1, i2, c0, c1, c2;
+            __device__ __forceinline__ Spacing(const Dims& G, const double* __restrict__ tab, long long lb)
+            {
+                if (UNIF) { i0 = G.idx[0]; i1 = G.idx[1]; i2 = G.idx[2]; c0 = G.cdx[0]; c1 = G.cdx[1]; c2 = G.cdx[2]; }
+                else
+                {
+                    i0 = tab[3*lb + 0]; i1 = tab[3*lb + 1]; i2 = tab[3*lb + 2];
+                    c0 = 0.25*i0; c1 = 0.25*i1; c2 = 0.25*i2;
+                }
+            }
+        };
+
+        template <int CONV, int VISC, bool UNIF>
+        __global__ void __launch_bounds__(NTHREADS, 2)
+        flux_div_narrow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_rhs,
+                               double* __restrict__ rhs, const __grid_constant__ FluxParams P, const __grid_constant__ Dims G,
+                               const double* __restrict__ inv_dx_tab)
+        {
+            extern __shared__ __align__(128) double smem_raw[];
+            double*   ring  = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
+            double*   pub   = ring + OFF_P;
+            double*   stage = ring + OFF_STAGE;
+            double*   Fx    = ring + OFF_FX;
+            double*   Fy    = ring + OFF_FY;
+            uint64_t* bars  = (uint64_t*)(ring + OFF_BAR);
+
+            const int tid = threadIdx.x;
+            const int lane = tid & 31, warp = tid >> 5;
+            const bool is_edge = (warp == TJ);
+
+            int t = blockIdx.x;
+            const int ti = t % G.tiles_i; t /= G.tiles_i;
+            const int tj = t % G.tiles_j; t /= G.tiles_j;
+            const long long lb = G.lb0 + t;
+            const int i0 = ti*TI, j0 = tj*TJ;
+            const int nz = G.nx[2];
+            const int ni_t = min(TI, G.nx[0] - i0);
+            const int nj_t = min(TJ, G.nx[1] - j0);
+            const Spacing<UNIF> H(G, inv_dx_tab, lb);
+
+            // TMA coordinates (fused (v,i) dimension first); the box starts one cell early if the halo start is odd
+            const int ash = (i0 + G.ng[0] - 1) & 1;
+            const int c0 = 5*(i0 + G.ng[0] - 1 - ash);
+            const int c1 = j0 + G.ng[1] - 1;
+            const int c2base = G.ng[2] - 1;               // plane p <-> k = p - 1
+            const int nplanes = nz + 2;
+
+            if (tid == NCOMPUTE)
+            {
+                prefetch_tmap(&tmap_q);
+                if (G.tma_store) prefetch_tmap(&tmap_rhs);
+                #pragma unroll
+                for (int s = 0; s < NP; ++s) mbar_init(&bars[s], 1);
+                fence_mbar_init();
+            }
+            __syncthreads();
+            if (tid == NCOMPUTE)
+            {
+                #pragma unroll
+                for (int p = 0; p < NP; ++p)
+                    if (p < nplanes)
+                    {
+                        mbar_arrive_expect_tx(&bars[p], PLANE_BYTES);
+                        tma_load_4d(ring + p*PLANE_STRIDE, &tmap_q, &bars[p], c0, c1, c2base + p, (int)lb);
+                    }
+            }
+
+            // raw cell (ci, cj) of a staged plane; ci, cj are tile-local and may be -1 .. TI / TJ
+            auto cell_off = [&](int ci, int cj) { return ((cj + 1)*TIp + (ci + 1 + ash))*5; };
+            auto pidx = [&](int ci, int cj) { return (cj + 1)*PW + (ci + 1); };
+
+            mbar_wait(&bars[0], 0);
+            mbar_wait(&bars[1], 0);
+
+            // Ring residency at step k: planes k-1, k, k+1 (plane index p = k + 1); plane k+2 is in flight. The slot of
+            // plane k-2 is refilled with plane k+2 right after barrier (1) of step k-1.
+            if (!is_edge)
+            {
+                // ======================= compute warps: one cell column per thread =======================
+                const int il = lane, jl = warp;
+                const bool active = (il < ni_t) && (jl < nj_t);
+                const int co = cell_off(il, jl);
+                const int po = pidx(il, jl);
+                // loop-carried state: density of cells k-1 and k, tangential differences of cell k-1 needed by the
+                // next z-face, and the divergence accumulator of cell k-1
+                double rhom, rho0;
+                double dpxu = 0.0, dpxw = 0.0, dpyv = 0.0, dpyw = 0.0;
+                {
+                    const double* pl = ring;
+                    rhom = pl[co]/(P.R*pl[co + 1]);
+                    rho0 = ring[PLANE_STRIDE + co]/(P.R*ring[PLANE_STRIDE + co + 1]);
+                    if (!active) { rhom = 1.0; rho0 = 1.0; }
+                    if (VISC)
+                    {
+                        dpxu = H.c0*(pl[co + 5 + 2] - pl[co - 5 + 2]);
+                        dpxw = H.c0*(pl[co + 5 + 4] - pl[co - 5 + 4]);
+                        dpyv = H.c1*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
+                        dpyw = H.c1*(pl[co + 5*TIp + 4] - pl[co - 5*TIp + 4]);
+                    }
+                }
+                double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                double* rhs_col = rhs + lb*G.block_stride
+                    + 5ll*((i0 + il + G.ng[0]) + (long long)G.np[0]*((j0 + jl + G.ng[1]) + (long long)G.np[1]*G.ng[2]));
+                const long long kstride = 5ll*G.np[0]*G.np[1];
+
+                for (int k = 0; k <= nz; ++k)
+                {
+                    const int pk = k + 1;                       // plane index of k
+                    const double* plm = ring + ((pk - 1) & (NP - 1))*PLANE_STRIDE + co;
+                    const double* plk = ring + (pk & (NP - 1))*PLANE_STRIDE + co;
+                    const double* plp = ring + ((pk + 1) & (NP - 1))*PLANE_STRIDE + co;
+                    if (pk + 1 < nplanes) mbar_wait(&bars[(pk + 1) & (NP - 1)], ((pk + 1)/NP) & 1);
+
+                    double q0[5];
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) q0[v] = plk[v];
+                    double rhop = plp[0]/(P.R*plp[1]);              // garbage at k = nz, never used
+                    if (!active) rhop = 1.0;
+
+                    // scaled central differences of cell k
+                    double dxu = 0.0, dxv = 0.0, dxw = 0.0, dyu = 0.0, dyv = 0.0, dyw = 0.0, dzu = 0.0, dzv = 0.0, dzw = 0.0;
+                    if (VISC)
+                    {
+                        dxu = H.c0*(plk[5 + 2] - plk[-5 + 2]);
+                        dxv = H.c0*(plk[5 + 3] - plk[-5 + 3]);
+                        dxw = H.c0*(plk[5 + 4] - plk[-5 + 4]);
+                        dyu = H.c1*(plk[5*TIp + 2] - plk[-5*TIp + 2]);
+                        dyv = H.c1*(plk[5*TIp + 3] - plk[-5*TIp + 3]);
+                        dyw = H.c1*(plk[5*TIp + 4] - plk[-5*TIp + 4]);
+                        if (k < nz)
+                        {
+                            dzu = H.c2*(plp[2] - plm[2]);
+                            dzv = H.c2*(plp[3] - plm[3]);
+                            dzw = H.c2*(plp[4] - plm[4]);
+                        }
+                    }
+                    if (k < nz)
+                    {
+                        pub[P_RHO*PSZ + po] = rho0;
+                        if (VISC)
+                        {
+                            pub[P_DXU*PSZ + po] = dxu; pub[P_DXV*PSZ + po] = dxv;
+                            pub[P_DYU*PSZ + po] = dyu; pub[P_DYV*PSZ + po] = dyv;
+                            pub[P_DZU*PSZ + po] = dzu; pub[P_DZV*PSZ + po] = dzv; pub[P_DZW*PSZ + po] = dzw;
+                        }
+                    }
+                    // z-face k-1/2. acc carries the divergence of a cell: lower-face fluxes are added as they are computed,
+                    // the neighbours' (upper-face) fluxes are subtracted after barrier (2).
+                    {
+                        double qm[5], Fz[5];
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v) qm[v] = plm[v];
+                        face<CONV, VISC, 2>(P, qm, q0, rhom, rho0, dpxu + dxu, dpxw + dxw, dpyv + dyv, dpyw + dyw, H.i2, Fz);
+                        if (k >= 1)
+                        {
+                            if (G.tma_store)
+                            {
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) stage[(jl*TI + il)*5 + v] = fma(-Fz[v], H.i2, acc[v]);
+                            }
+                            else if (active)
+                            {
+                                double* o = rhs_col + (long long)(k - 1)*kstride;
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v)
+                                {
+                                    double r = fma(-Fz[v], H.i2, acc[v]);
+                                    if (G.increment) r += o[v];
+                                    o[v] = r;
+                                }
+                            }
+                        }
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v) acc[v] = Fz[v]*H.i2;
+                    }
+                    if (G.tma_store) fence_proxy_async();
+                    __syncthreads();                                            // (1) published data + staged rhs visible
+                    if (k < nz)
+                    {
+                        {
+                            double qL[5], F[5];
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) qL[v] = plk[-5 + v];
+                            const int pl_ = po - 1;
+                            const double rhoL = pub[P_RHO*PSZ + pl_];
+                            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+                            if (VISC)
+                            {
+                                a = pub[P_DYV*PSZ + pl_] + dyv; b = pub[P_DYU*PSZ + pl_] + dyu;
+                                c = pub[P_DZW*PSZ + pl_] + dzw; d = pub[P_DZU*PSZ + pl_] + dzu;
+                            }
+                            face<CONV, VISC, 0>(P, qL, q0, rhoL, rho0, a, b, c, d, H.i0, F);
+                            if (active)
+                            {
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) Fx[(jl*(TI + 1) + il)*5 + v] = F[v];
+                            }
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) acc[v] = fma(F[v], H.i0, acc[v]);
+                        }
+                        {
+                            double qL[5], F[5];
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) qL[v] = plk[-5*TIp + v];
+                            const int pl_ = po - PW;
+                            const double rhoL = pub[P_RHO*PSZ + pl_];
+                            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+                            if (VISC)
+                            {
+                                a = pub[P_DZW*PSZ + pl_] + dzw; b = pub[P_DZV*PSZ + pl_] + dzv;
+                                c = pub[P_DXU*PSZ + pl_] + dxu; d = pub[P_DXV*PSZ + pl_] + dxv;
+                            }
+                            face<CONV, VISC, 1>(P, qL, q0, rhoL, rho0, a, b, c, d, H.i1, F);
+                            if (active)
+                            {
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) Fy[(jl*TI + il)*5 + v] = F[v];
+                            }
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) acc[v] = fma(F[v], H.i1, acc[v]);
+                        }
+                    }
+                    __syncthreads();                                            // (2) fluxes visible; pub free
+                    if (k < nz)
+                    {
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v)
+                        {
+                            acc[v] = fma(-Fx[(jl*(TI + 1) + il + 1)*5 + v], H.i0, acc[v]);
+                            acc[v] = fma(-Fy[((jl + 1)*TI + il)*5 + v], H.i1, acc[v]);
+                        }
+                    }
+                    rhom = rho0; rho0 = rhop;
+                    dpxu = dxu; dpxw = dxw; dpyv = dyv; dpyw = dyw;
+                }
+            }
+            else
+            {
+                // ======================= edge warp: halo ring + upper-edge faces + TMA traffic =======================
+                // row job (lanes 0..31): cell (lane, -1) is published, cell (lane, nj_t) is the R cell of the upper y-face
+                // col job (lanes 0..15): cell (-1, lane) is published, cell (ni_t, lane-8) is the R cell of the upper x-face
+                const bool row_on = lane < ni_t;
+                const int  ccj = lane & 7;
+                const bool col_lo = lane < 8, col_on = (lane < 16) && (ccj < nj_t);
+                const int  cci = col_lo ? -1 : ni_t;
+                const int co_r0 = cell_off(lane, -1), co_r1 = cell_off(lane, nj_t), co_c = cell_off(cci, ccj);
+                for (int k = 0; k <= nz; ++k)
+                {
+                    const int pk = k + 1;
+                    const double* plm = ring + ((pk - 1) & (NP - 1))*PLANE_STRIDE;
+                    const double* plk = ring + (pk & (NP - 1))*PLANE_STRIDE;
+                    const double* plp = ring + ((pk + 1) & (NP - 1))*PLANE_STRIDE;
+                    if (pk + 1 < nplanes) mbar_wait(&bars[(pk + 1) & (NP - 1)], ((pk + 1)/NP) & 1);
+                    // ---- before (1): publish the lower halo; z-differences of the upper R cells (plane k-1 is recycled after (1))
+                    // and everything else the upper faces need from their R cells, so that the work after (1) is two faces
+                    double uDzv = 0.0, uDzw = 0.0, uDxu = 0.0, uDxv = 0.0, xDzu = 0.0, xDzw = 0.0, xDyu = 0.0, xDyv = 0.0;
+                    double uRho = 1.0, xRho = 1.0;
+                    if (k < nz)
+                    {
+                        if (row_on) uRho = plk[co_r1]/(P.R*plk[co_r1 + 1]);
+                        if (col_on && !col_lo) xRho = plk[co_c]/(P.R*plk[co_c + 1]);
+                        if (VISC)
+                        {
+                            uDzv = H.c2*(plp[co_r1 + 3] - plm[co_r1 + 3]);
+                            uDzw = H.c2*(plp[co_r1 + 4] - plm[co_r1 + 4]);
+                            uDxu = H.c0*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
+                            uDxv = H.c0*(plk[co_r1 + 5 + 3] - plk[co_r1 - 5 + 3]);
+                            xDzu = H.c2*(plp[co_c + 2] - plm[co_c + 2]);
+                            xDzw = H.c2*(plp[co_c + 4] - plm[co_c + 4]);
+                            xDyu = H.c1*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
+                            xDyv = H.c1*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]);
+                        }
+                    }
+                    if (k < nz)
+                    {
+                        if (row_on)
+                        {
+                            const int po = pidx(lane, -1);
+                            pub[P_RHO*PSZ + po] = plk[co_r0 + 0]/(P.R*plk[co_r0 + 1]);
+                            if (VISC)
+                            {
+                                pub[P_DZV*PSZ + po] = H.c2*(plp[co_r0 + 3] - plm[co_r0 + 3]);
+                                pub[P_DZW*PSZ + po] = H.c2*(plp[co_r0 + 4] - plm[co_r0 + 4]);
+                                pub[P_DXU*PSZ + po] = H.c0*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
+                                pub[P_DXV*PSZ + po] = H.c0*(plk[co_r0 + 5 + 3] - plk[co_r0 - 5 + 3]);
+                            }
+                        }
+                        if (col_on && col_lo)
+                        {
+                            const int po = pidx(-1, ccj);
+                            pub[P_RHO*PSZ + po] = plk[co_c + 0]/(P.R*plk[co_c + 1]);
+                            if (VISC)
+                            {
+                                pub[P_DYU*PSZ + po] = H.c1*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
+                                pub[P_DYV*PSZ + po] = H.c1*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]);
+                                pub[P_DZU*PSZ + po] = H.c2*(plp[co_c + 2] - plm[co_c + 2]);
+                                pub[P_DZW*PSZ + po] = H.c2*(plp[co_c + 4] - plm[co_c + 4]);
+                            }
+                        }
+                    }
+                    __syncthreads();                                            // (1)
+                    if (lane == 0)
+                    {
+                        if (G.tma_store && k >= 1)
+                        {
+                            tma_store_4d(&tmap_rhs, stage, 5*i0, j0, k - 1, (int)lb);
+                            tma_store_commit();
+                        }
+                        // plane k-1 (index pk-1) has been consumed by every thread: refill its slot with plane pk-1+NP
+                        const int pnew = pk - 1 + NP;
+                        if (pnew < nplanes)
+                        {
+                            const int s = (pk - 1) & (NP - 1);
+                            mbar_arrive_expect_tx(&bars[s], PLANE_BYTES);
+                            tma_load_4d(ring + s*PLANE_STRIDE, &tmap_q, &bars[s], c0, c1, c2base + pnew, (int)lb);
+                        }
+                    }
+                    if (k < nz)
+                    {
+                        if (row_on)                                              // upper y-face (lane, nj_t)
+                        {
+                            double qL[5], qR[5], F[5];
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) { qL[v] = plk[co_r1 - 5*TIp + v]; qR[v] = plk[co_r1 + v]; }
+                            const int pl_ = pidx(lane, nj_t - 1);
+                            const double rhoL = pub[P_RHO*PSZ + pl_];
+                            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+                            if (VISC)
+                            {
+                                a = pub[P_DZW*PSZ + pl_] + uDzw;
+                                b = pub[P_DZV*PSZ + pl_] + uDzv;
+                                c = pub[P_DXU*PSZ + pl_] + uDxu;
+                                d = pub[P_DXV*PSZ + pl_] + uDxv;
+                            }
+                            face<CONV, VISC, 1>(P, qL, qR, rhoL, uRho, a, b, c, d, H.i1, F);
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) Fy[(nj_t*TI + lane)*5 + v] = F[v];
+                        }
+                        if (col_on && !col_lo)                                   // upper x-face (ni_t, ccj)
+                        {
+                            double qL[5], qR[5], F[5];
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) { qL[v] = plk[co_c - 5 + v]; qR[v] = plk[co_c + v]; }
+                            const int pl_ = pidx(ni_t - 1, ccj);
+                            const double rhoL = pub[P_RHO*PSZ + pl_];
+                            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+                            if (VISC)
+                            {
+                                a = pub[P_DYV*PSZ + pl_] + xDyv;
+                                b = pub[P_DYU*PSZ + pl_] + xDyu;
+                                c = pub[P_DZW*PSZ + pl_] + xDzw;
+                                d = pub[P_DZU*PSZ + pl_] + xDzu;
+                            }
+                            face<CONV, VISC, 0>(P, qL, qR, rhoL, xRho, a, b, c, d, H.i0, F);
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) Fx[(ccj*(TI + 1) + ni_t)*5 + v] = F[v];
+                        }
+                    }
+                    if (lane == 0 && G.tma_store) tma_store_wait_read<0>();     // staging tile may be rewritten after (2)
+                    __syncthreads();                                            // (2)
+                }
+                if (lane == 0 && G.tma_store) tma_store_wait<0>();
+            }
+        }
+    }
+
+    template <int CONV, int VISC>
+    int launch_fdiv_narrow(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream)
+    {
+        using namespace nrw;
+        for (int d = 0; d < 3; ++d)
+            if (g->ng[d] < 1) { set_error("spb_flux_div: scheme needs 1 exchange cell"); return SPB_ERR_BAD_ARG; }
+        if ((5*g->np[0]) % 2 != 0) { set_error("spb_flux_div: n0 + 2*g0 must be even (16-byte TMA row pitch)"); return SPB_ERR_UNSUPPORTED; }
+        encode_tiled_fn enc = get_encode_tiled();
+        if (!enc) { set_error("spb_flux_div: cuTensorMapEncodeTiled not available from the driver"); return SPB_ERR_DRIVER; }
+
+        CUtensorMap tq, tr;
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        {
+            const cuuint64_t dims[4]    = {(cuuint64_t)5*g->np[0], (cuuint64_t)g->np[1], (cuuint64_t)g->np[2], (cuuint64_t)g->nlb};
+            const cuuint64_t strides[3] = {(cuuint64_t)40*g->np[0], (cuuint64_t)40*g->np[0]*g->np[1], (cuuint64_t)8*g->block_stride};
+            const cuuint32_t box[4]     = {(cuuint32_t)(5*TIp), (cuuint32_t)TJp, 1, 1};
+            CUresult cr = enc(&tq, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)q, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) { set_error("spb_flux_div: cuTensorMapEncodeTiled(q) failed with CUresult " + std::to_string((int)cr)); return SPB_ERR_DRIVER; }
+        }
+        // interior-only view of rhs for the tensor store: the hardware clips ragged tiles to the interior
+        const long long org = 5ll*(g->ng[0] + (long long)g->np[0]*(g->ng[1] + (long long)g->np[1]*g->ng[2]));
+        int tma_store = (!increment && (org % 2 == 0) && (((uintptr_t)rhs) % 16 == 0)) ? 1 : 0;
+        if (tma_store)
+        {
+            const cuuint64_t dims[4]    = {(cuuint64_t)5*g->nx[0], (cuuint64_t)g->nx[1], (cuuint64_t)g->nx[2], (cuuint64_t)g->nlb};
+            const cuuint64_t strides[3] = {(cuuint64_t)40*g->np[0], (cuuint64_t)40*g->np[0]*g->np[1], (cuuint64_t)8*g->block_stride};
+            const cuuint32_t box[4]     = {(cuuint32_t)(5*TI), (cuuint32_t)TJ, 1, 1};
+            CUresult cr = enc(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)(rhs + org), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) tma_store = 0;
+        }
+        if (!tma_store) tr = tq;
+
+        Dims G;
+        for (int d = 0; d < 3; ++d) { G.nx[d] = g->nx[d]; G.ng[d] = g->ng[d]; G.np[d] = g->np[d]; }
+        G.tiles_i = (g->nx[0] + TI - 1)/TI;
+        G.tiles_j = (g->nx[1] + TJ - 1)/TJ;
+        G.block_stride = g->block_stride;
+        G.lb0 = lb_begin;
+        G.increment = increment;
+        G.tma_store = tma_store;
+        const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
+        if (nblk <= 0) return 0;
+        bool uniform = true;
+        for (int64_t b = lb_begin; b < lb_end && uniform; ++b)
+            for (int d = 0; d < 3; ++d) uniform = uniform && (g->inv_dx_host[3*b + d] == g->inv_dx_host[3*lb_begin + d]);
+        for (int d = 0; d < 3; ++d) { G.idx[d] = g->inv_dx_host[3*lb_begin + d]; G.cdx[d] = 0.25*G.idx[d]; }
+        auto go = [&](auto kern) -> int
+        {
+            SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, rhs, P, G, g->inv_dx_dev);
+            SPB_LAUNCH_CHECK();
+            return 0;
+        };
+        return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true>) : go(flux_div_narrow_kernel<CONV, VISC, false>);
+    }
+
+    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t);
+    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 0>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t);
+    template int launch_fdiv_narrow<SPB_CONV_NONE, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t);
+}
