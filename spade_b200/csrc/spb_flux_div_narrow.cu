@@ -36,7 +36,7 @@ namespace spb
         constexpr int PLANE_STRIDE = ((PLANE_BYTES + 127)/128*128)/8;
         constexpr int PW = TI + 2;                      // published arrays: [NPUB][TJ+2][PW]
         constexpr int PSZ = (TJ + 2)*PW;
-        constexpr int NPUB = 8;                         // rho, Dx.u, Dx.v, Dy.u, Dy.v, Dz.u, Dz.v, Dz.w
+        constexpr int NPUB = 7;                         // rho, cX, Dy.u, Dz.u, cY, Dz.v, Dx.v
         constexpr int FX_DOUBLES = TJ*(TI + 1)*5;
         constexpr int FY_DOUBLES = (TJ + 1)*TI*5;
         constexpr int STAGE_DOUBLES = TJ*TI*5;
@@ -47,7 +47,7 @@ namespace spb
         constexpr int OFF_BAR = OFF_FY + FY_DOUBLES;
         constexpr int SMEM_BYTES = (OFF_BAR + NP)*8 + 128;
 
-        enum { P_RHO = 0, P_DXU, P_DXV, P_DYU, P_DYV, P_DZU, P_DZV, P_DZW };
+        enum { P_RHO = 0, P_CX /* Dy.v + Dz.w */, P_DYU, P_DZU, P_CY /* Dz.w + Dx.u */, P_DZV, P_DXV };
 
         struct Dims
         {
@@ -61,11 +61,26 @@ namespace spb
         };
 
         // One face of direction D. s-sums and differences are shared between the convective and the viscous part.
-        //   a = g[T1][u_T1], b = g[T1][u_D], c = g[T2][u_T2], d = g[T2][u_D]   (tangential face gradients)
+        //   ac = g[T1][u_T1] + g[T2][u_T2], b = g[T1][u_D], d = g[T2][u_D]   (tangential face gradients; the two
+        //   tangential diagonal terms only enter through the divergence)
+        // rho = p/(R T) (reference convective.h:70, fluid_state.h:105) with a Newton-refined hardware reciprocal:
+        // MUFU.RCP64H seed (>= 20 bits) + 2 iterations -> relative error ~1e-16, no slow-path branch.
+        __device__ __forceinline__ double density(const double R, const double p, const double T)
+        {
+            const double a = R*T;
+            double x;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+            double e = fma(-a, x, 1.0);
+            x = fma(x, e, x);
+            e = fma(-a, x, 1.0);
+            x = fma(x, e, x);
+            return p*x;
+        }
+
         template <int CONV, int VISC, int D>
         __device__ __forceinline__ void face(const FluxParams& P, const double (&qL)[5], const double (&qR)[5],
-                                             const double rhoL, const double rhoR, const double a, const double b,
-                                             const double c, const double d, const double invdxD, double (&F)[5])
+                                             const double rhoL, const double rhoR, const double ac, const double b,
+                                             const double d, const double invdxD, double (&F)[5])
         {
             constexpr int T1 = (D + 1) % 3, T2 = (D + 2) % 3;
             const double s0 = qL[2] + qR[2], s1 = qL[3] + qR[3], s2 = qL[4] + qR[4];
@@ -91,7 +106,7 @@ namespace spb
             {
                 // reference viscous.h:39-80 with n = e_D: only the stress row D is needed
                 const double gD  = (qR[2+D] - qL[2+D])*invdxD;
-                const double div = gD + a + c;
+                const double div = gD + ac;
                 const double tDD = fma(P.two_mu, gD, P.beta*div);
                 const double tD1 = P.mu*fma(qR[2+T1] - qL[2+T1], invdxD, b);
                 const double tD2 = P.mu*fma(qR[2+T2] - qL[2+T2], invdxD, d);
@@ -183,7 +198,7 @@ namespace spb
             mbar_wait(&bars[1], 0);
 
             // Ring residency at step k: planes k-1, k, k+1 (plane index p = k + 1); plane k+2 is in flight. The slot of
-            // plane k-2 is refilled with plane k+2 right after barrier (1) of step k-1.
+            // plane k-1 is refilled with plane k+3 right after barrier (1) of step k.
             if (!is_edge)
             {
                 // ======================= compute warps: one cell column per thread =======================
@@ -194,21 +209,23 @@ namespace spb
                 // loop-carried state: density of cells k-1 and k, tangential differences of cell k-1 needed by the
                 // next z-face, and the divergence accumulator of cell k-1
                 double rhom, rho0;
-                double dpxu = 0.0, dpxw = 0.0, dpyv = 0.0, dpyw = 0.0;
+                double dpc = 0.0, dpxw = 0.0, dpyw = 0.0;
                 {
                     const double* pl = ring;
-                    rhom = pl[co]/(P.R*pl[co + 1]);
-                    rho0 = ring[PLANE_STRIDE + co]/(P.R*ring[PLANE_STRIDE + co + 1]);
+                    rhom = density(P.R, pl[co], pl[co + 1]);
+                    rho0 = density(P.R, ring[PLANE_STRIDE + co], ring[PLANE_STRIDE + co + 1]);
                     if (!active) { rhom = 1.0; rho0 = 1.0; }
                     if (VISC)
                     {
-                        dpxu = H.c0*(pl[co + 5 + 2] - pl[co - 5 + 2]);
+                        dpc  = H.c0*(pl[co + 5 + 2] - pl[co - 5 + 2]) + H.c1*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
                         dpxw = H.c0*(pl[co + 5 + 4] - pl[co - 5 + 4]);
-                        dpyv = H.c1*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
                         dpyw = H.c1*(pl[co + 5*TIp + 4] - pl[co - 5*TIp + 4]);
                     }
                 }
                 double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                double qm[5], q0[5], qp[5];                       // own column k-1, k, k+1 stays in registers
+                #pragma unroll
+                for (int v = 0; v < 5; ++v) { qm[v] = ring[co + v]; q0[v] = ring[PLANE_STRIDE + co + v]; qp[v] = q0[v]; }
                 double* rhs_col = rhs + lb*G.block_stride
                     + 5ll*((i0 + il + G.ng[0]) + (long long)G.np[0]*((j0 + jl + G.ng[1]) + (long long)G.np[1]*G.ng[2]));
                 const long long kstride = 5ll*G.np[0]*G.np[1];
@@ -216,19 +233,11 @@ namespace spb
                 for (int k = 0; k <= nz; ++k)
                 {
                     const int pk = k + 1;                       // plane index of k
-                    const double* plm = ring + ((pk - 1) & (NP - 1))*PLANE_STRIDE + co;
                     const double* plk = ring + (pk & (NP - 1))*PLANE_STRIDE + co;
                     const double* plp = ring + ((pk + 1) & (NP - 1))*PLANE_STRIDE + co;
-                    if (pk + 1 < nplanes) mbar_wait(&bars[(pk + 1) & (NP - 1)], ((pk + 1)/NP) & 1);
 
-                    double q0[5];
-                    #pragma unroll
-                    for (int v = 0; v < 5; ++v) q0[v] = plk[v];
-                    double rhop = plp[0]/(P.R*plp[1]);              // garbage at k = nz, never used
-                    if (!active) rhop = 1.0;
-
-                    // scaled central differences of cell k
-                    double dxu = 0.0, dxv = 0.0, dxw = 0.0, dyu = 0.0, dyv = 0.0, dyw = 0.0, dzu = 0.0, dzv = 0.0, dzw = 0.0;
+                    // in-plane scaled central differences of cell k (plane k has been resident since the previous step)
+                    double dxu = 0.0, dxv = 0.0, dxw = 0.0, dyu = 0.0, dyv = 0.0, dyw = 0.0;
                     if (VISC)
                     {
                         dxu = H.c0*(plk[5 + 2] - plk[-5 + 2]);
@@ -237,30 +246,14 @@ namespace spb
                         dyu = H.c1*(plk[5*TIp + 2] - plk[-5*TIp + 2]);
                         dyv = H.c1*(plk[5*TIp + 3] - plk[-5*TIp + 3]);
                         dyw = H.c1*(plk[5*TIp + 4] - plk[-5*TIp + 4]);
-                        if (k < nz)
-                        {
-                            dzu = H.c2*(plp[2] - plm[2]);
-                            dzv = H.c2*(plp[3] - plm[3]);
-                            dzw = H.c2*(plp[4] - plm[4]);
-                        }
                     }
-                    if (k < nz)
+                    const double cZ = dxu + dyv;
+                    // z-face k-1/2: registers only, overlaps the wait for plane k+1. acc carries the divergence of a cell:
+                    // lower-face fluxes are added as they are computed, the neighbours' (upper-face) fluxes are subtracted
+                    // after barrier (2).
                     {
-                        pub[P_RHO*PSZ + po] = rho0;
-                        if (VISC)
-                        {
-                            pub[P_DXU*PSZ + po] = dxu; pub[P_DXV*PSZ + po] = dxv;
-                            pub[P_DYU*PSZ + po] = dyu; pub[P_DYV*PSZ + po] = dyv;
-                            pub[P_DZU*PSZ + po] = dzu; pub[P_DZV*PSZ + po] = dzv; pub[P_DZW*PSZ + po] = dzw;
-                        }
-                    }
-                    // z-face k-1/2. acc carries the divergence of a cell: lower-face fluxes are added as they are computed,
-                    // the neighbours' (upper-face) fluxes are subtracted after barrier (2).
-                    {
-                        double qm[5], Fz[5];
-                        #pragma unroll
-                        for (int v = 0; v < 5; ++v) qm[v] = plm[v];
-                        face<CONV, VISC, 2>(P, qm, q0, rhom, rho0, dpxu + dxu, dpxw + dxw, dpyv + dyv, dpyw + dyw, H.i2, Fz);
+                        double Fz[5];
+                        face<CONV, VISC, 2>(P, qm, q0, rhom, rho0, dpc + cZ, dpxw + dxw, dpyw + dyw, H.i2, Fz);
                         if (k >= 1)
                         {
                             if (G.tma_store)
@@ -283,6 +276,31 @@ namespace spb
                         #pragma unroll
                         for (int v = 0; v < 5; ++v) acc[v] = Fz[v]*H.i2;
                     }
+                    if (pk + 1 < nplanes)
+                    {
+                        mbar_wait(&bars[(pk + 1) & (NP - 1)], ((pk + 1)/NP) & 1);
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v) qp[v] = plp[v];
+                    }
+                    double rhop = density(P.R, qp[0], qp[1]);           // stale at k = nz, never used
+                    if (!active) rhop = 1.0;
+                    double cX = 0.0, cY = 0.0, dzu = 0.0, dzv = 0.0;
+                    if (VISC && k < nz)
+                    {
+                        const double dzw = H.c2*(qp[4] - qm[4]);
+                        dzu = H.c2*(qp[2] - qm[2]);
+                        dzv = H.c2*(qp[3] - qm[3]);
+                        cX = dyv + dzw; cY = dzw + dxu;
+                    }
+                    if (k < nz)
+                    {
+                        pub[P_RHO*PSZ + po] = rho0;
+                        if (VISC)
+                        {
+                            pub[P_CX*PSZ + po] = cX; pub[P_DYU*PSZ + po] = dyu; pub[P_DZU*PSZ + po] = dzu;
+                            pub[P_CY*PSZ + po] = cY; pub[P_DZV*PSZ + po] = dzv; pub[P_DXV*PSZ + po] = dxv;
+                        }
+                    }
                     if (G.tma_store) fence_proxy_async();
                     __syncthreads();                                            // (1) published data + staged rhs visible
                     if (k < nz)
@@ -293,13 +311,9 @@ namespace spb
                             for (int v = 0; v < 5; ++v) qL[v] = plk[-5 + v];
                             const int pl_ = po - 1;
                             const double rhoL = pub[P_RHO*PSZ + pl_];
-                            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-                            if (VISC)
-                            {
-                                a = pub[P_DYV*PSZ + pl_] + dyv; b = pub[P_DYU*PSZ + pl_] + dyu;
-                                c = pub[P_DZW*PSZ + pl_] + dzw; d = pub[P_DZU*PSZ + pl_] + dzu;
-                            }
-                            face<CONV, VISC, 0>(P, qL, q0, rhoL, rho0, a, b, c, d, H.i0, F);
+                            double ac = 0.0, b = 0.0, d = 0.0;
+                            if (VISC) { ac = pub[P_CX*PSZ + pl_] + cX; b = pub[P_DYU*PSZ + pl_] + dyu; d = pub[P_DZU*PSZ + pl_] + dzu; }
+                            face<CONV, VISC, 0>(P, qL, q0, rhoL, rho0, ac, b, d, H.i0, F);
                             if (active)
                             {
                                 #pragma unroll
@@ -314,13 +328,9 @@ namespace spb
                             for (int v = 0; v < 5; ++v) qL[v] = plk[-5*TIp + v];
                             const int pl_ = po - PW;
                             const double rhoL = pub[P_RHO*PSZ + pl_];
-                            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-                            if (VISC)
-                            {
-                                a = pub[P_DZW*PSZ + pl_] + dzw; b = pub[P_DZV*PSZ + pl_] + dzv;
-                                c = pub[P_DXU*PSZ + pl_] + dxu; d = pub[P_DXV*PSZ + pl_] + dxv;
-                            }
-                            face<CONV, VISC, 1>(P, qL, q0, rhoL, rho0, a, b, c, d, H.i1, F);
+                            double ac = 0.0, b = 0.0, d = 0.0;
+                            if (VISC) { ac = pub[P_CY*PSZ + pl_] + cY; b = pub[P_DZV*PSZ + pl_] + dzv; d = pub[P_DXV*PSZ + pl_] + dxv; }
+                            face<CONV, VISC, 1>(P, qL, q0, rhoL, rho0, ac, b, d, H.i1, F);
                             if (active)
                             {
                                 #pragma unroll
@@ -341,7 +351,9 @@ namespace spb
                         }
                     }
                     rhom = rho0; rho0 = rhop;
-                    dpxu = dxu; dpxw = dxw; dpyv = dyv; dpyw = dyw;
+                    dpc = cZ; dpxw = dxw; dpyw = dyw;
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) { qm[v] = q0[v]; q0[v] = qp[v]; }
                 }
             }
             else
@@ -361,50 +373,40 @@ namespace spb
                     const double* plk = ring + (pk & (NP - 1))*PLANE_STRIDE;
                     const double* plp = ring + ((pk + 1) & (NP - 1))*PLANE_STRIDE;
                     if (pk + 1 < nplanes) mbar_wait(&bars[(pk + 1) & (NP - 1)], ((pk + 1)/NP) & 1);
-                    // ---- before (1): publish the lower halo; z-differences of the upper R cells (plane k-1 is recycled after (1))
-                    // and everything else the upper faces need from their R cells, so that the work after (1) is two faces
-                    double uDzv = 0.0, uDzw = 0.0, uDxu = 0.0, uDxv = 0.0, xDzu = 0.0, xDzw = 0.0, xDyu = 0.0, xDyv = 0.0;
+                    // ---- before (1): publish the lower halo, and prepare what the upper faces need from their R cells
+                    double uCY = 0.0, uDzv = 0.0, uDxv = 0.0, xCX = 0.0, xDyu = 0.0, xDzu = 0.0;
                     double uRho = 1.0, xRho = 1.0;
-                    if (k < nz)
-                    {
-                        if (row_on) uRho = plk[co_r1]/(P.R*plk[co_r1 + 1]);
-                        if (col_on && !col_lo) xRho = plk[co_c]/(P.R*plk[co_c + 1]);
-                        if (VISC)
-                        {
-                            uDzv = H.c2*(plp[co_r1 + 3] - plm[co_r1 + 3]);
-                            uDzw = H.c2*(plp[co_r1 + 4] - plm[co_r1 + 4]);
-                            uDxu = H.c0*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
-                            uDxv = H.c0*(plk[co_r1 + 5 + 3] - plk[co_r1 - 5 + 3]);
-                            xDzu = H.c2*(plp[co_c + 2] - plm[co_c + 2]);
-                            xDzw = H.c2*(plp[co_c + 4] - plm[co_c + 4]);
-                            xDyu = H.c1*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
-                            xDyv = H.c1*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]);
-                        }
-                    }
                     if (k < nz)
                     {
                         if (row_on)
                         {
                             const int po = pidx(lane, -1);
-                            pub[P_RHO*PSZ + po] = plk[co_r0 + 0]/(P.R*plk[co_r0 + 1]);
+                            pub[P_RHO*PSZ + po] = density(P.R, plk[co_r0], plk[co_r0 + 1]);
+                            uRho = density(P.R, plk[co_r1], plk[co_r1 + 1]);
                             if (VISC)
                             {
+                                pub[P_CY*PSZ + po]  = H.c2*(plp[co_r0 + 4] - plm[co_r0 + 4]) + H.c0*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
                                 pub[P_DZV*PSZ + po] = H.c2*(plp[co_r0 + 3] - plm[co_r0 + 3]);
-                                pub[P_DZW*PSZ + po] = H.c2*(plp[co_r0 + 4] - plm[co_r0 + 4]);
-                                pub[P_DXU*PSZ + po] = H.c0*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
                                 pub[P_DXV*PSZ + po] = H.c0*(plk[co_r0 + 5 + 3] - plk[co_r0 - 5 + 3]);
+                                uCY  = H.c2*(plp[co_r1 + 4] - plm[co_r1 + 4]) + H.c0*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
+                                uDzv = H.c2*(plp[co_r1 + 3] - plm[co_r1 + 3]);
+                                uDxv = H.c0*(plk[co_r1 + 5 + 3] - plk[co_r1 - 5 + 3]);
                             }
                         }
-                        if (col_on && col_lo)
+                        if (col_on)
                         {
-                            const int po = pidx(-1, ccj);
-                            pub[P_RHO*PSZ + po] = plk[co_c + 0]/(P.R*plk[co_c + 1]);
+                            xRho = density(P.R, plk[co_c], plk[co_c + 1]);
                             if (VISC)
                             {
-                                pub[P_DYU*PSZ + po] = H.c1*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
-                                pub[P_DYV*PSZ + po] = H.c1*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]);
-                                pub[P_DZU*PSZ + po] = H.c2*(plp[co_c + 2] - plm[co_c + 2]);
-                                pub[P_DZW*PSZ + po] = H.c2*(plp[co_c + 4] - plm[co_c + 4]);
+                                xCX  = H.c1*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]) + H.c2*(plp[co_c + 4] - plm[co_c + 4]);
+                                xDyu = H.c1*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
+                                xDzu = H.c2*(plp[co_c + 2] - plm[co_c + 2]);
+                            }
+                            if (col_lo)
+                            {
+                                const int po = pidx(-1, ccj);
+                                pub[P_RHO*PSZ + po] = xRho;
+                                if (VISC) { pub[P_CX*PSZ + po] = xCX; pub[P_DYU*PSZ + po] = xDyu; pub[P_DZU*PSZ + po] = xDzu; }
                             }
                         }
                     }
@@ -416,7 +418,8 @@ namespace spb
                             tma_store_4d(&tmap_rhs, stage, 5*i0, j0, k - 1, (int)lb);
                             tma_store_commit();
                         }
-                        // plane k-1 (index pk-1) has been consumed by every thread: refill its slot with plane pk-1+NP
+                        // plane k-1 (index pk-1) is only read before (1) (compute warps keep their column in registers):
+                        // refill its slot with plane pk-1+NP, three planes ahead of its first use
                         const int pnew = pk - 1 + NP;
                         if (pnew < nplanes)
                         {
@@ -434,15 +437,9 @@ namespace spb
                             for (int v = 0; v < 5; ++v) { qL[v] = plk[co_r1 - 5*TIp + v]; qR[v] = plk[co_r1 + v]; }
                             const int pl_ = pidx(lane, nj_t - 1);
                             const double rhoL = pub[P_RHO*PSZ + pl_];
-                            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-                            if (VISC)
-                            {
-                                a = pub[P_DZW*PSZ + pl_] + uDzw;
-                                b = pub[P_DZV*PSZ + pl_] + uDzv;
-                                c = pub[P_DXU*PSZ + pl_] + uDxu;
-                                d = pub[P_DXV*PSZ + pl_] + uDxv;
-                            }
-                            face<CONV, VISC, 1>(P, qL, qR, rhoL, uRho, a, b, c, d, H.i1, F);
+                            double ac = 0.0, b = 0.0, d = 0.0;
+                            if (VISC) { ac = pub[P_CY*PSZ + pl_] + uCY; b = pub[P_DZV*PSZ + pl_] + uDzv; d = pub[P_DXV*PSZ + pl_] + uDxv; }
+                            face<CONV, VISC, 1>(P, qL, qR, rhoL, uRho, ac, b, d, H.i1, F);
                             #pragma unroll
                             for (int v = 0; v < 5; ++v) Fy[(nj_t*TI + lane)*5 + v] = F[v];
                         }
@@ -453,20 +450,14 @@ namespace spb
                             for (int v = 0; v < 5; ++v) { qL[v] = plk[co_c - 5 + v]; qR[v] = plk[co_c + v]; }
                             const int pl_ = pidx(ni_t - 1, ccj);
                             const double rhoL = pub[P_RHO*PSZ + pl_];
-                            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-                            if (VISC)
-                            {
-                                a = pub[P_DYV*PSZ + pl_] + xDyv;
-                                b = pub[P_DYU*PSZ + pl_] + xDyu;
-                                c = pub[P_DZW*PSZ + pl_] + xDzw;
-                                d = pub[P_DZU*PSZ + pl_] + xDzu;
-                            }
-                            face<CONV, VISC, 0>(P, qL, qR, rhoL, xRho, a, b, c, d, H.i0, F);
+                            double ac = 0.0, b = 0.0, d = 0.0;
+                            if (VISC) { ac = pub[P_CX*PSZ + pl_] + xCX; b = pub[P_DYU*PSZ + pl_] + xDyu; d = pub[P_DZU*PSZ + pl_] + xDzu; }
+                            face<CONV, VISC, 0>(P, qL, qR, rhoL, xRho, ac, b, d, H.i0, F);
                             #pragma unroll
                             for (int v = 0; v < 5; ++v) Fx[(ccj*(TI + 1) + ni_t)*5 + v] = F[v];
                         }
                     }
-                    if (lane == 0 && G.tma_store) tma_store_wait_read<0>();     // staging tile may be rewritten after (2)
+                    if (lane == 0 && G.tma_store) tma_store_wait_read<0>();     // staging tile is rewritten after (2)
                     __syncthreads();                                            // (2)
                 }
                 if (lane == 0 && G.tma_store) tma_store_wait<0>();
