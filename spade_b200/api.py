@@ -406,19 +406,24 @@ class arr_exchange_t:
             if self.recv_cells[p] and p not in self._recvbuf:
                 self._recvbuf[p] = torch.empty(NVAR * self.recv_cells[p], dtype=torch.float64, device="cuda")
 
+    def sendrecv(self, sendbufs, recvbufs):
+        """exchange_message_t::send_all (exchange_message.h:14-56) over torch.distributed: one message per peer in each
+        direction, posted as one batch (NCCL groups them; gloo runs them as they come). Returns the requests."""
+        import torch.distributed as dist
+        ops = []
+        for p in sorted(recvbufs):
+            ops.append(dist.P2POp(dist.irecv, recvbufs[p], p, group=self.pool.group))
+        for p in sorted(sendbufs):
+            ops.append(dist.P2POp(dist.isend, sendbufs[p], p, group=self.pool.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
     def exchange(self, array, pool=None):
         st = _stream_ptr()
-        me = self.pool.rank()
         if self.pool.size() > 1:
-            import torch.distributed as dist
             self._buffers()
-            ops = []
-            for p, buf in self._recvbuf.items():
-                ops.append(dist.P2POp(dist.irecv, buf, p, group=self.pool.group))
             for p, buf in self._sendbuf.items():
                 check(lib().spb_exchange_pack(self._h, _dptr(array.data), p, _dptr(buf), st))
-                ops.append(dist.P2POp(dist.isend, buf, p, group=self.pool.group))
-            reqs = dist.batch_isend_irecv(ops) if ops else []
+            reqs = self.sendrecv(self._sendbuf, self._recvbuf)
             check(lib().spb_exchange_local(self._h, _dptr(array.data), st))      # overlaps the NVLink transfers
             for r in reqs:
                 r.wait()

@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Generates the committed golden vectors of tests/golden/*.npz from the UNMODIFIED reference
+(oracle/_ref/libspade_ref.so = /root/reference/src behind oracle/ref_driver.cc). Run in the dev container:
+
+    python tests/golden/make_golden.py
+
+The GPU box has no /root/reference; it checks the CUDA path and the oracle against these files.
+Reference paths exercised: flux_div_basic.h:17-77, make_exchange.h:111-410, exchange_config.h:286-419,
+advance.h:57-102,236-402, transform_reduce.h:53-191."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from util import make_state, oracle_cfg, zero_ghosts  # noqa: E402
+from oracle import ref  # noqa: E402
+
+NB, N, NG = (2, 1, 2), (8, 4, 4), 2   # multiples of 4: the reference's transform_inplace tiles are 4^3 (transform_inplace.h:34-96)
+
+
+def main():
+    assert ref.available(), "build oracle/_ref first (make -C oracle ref)"
+    out = {}
+    # (i) rhs of one flux_div for every scheme combination
+    for scheme in range(9):
+        q = make_state(NB, N, NG, seed=100 + scheme, jump=scheme in (1, 6, 8))
+        cfg = oracle_cfg(NB, N, NG, scheme=scheme)
+        out[f"fdiv_q_{scheme}"] = q
+        out[f"fdiv_rhs_{scheme}"] = ref.flux_div(cfg, q.ravel()).reshape(q.shape)
+    # (ii) exchange (ghost fill) for three periodicities
+    for tag, periodic in (("ppp", (1, 1, 1)), ("pwp", (1, 0, 1)), ("www", (0, 0, 0))):
+        q = zero_ghosts(make_state(NB, N, NG, seed=7), NG)
+        cfg = oracle_cfg(NB, N, NG, periodic=periodic)
+        out[f"exch_in_{tag}"] = q
+        out[f"exch_out_{tag}"] = ref.exchange(cfg, q.ravel()).reshape(q.shape)
+    # (iii) short RK trajectories (rk4 and the 2-register ssprk3) and the CFL reduction
+    for integ, name in ((0, "rk4"), (1, "ssprk3opt")):
+        cfg = oracle_cfg(NB, N, NG, scheme=0, integrator=integ)
+        q0 = ref.exchange(cfg, make_state(NB, N, NG, seed=13).ravel())
+        umax = ref.reduce_umax(cfg, q0)
+        dt = 0.2 * (2 * np.pi / 16) / umax
+        q1, _ = ref.advance(cfg, q0, dt, 3)
+        out[f"adv_q0_{name}"] = q0.reshape((-1,) + (N[2] + 2 * NG, N[1] + 2 * NG, N[0] + 2 * NG, 5))
+        out[f"adv_q3_{name}"] = q1.reshape(out[f"adv_q0_{name}"].shape)
+        out[f"adv_dt_{name}"] = np.array([dt, umax])
+    np.savez_compressed(os.path.join(HERE, "hotpath_small.npz"), **out)
+    # (iv) exchange tables (bit-exact integer maps) for 1/2/4/8 ranks, periodic and wall-bounded
+    tabs = {}
+    for nranks in (1, 2, 4, 8):
+        for tag, periodic in (("ppp", (1, 1, 1)), ("pwp", (1, 0, 1))):
+            cfg = oracle_cfg((2, 2, 2), (16, 16, 16), 2, periodic=periodic, nranks=nranks)
+            for rank in range(nranks):
+                s, r, o = ref.exchange_tables(cfg, rank)
+                tabs[f"send_{nranks}_{tag}_{rank}"] = s
+                tabs[f"recv_{nranks}_{tag}_{rank}"] = r
+                tabs[f"offs_{nranks}_{tag}_{rank}"] = o
+    np.savez_compressed(os.path.join(HERE, "exchange_tables.npz"), **tabs)
+    for f in ("hotpath_small.npz", "exchange_tables.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,77 @@
+"""The C-ABI shared library loads on a machine without a GPU, exports every symbol include/spade_b200.h declares,
+and refuses compute calls loudly instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "spade_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    from spade_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 25
+    lib = _lib.lib()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/spade_b200.h but not exported"
+    assert set(names) == set(_lib.SYMBOLS), "python binding table and header disagree"
+
+
+def test_no_oracle_in_product_path():
+    """the product package must not import or link anything under oracle/"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "spade_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", "Makefile")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", "").replace("oracle restatement", ""), f
+    out = os.popen(f"ldd {os.path.join(ROOT, 'spade_b200', 'libspade_b200.so')}").read()
+    assert "oracle" not in out and "spade_ref" not in out
+
+
+def test_version_and_error_convention():
+    from spade_b200 import _lib
+    lib = _lib.lib()
+    assert b"sm_100a" in lib.spb_version()
+    # bad arguments give a nonzero code and a message, never a crash
+    rc = lib.spb_exchange_create(None, _lib.int3((1, 1, 1)), _lib.int3((4, 4, 4)), _lib.int3((2, 2, 2)), _lib.int3((1, 1, 1)), 0, 1)
+    assert rc != 0 and b"spb_exchange_create" in lib.spb_last_error()
+    with pytest.raises(_lib.SpbError):
+        _lib.check(rc)
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from spade_b200 import _lib
+    lib = _lib.lib()
+    assert lib.spb_device_count() == 0
+    h = C.c_void_p()
+    bbox = np.array([0, 1, 0, 1, 0, 1], dtype=np.float64)
+    rc = lib.spb_grid_create(C.byref(h), _lib.int3((8, 8, 8)), _lib.int3((2, 2, 2)), 1, bbox.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 10003 and b"no CUDA device" in lib.spb_last_error()      # SPB_ERR_NO_DEVICE
+
+
+def test_host_mirror_tables_match_reference_rk_tables():
+    """rk_t tables (explicit.h:27-116) and the coefficient differences formed like advance.h:47-55,84-92."""
+    import spade_b200.api as sp
+    rk4 = sp.rk4_t
+    assert [[float(x) for x in r] for r in rk4.table] == [[0, 0, 0, 0], [0.5, 0, 0, 0], [0, 0.5, 0, 0], [0, 0, 1, 0]]
+    assert [float(x) for x in rk4.accum] == [1 / 6, 1 / 3, 1 / 3, 1 / 6]
+    diffs = [[sp._ratio_diff_value(c, p) for c, p in zip(cur, prev)] for prev, cur in
+             zip(rk4.table, rk4.table[1:] + [rk4.accum])]
+    assert [sum(1 for d in row if d != 0.0) for row in diffs] == [1, 2, 2, 4]      # 9 residual reads per step
+    assert diffs[3] == [1 / 6, 1 / 3, -2 / 3, 1 / 6]       # exact ratio difference, then one rounding (advance.h:47-55)
+    for alg in (sp.rk2_t, sp.ssprk3_t, sp.ssprk34_t, sp.rk38r_t, rk4):
+        assert abs(float(sum(alg.accum)) - 1.0) < 1e-15                              # consistency of every table
+        for row, c in zip(alg.table, alg.dt):
+            assert sum(row) == c
