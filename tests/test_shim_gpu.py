@@ -1,0 +1,23 @@
+"""A solver written against SPADE's own C++ API (integration/tgv_shim_demo.cc, compiled in the dev container against the
+unmodified reference headers + include/spade_b200_shim.hpp) runs the reference's generic CUDA path and the drop-in
+back to back on the GPU; the final states must agree to the north-star tolerance."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "integration", "_build", "tgv_shim_demo")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_spade_api_solver_through_the_shim(scheme):
+    if not os.path.exists(BIN):
+        pytest.skip("integration/_build/tgv_shim_demo not built (needs /root/reference at build time)")
+    out = subprocess.run([BIN, "2", "16", "2", str(scheme)], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(BIN))
+    assert out.returncode == 0, out.stdout + out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["rel_l2"] < 1e-12
+    assert line["umax"] > 300.0
