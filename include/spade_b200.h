@@ -90,6 +90,28 @@ int spb_flux_div(const spb_grid* g, const double* q_dev, double* rhs_dev, const 
 int spb_flux_div_blocks(const spb_grid* g, const double* q_dev, double* rhs_dev, const spb_flux_desc* flux,
                         int increment, int64_t lb_begin, int64_t lb_end, void* stream);
 
+/* ---- fused RK stage: flux_div + stage update in one pass over q ------------------------------
+ * Replaces the pair  rhs(k_i, q, t); detail::transform_advance_to(...)  of integrate_advance
+ * (reference src/time-integration/advance.h:254-275, 57-102) when the rhs callback is flux_div itself:
+ * with r = flux_div(q_in) on a cell,
+ *     q_out = prim( cons(q_in) + cq_self*r + cq[0]*in[0] + cq[1]*in[1] )      (interior cells; ghosts of q_out untouched)
+ *     out   = co_self*r + co[0]*in[0] + co[1]*in[1]                           (if out != NULL; may alias in[a])
+ * q is read once and the residual never makes a round trip through HBM before the update. q_out must be a
+ * different array from q_in (neighbouring cells still read q_in). Implemented for the one-ghost-cell functor
+ * set (totani_lr and/or visc_lr); other descriptors return SPB_ERR_UNSUPPORTED and the caller uses
+ * spb_flux_div + spb_rk_update. The caller folds dt and the Butcher coefficients into cq (see
+ * spade_b200/api.py::integrator_t for rk4_t). */
+typedef struct spb_stage_desc
+{
+    int           nin;          /* number of residual registers read (0..2) */
+    const double* in[2];
+    double        cq_self, cq[2];
+    double*       out;          /* residual register written, or NULL */
+    double        co_self, co[2];
+} spb_stage_desc;
+int spb_flux_div_rk_stage(const spb_grid* g, const double* q_in_dev, double* q_out_dev, const spb_flux_desc* flux,
+                          const spb_stage_desc* stage, int64_t lb_begin, int64_t lb_end, void* stream);
+
 /* ---- RK stage update: replaces detail::transform_advance_to -----------------------------------
  * reference src/time-integration/advance.h:57-102: per interior cell
  *   w = cons(q); w += sum_j coeff[j]*k_j  (only j with coeff[j] != 0, in order); q = prim(w)

@@ -17,6 +17,12 @@ class FluxDesc(C.Structure):
                 ("prandtl_inv", C.c_double), ("sensor_eps", C.c_double)]
 
 
+class StageDesc(C.Structure):
+    """spb_stage_desc (include/spade_b200.h)."""
+    _fields_ = [("nin", C.c_int), ("inp", C.c_void_p * 2), ("cq_self", C.c_double), ("cq", C.c_double * 2),
+                ("out", C.c_void_p), ("co_self", C.c_double), ("co", C.c_double * 2)]
+
+
 class SpbError(RuntimeError):
     pass
 
@@ -35,6 +41,8 @@ SYMBOLS = {
     "spb_flux_div": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.c_int, C.c_void_p]),
     "spb_flux_div_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.c_int,
                                       C.c_int64, C.c_int64, C.c_void_p]),
+    "spb_flux_div_rk_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.POINTER(StageDesc),
+                                        C.c_int64, C.c_int64, C.c_void_p]),
     "spb_rk_update": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, _dp, C.c_double,
                                 C.c_double, C.c_void_p]),
     "spb_ssprk3_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

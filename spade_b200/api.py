@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FluxDesc, SpbError, check, int3, lib
+from ._lib import FluxDesc, SpbError, StageDesc, check, int3, lib
 
 NVAR = 5
 
@@ -364,6 +364,19 @@ def flux_div(prims, rhs, flux_func, traits=increment, blocks=None):
                                         int(blocks[0]), int(blocks[1]), _stream_ptr()))
 
 
+class flux_div_rhs_t:
+    """The usual rhs callback of a SPADE solver, `[&](auto& rhs, const auto& q, const auto& t) { flux_div(q, rhs, f, traits); }`
+    (development/cuda-tgv/main.cc:174-186), as an object the integrator can recognise: integrator_t then runs the
+    fused flux_div + stage-update kernel (spb_flux_div_rk_stage) instead of two passes over q."""
+
+    def __init__(self, flux_func, traits=overwrite):
+        self.flux = flux_func if isinstance(flux_func, FluxDesc) else flux_desc(flux_func)
+        self.traits = traits
+
+    def __call__(self, rhs, q, t):
+        flux_div(q, rhs, self.flux, self.traits)
+
+
 # ---- exchange ------------------------------------------------------------------------------------------------
 class arr_exchange_t:
     """make_exchange(array, periodic) -> handle; handle.exchange(array, pool) (make_exchange.h:111-421)."""
@@ -528,17 +541,89 @@ class state_transform_t:
 
 class integrator_t:
     """integrator_t(axis, scheme, data, rhs_calc, boundary_cond, trans).advance()
-    — the fused prim/cons path of advance.h:236-280 and the ssprk3_opt path of advance.h:359-402."""
+    — the fused prim/cons path of advance.h:236-280 and the ssprk3_opt path of advance.h:359-402.
+    If rhs_calc is a flux_div_rhs_t (overwrite trait) and the functor set is supported, every stage is ONE kernel
+    (flux_div + stage update, spb_flux_div_rk_stage) writing into a second solution buffer; `fused=False` forces the
+    two-kernel path."""
 
-    def __init__(self, axis, scheme, data, rhs_calc, boundary_cond, trans):
+    def __init__(self, axis, scheme, data, rhs_calc, boundary_cond, trans, fused=True):
         self.axis, self.scheme, self.data = axis, scheme, data
         self.rhs_calc, self.boundary_cond, self.trans = rhs_calc, boundary_cond, trans
+        self._plan = None
+        self._scratch = None
+        if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
+            f = rhs_calc.flux
+            if f.diss == DISS_NONE and f.conv in (CONV_NONE, CONV_TOTANI) and (f.conv != CONV_NONE or f.visc):
+                self._plan = self._fused_plan(scheme)
 
     def solution(self):
         return self.data.solution(0)
 
     def time(self):
         return self.axis.t
+
+    @staticmethod
+    def _fused_plan(s):
+        """Per stage: which residual registers are read, which one is written, and the coefficients (without dt).
+        diffs[i][j] is the coefficient difference (a_{i+1,j} - a_{i,j}; last row: b_j - a_{n-1,j}) exactly as
+        advance.h:47-55,84-92 forms it. A final update that needs more than two earlier residuals gets their
+        combination C prepared by the stage before it (rk4: C = k0/6 + k1/3 - 2 k2/3)."""
+        n = s.rows()
+        rows = s.table + [s.accum]
+        diffs = [[_ratio_diff_value(c, p) for c, p in zip(rows[i + 1], rows[i])] for i in range(n)]
+        final_prior = [j for j in range(n - 1) if diffs[n - 1][j] != 0.0]
+        use_c = len(final_prior) > 2
+        plan = []
+        for i in range(n):
+            d = diffs[i]
+            st = {"cq_self": d[i], "in": [], "cq": [], "co": [], "out": None, "co_self": 0.0}
+            if i == n - 1 and use_c:
+                st["in"], st["cq"], st["co"] = [("c", n - 2)], [1.0], [0.0]
+            else:
+                prior = [j for j in range(i) if d[j] != 0.0]
+                extra = [j for j in final_prior if j < i and j not in prior] if (use_c and i == n - 2) else []
+                ins = sorted(prior + extra)
+                if len(ins) > 2:
+                    return None
+                st["in"] = [("k", j) for j in ins]
+                st["cq"] = [d[j] for j in ins]
+                st["co"] = [0.0] * len(ins)
+                if use_c and i == n - 2:
+                    st["out"], st["co_self"], st["co"] = ("c", n - 2), diffs[n - 1][i], [diffs[n - 1][j] for j in ins]
+                else:
+                    needed_later = any(diffs[m][i] != 0.0 for m in range(i + 1, n))
+                    if needed_later:
+                        st["out"], st["co_self"], st["co"] = ("k", i), 1.0, [0.0] * len(ins)
+            plan.append(st)
+        return plan
+
+    def _advance_fused(self):
+        ax, dt, d = self.axis, self.axis.dt, self.data
+        f = self.rhs_calc.flux
+        if self._scratch is None:
+            self._scratch = d.solution(0).clone()
+        cur, nxt = d.solution(0), self._scratch
+        s = self.scheme
+        for i, st in enumerate(self._plan):
+            sd = StageDesc()
+            sd.nin = len(st["in"])
+            for a, (_, j) in enumerate(st["in"]):
+                sd.inp[a] = d.residual(j).data.data_ptr()
+                sd.cq[a] = st["cq"][a] * dt
+                sd.co[a] = st["co"][a]
+            sd.cq_self = st["cq_self"] * dt
+            sd.out = d.residual(st["out"][1]).data.data_ptr() if st["out"] else None
+            sd.co_self = st["co_self"]
+            check(lib().spb_flux_div_rk_stage(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd),
+                                              0, cur.grid.num_local_blocks, _stream_ptr()))
+            cur, nxt = nxt, cur
+            tnext = ax.t + (float(s.dt[i + 1]) * dt if i + 1 < s.rows() else dt)
+            if i + 1 == s.rows():
+                ax.t += dt
+                tnext = ax.t
+            self.boundary_cond(cur, tnext)
+        if cur is not d.solution(0):                       # odd number of stages: the result sits in the scratch buffer
+            d.solution(0).data, self._scratch.data = self._scratch.data, d.solution(0).data
 
     def _update(self, prev_row, curr_row):
         q = self.data.solution(0)
@@ -549,6 +634,8 @@ class integrator_t:
         check(lib().spb_rk_update(q.h, _dptr(q.data), ks, nk, coeff, self.trans.gas.gamma, self.trans.gas.R, _stream_ptr()))
 
     def advance(self):
+        if self._plan is not None:
+            return self._advance_fused()
         ax, q, dt = self.axis, self.data.solution(0), self.axis.dt
         gas = self.trans.gas
         if isinstance(self.scheme, tspecial_rk3_t):

@@ -25,6 +25,18 @@ namespace spb
         int    blend;                 // SPB_BLEND_*
     };
 
+    // Fused RK stage (spb_flux_div_rk_stage): with r = rhs(q_in) of a cell,
+    //   q_out = prim(cons(q_in) + cq_self r + cq[0] in[0] + cq[1] in[1])      (advance.h:57-102, fluid_state.h:103-135)
+    //   out   = co_self r + co[0] in[0] + co[1] in[1]                         (residual register for later stages)
+    struct StageParams
+    {
+        int nin, has_out;
+        const double* in[2];
+        double cq_self, cq[2];
+        double co_self, co[2];
+        double gm1, inv_gm1, inv_R;
+    };
+
     // q_v at offset (sD along D, sT1 along (D+1)%3, sT2 along (D+2)%3) from the face's right cell
     template <int D, class A>
     __device__ __forceinline__ double qrel(const A& a, int v, int sD, int sT1, int sT2)

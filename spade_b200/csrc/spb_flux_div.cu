@@ -259,7 +259,18 @@ namespace spb
 {
     template <int CONV, int VISC>
     int launch_fdiv_narrow(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
-                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream);     // spb_flux_div_narrow.cu
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage);     // spb_flux_div_narrow.cu
+
+    static FluxParams make_params(const spb_flux_desc* f)
+    {
+        FluxParams P;
+        P.gamma = f->gamma; P.R = f->R; P.gm1 = f->gamma - 1.0; P.cv = f->R/(f->gamma - 1.0);
+        P.mu = f->mu; P.beta = f->beta; P.two_mu = 2.0*f->mu;
+        // reference viscous.h:64-68: cond = (gamma R/(gamma-1)) * (mu * prandtl_inv)
+        P.kappa = (f->gamma*f->R/(f->gamma - 1.0))*(f->mu*f->prandtl_inv);
+        P.eps = f->sensor_eps; P.blend = f->blend;
+        return P;
+    }
 }
 
 extern "C"
@@ -270,17 +281,12 @@ extern "C"
         using namespace spb;
         if (!g || !q_dev || !rhs_dev || !f) { set_error("spb_flux_div: null argument"); return SPB_ERR_BAD_ARG; }
         if (lb_begin < 0 || lb_end > g->nlb || lb_begin > lb_end) { set_error("spb_flux_div: bad block range"); return SPB_ERR_BAD_ARG; }
-        FluxParams P;
-        P.gamma = f->gamma; P.R = f->R; P.gm1 = f->gamma - 1.0; P.cv = f->R/(f->gamma - 1.0);
-        P.mu = f->mu; P.beta = f->beta; P.two_mu = 2.0*f->mu;
-        // reference viscous.h:64-68: cond = (gamma R/(gamma-1)) * (mu * prandtl_inv)
-        P.kappa = (f->gamma*f->R/(f->gamma - 1.0))*(f->mu*f->prandtl_inv);
-        P.eps = f->sensor_eps; P.blend = f->blend;
+        const FluxParams P = make_params(f);
         cudaStream_t st = (cudaStream_t)stream;
 #define SPB_CASE(C, D, V) if (f->conv == C && f->diss == D && (f->visc != 0) == (V != 0)) \
             return launch_fdiv<C, D, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st)
 #define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
-            return launch_fdiv_narrow<C, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st)
+            return launch_fdiv_narrow<C, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st, nullptr, nullptr)
         SPB_NARROW(SPB_CONV_TOTANI, 1);
         SPB_NARROW(SPB_CONV_TOTANI, 0);
         SPB_NARROW(SPB_CONV_NONE,   1);
@@ -293,6 +299,30 @@ extern "C"
         SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_FWENO, 0);
 #undef SPB_CASE
         set_error("spb_flux_div: this combination of flux functors is not in the implemented set");
+        return SPB_ERR_UNSUPPORTED;
+    }
+
+    int spb_flux_div_rk_stage(const spb_grid* g, const double* q_in, double* q_out, const spb_flux_desc* f,
+                              const spb_stage_desc* sd, int64_t lb_begin, int64_t lb_end, void* stream)
+    {
+        using namespace spb;
+        if (!g || !q_in || !q_out || !f || !sd || q_in == q_out) { set_error("spb_flux_div_rk_stage: bad argument (q_out must differ from q_in)"); return SPB_ERR_BAD_ARG; }
+        if (lb_begin < 0 || lb_end > g->nlb || lb_begin > lb_end) { set_error("spb_flux_div_rk_stage: bad block range"); return SPB_ERR_BAD_ARG; }
+        if (sd->nin < 0 || sd->nin > 2 || (sd->nin > 0 && !sd->in[0]) || (sd->nin > 1 && !sd->in[1])) { set_error("spb_flux_div_rk_stage: bad inputs"); return SPB_ERR_BAD_ARG; }
+        const FluxParams P = make_params(f);
+        StageParams S{};
+        S.nin = sd->nin; S.has_out = sd->out ? 1 : 0;
+        for (int a = 0; a < 2; ++a) { S.in[a] = a < sd->nin ? sd->in[a] : nullptr; S.cq[a] = a < sd->nin ? sd->cq[a] : 0.0; S.co[a] = a < sd->nin ? sd->co[a] : 0.0; }
+        S.cq_self = sd->cq_self; S.co_self = sd->co_self;
+        S.gm1 = f->gamma - 1.0; S.inv_gm1 = 1.0/(f->gamma - 1.0); S.inv_R = 1.0/f->R;
+        cudaStream_t st = (cudaStream_t)stream;
+#define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
+            return launch_fdiv_narrow<C, V>(g, q_in, sd->out, P, 0, lb_begin, lb_end, st, q_out, &S)
+        SPB_NARROW(SPB_CONV_TOTANI, 1);
+        SPB_NARROW(SPB_CONV_TOTANI, 0);
+        SPB_NARROW(SPB_CONV_NONE,   1);
+#undef SPB_NARROW
+        set_error("spb_flux_div_rk_stage: the fused stage is implemented for the one-ghost-cell functor set (totani_lr and/or visc_lr)");
         return SPB_ERR_UNSUPPORTED;
     }
 

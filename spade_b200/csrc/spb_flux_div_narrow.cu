@@ -30,7 +30,7 @@ namespace spb
         constexpr int NTHREADS = NCOMPUTE + 32;         // + edge warp
         constexpr int TIp = TI + 2 + 2;                 // halo + 16-byte TMA start alignment slack
         constexpr int TJp = TJ + 2;
-        constexpr int NP = 4;                           // ring slots
+        constexpr int NP = 3;                           // ring slots: planes k, k+1 resident, k+2 in flight
         constexpr int PLANE_DOUBLES = TIp*TJp*5;
         constexpr int PLANE_BYTES = PLANE_DOUBLES*8;
         constexpr int PLANE_STRIDE = ((PLANE_BYTES + 127)/128*128)/8;
@@ -39,13 +39,14 @@ namespace spb
         constexpr int NPUB = 7;                         // rho, cX, Dy.u, Dz.u, cY, Dz.v, Dx.v
         constexpr int FX_DOUBLES = TJ*(TI + 1)*5;
         constexpr int FY_DOUBLES = (TJ + 1)*TI*5;
-        constexpr int STAGE_DOUBLES = TJ*TI*5;
+        constexpr int STAGE_DOUBLES = TJ*TI*5;          // 10 240 B, a multiple of 128
         constexpr int OFF_P = NP*PLANE_STRIDE;
-        constexpr int OFF_STAGE = (OFF_P + NPUB*PSZ + 15)/16*16;          // 128-byte aligned for the TMA store
-        constexpr int OFF_FX = OFF_STAGE + STAGE_DOUBLES;
+        constexpr int OFF_STAGE_K = (OFF_P + NPUB*PSZ + 15)/16*16;        // 128-byte aligned for the TMA stores
+        constexpr int OFF_STAGE_Q = OFF_STAGE_K + STAGE_DOUBLES;
+        constexpr int OFF_FX = OFF_STAGE_Q + STAGE_DOUBLES;
         constexpr int OFF_FY = OFF_FX + FX_DOUBLES;
         constexpr int OFF_BAR = OFF_FY + FY_DOUBLES;
-        constexpr int SMEM_BYTES = (OFF_BAR + NP)*8 + 128;
+        constexpr int SMEM_BYTES = (OFF_BAR + NP + 1)*8 + 128;      // ring barriers + the input-tile barrier
 
         enum { P_RHO = 0, P_CX /* Dy.v + Dz.w */, P_DYU, P_DZU, P_CY /* Dz.w + Dx.u */, P_DZV, P_DXV };
 
@@ -60,9 +61,8 @@ namespace spb
             double idx[3], cdx[3];          // uniform lattice: 1/dx and 0.25/dx
         };
 
-        // One face of direction D. s-sums and differences are shared between the convective and the viscous part.
-        //   ac = g[T1][u_T1] + g[T2][u_T2], b = g[T1][u_D], d = g[T2][u_D]   (tangential face gradients; the two
-        //   tangential diagonal terms only enter through the divergence)
+        using Stage = spb::StageParams;
+
         // rho = p/(R T) (reference convective.h:70, fluid_state.h:105) with a Newton-refined hardware reciprocal:
         // MUFU.RCP64H seed (>= 20 bits) + 2 iterations -> relative error ~1e-16, no slow-path branch.
         __device__ __forceinline__ double density(const double R, const double p, const double T)
@@ -119,6 +119,24 @@ namespace spb
             }
         }
 
+        __device__ __forceinline__ double fast_rcp(const double a)
+        {
+            double x;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+            double e = fma(-a, x, 1.0);
+            x = fma(x, e, x);
+            e = fma(-a, x, 1.0);
+            x = fma(x, e, x);
+            return x;
+        }
+
+        __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
+        {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+        }
+        __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+        __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
         // Inverse spacings: for a uniform lattice (all blocks the same dx) they come from the kernel-parameter constant
         // bank and cost no registers; otherwise (AMR: per-block dx) they are read from the per-block table.
         template <bool UNIF> struct Spacing
@@ -135,19 +153,22 @@ namespace spb
             }
         };
 
-        template <int CONV, int VISC, bool UNIF>
+        template <int CONV, int VISC, bool UNIF, bool FUSED>
         __global__ void __launch_bounds__(NTHREADS, 2)
         flux_div_narrow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_rhs,
-                               double* __restrict__ rhs, const __grid_constant__ FluxParams P, const __grid_constant__ Dims G,
-                               const double* __restrict__ inv_dx_tab)
+                               const __grid_constant__ CUtensorMap tmap_qout, const __grid_constant__ CUtensorMap tmap_in0,
+                               const __grid_constant__ CUtensorMap tmap_in1, double* __restrict__ rhs,
+                               const __grid_constant__ FluxParams P, const __grid_constant__ Dims G,
+                               const __grid_constant__ Stage S, const double* __restrict__ inv_dx_tab)
         {
             extern __shared__ __align__(128) double smem_raw[];
-            double*   ring  = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
-            double*   pub   = ring + OFF_P;
-            double*   stage = ring + OFF_STAGE;
-            double*   Fx    = ring + OFF_FX;
-            double*   Fy    = ring + OFF_FY;
-            uint64_t* bars  = (uint64_t*)(ring + OFF_BAR);
+            double*   ring    = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
+            double*   pub     = ring + OFF_P;
+            double*   stage_k = ring + OFF_STAGE_K;     // rhs / residual-register plane on its way out (fused: also input 1 on its way in)
+            double*   stage_q = ring + OFF_STAGE_Q;     // fused: q_out plane on its way out (also input 0 on its way in)
+            double*   Fx      = ring + OFF_FX;
+            double*   Fy      = ring + OFF_FY;
+            uint64_t* bars    = (uint64_t*)(ring + OFF_BAR);
 
             const int tid = threadIdx.x;
             const int lane = tid & 31, warp = tid >> 5;
@@ -174,8 +195,9 @@ namespace spb
             {
                 prefetch_tmap(&tmap_q);
                 if (G.tma_store) prefetch_tmap(&tmap_rhs);
+                if (FUSED) { prefetch_tmap(&tmap_qout); if (S.nin > 0) prefetch_tmap(&tmap_in0); if (S.nin > 1) prefetch_tmap(&tmap_in1); }
                 #pragma unroll
-                for (int s = 0; s < NP; ++s) mbar_init(&bars[s], 1);
+                for (int s = 0; s < NP + 1; ++s) mbar_init(&bars[s], 1);
                 fence_mbar_init();
             }
             __syncthreads();
@@ -197,8 +219,9 @@ namespace spb
             mbar_wait(&bars[0], 0);
             mbar_wait(&bars[1], 0);
 
-            // Ring residency at step k: planes k-1, k, k+1 (plane index p = k + 1); plane k+2 is in flight. The slot of
-            // plane k-1 is refilled with plane k+3 right after barrier (1) of step k.
+            // Ring: plane p lives in slot p % 3. At step k (plane index pk = k + 1) planes pk and pk+1 are resident and
+            // pk+2 is in flight; plane pk is last read before barrier (2) of step k, after which its slot is re-armed
+            // with plane pk+3 (one full step ahead of its first use). Plane 0 (k = -1) is consumed by the prologue.
             if (!is_edge)
             {
                 // ======================= compute warps: one cell column per thread =======================
@@ -206,35 +229,35 @@ namespace spb
                 const bool active = (il < ni_t) && (jl < nj_t);
                 const int co = cell_off(il, jl);
                 const int po = pidx(il, jl);
-                // loop-carried state: density of cells k-1 and k, tangential differences of cell k-1 needed by the
-                // next z-face, and the divergence accumulator of cell k-1
-                double rhom, rho0;
-                double dpc = 0.0, dpxw = 0.0, dpyw = 0.0;
-                {
-                    const double* pl = ring;
-                    rhom = density(P.R, pl[co], pl[co + 1]);
-                    rho0 = density(P.R, ring[PLANE_STRIDE + co], ring[PLANE_STRIDE + co + 1]);
-                    if (!active) { rhom = 1.0; rho0 = 1.0; }
-                    if (VISC)
-                    {
-                        dpc  = H.c0*(pl[co + 5 + 2] - pl[co - 5 + 2]) + H.c1*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
-                        dpxw = H.c0*(pl[co + 5 + 4] - pl[co - 5 + 4]);
-                        dpyw = H.c1*(pl[co + 5*TIp + 4] - pl[co - 5*TIp + 4]);
-                    }
-                }
-                double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-                double qm[5], q0[5], qp[5];                       // own column k-1, k, k+1 stays in registers
+                const int so = (jl*TI + il)*5;                  // this thread's slot in the staging tiles
+                // loop-carried state: own column k-1, k, k+1; density of cells k-1 and k; tangential differences of
+                // cell k-1 needed by the next z-face; the divergence accumulator of cell k-1
+                double qm[5], q0[5], qp[5];
                 #pragma unroll
                 for (int v = 0; v < 5; ++v) { qm[v] = ring[co + v]; q0[v] = ring[PLANE_STRIDE + co + v]; qp[v] = q0[v]; }
-                double* rhs_col = rhs + lb*G.block_stride
+                double rhom = density(P.R, qm[0], qm[1]);
+                double rho0 = density(P.R, q0[0], q0[1]);
+                if (!active) { rhom = 1.0; rho0 = 1.0; }
+                double dpc = 0.0, dpxw = 0.0, dpyw = 0.0;
+                if (VISC)
+                {
+                    const double* pl = ring;
+                    dpc  = H.c0*(pl[co + 5 + 2] - pl[co - 5 + 2]) + H.c1*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
+                    dpxw = H.c0*(pl[co + 5 + 4] - pl[co - 5 + 4]);
+                    dpyw = H.c1*(pl[co + 5*TIp + 4] - pl[co - 5*TIp + 4]);
+                }
+                double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                const long long cell0 = lb*G.block_stride
                     + 5ll*((i0 + il + G.ng[0]) + (long long)G.np[0]*((j0 + jl + G.ng[1]) + (long long)G.np[1]*G.ng[2]));
                 const long long kstride = 5ll*G.np[0]*G.np[1];
+                __syncthreads();                                                // (0) plane 0 consumed
 
+                int sk = 1, sp = 2;                                             // slots of planes pk and pk+1
                 for (int k = 0; k <= nz; ++k)
                 {
                     const int pk = k + 1;                       // plane index of k
-                    const double* plk = ring + (pk & (NP - 1))*PLANE_STRIDE + co;
-                    const double* plp = ring + ((pk + 1) & (NP - 1))*PLANE_STRIDE + co;
+                    const double* plk = ring + sk*PLANE_STRIDE + co;
+                    const double* plp = ring + sp*PLANE_STRIDE + co;
 
                     // in-plane scaled central differences of cell k (plane k has been resident since the previous step)
                     double dxu = 0.0, dxv = 0.0, dxw = 0.0, dyu = 0.0, dyv = 0.0, dyw = 0.0;
@@ -256,20 +279,65 @@ namespace spb
                         face<CONV, VISC, 2>(P, qm, q0, rhom, rho0, dpc + cZ, dpxw + dxw, dpyw + dyw, H.i2, Fz);
                         if (k >= 1)
                         {
-                            if (G.tma_store)
+                            double r[5];
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) r[v] = fma(-Fz[v], H.i2, acc[v]);      // rhs of cell k-1
+                            if (FUSED)
+                            {
+                                // the inputs of this cell were fetched by cp.async into this thread's own staging slots
+                                double w[5], o[5];
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) { w[v] = S.cq_self*r[v]; o[v] = S.co_self*r[v]; }
+                                if (S.nin > 0)
+                                {
+                                    mbar_wait(&bars[NP], (k - 1) & 1);          // input tiles of cell k-1 have landed (TMA)
+                                    #pragma unroll
+                                    for (int v = 0; v < 5; ++v)
+                                    {
+                                        const double a0 = stage_q[so + v];
+                                        w[v] = fma(S.cq[0], a0, w[v]); o[v] = fma(S.co[0], a0, o[v]);
+                                    }
+                                    if (S.nin > 1)
+                                    {
+                                        #pragma unroll
+                                        for (int v = 0; v < 5; ++v)
+                                        {
+                                            const double a1 = stage_k[so + v];
+                                            w[v] = fma(S.cq[1], a1, w[v]); o[v] = fma(S.co[1], a1, o[v]);
+                                        }
+                                    }
+                                }
+                                if (S.has_out)
+                                {
+                                    #pragma unroll
+                                    for (int v = 0; v < 5; ++v) stage_k[so + v] = o[v];
+                                }
+                                // prim -> cons (fluid_state.h:103-116), add the increment, cons -> prim (fluid_state.h:119-135)
+                                const double u2 = fma(qm[2], qm[2], fma(qm[3], qm[3], qm[4]*qm[4]));
+                                const double rho  = rhom + w[0];
+                                const double rhoE = fma(0.5*rhom, u2, qm[0]*S.inv_gm1) + w[1];
+                                const double mx = fma(rhom, qm[2], w[2]), my = fma(rhom, qm[3], w[3]), mz = fma(rhom, qm[4], w[4]);
+                                const double ir = fast_rcp(active ? rho : 1.0);
+                                const double un = ir*mx, vn = ir*my, wn = ir*mz;
+                                const double pn = S.gm1*fma(-0.5*rho, fma(un, un, fma(vn, vn, wn*wn)), rhoE);
+                                stage_q[so + 0] = pn;
+                                stage_q[so + 1] = pn*ir*S.inv_R;
+                                stage_q[so + 2] = un; stage_q[so + 3] = vn; stage_q[so + 4] = wn;
+                            }
+                            else if (G.tma_store)
                             {
                                 #pragma unroll
-                                for (int v = 0; v < 5; ++v) stage[(jl*TI + il)*5 + v] = fma(-Fz[v], H.i2, acc[v]);
+                                for (int v = 0; v < 5; ++v) stage_k[so + v] = r[v];
                             }
                             else if (active)
                             {
-                                double* o = rhs_col + (long long)(k - 1)*kstride;
+                                double* o = rhs + cell0 + (long long)(k - 1)*kstride;
                                 #pragma unroll
                                 for (int v = 0; v < 5; ++v)
                                 {
-                                    double r = fma(-Fz[v], H.i2, acc[v]);
-                                    if (G.increment) r += o[v];
-                                    o[v] = r;
+                                    double rr = r[v];
+                                    if (G.increment) rr += o[v];
+                                    o[v] = rr;
                                 }
                             }
                         }
@@ -278,7 +346,7 @@ namespace spb
                     }
                     if (pk + 1 < nplanes)
                     {
-                        mbar_wait(&bars[(pk + 1) & (NP - 1)], ((pk + 1)/NP) & 1);
+                        mbar_wait(&bars[sp], ((pk + 1)/NP) & 1);
                         #pragma unroll
                         for (int v = 0; v < 5; ++v) qp[v] = plp[v];
                     }
@@ -302,7 +370,7 @@ namespace spb
                         }
                     }
                     if (G.tma_store) fence_proxy_async();
-                    __syncthreads();                                            // (1) published data + staged rhs visible
+                    __syncthreads();                                            // (1) published data + staged planes visible
                     if (k < nz)
                     {
                         {
@@ -340,7 +408,7 @@ namespace spb
                             for (int v = 0; v < 5; ++v) acc[v] = fma(F[v], H.i1, acc[v]);
                         }
                     }
-                    __syncthreads();                                            // (2) fluxes visible; pub free
+                    __syncthreads();                                            // (2) fluxes visible; pub, plane k, staging tiles free
                     if (k < nz)
                     {
                         #pragma unroll
@@ -354,6 +422,7 @@ namespace spb
                     dpc = cZ; dpxw = dxw; dpyw = dyw;
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) { qm[v] = q0[v]; q0[v] = qp[v]; }
+                    sk = sp; sp = (sp + 1 == NP) ? 0 : sp + 1;
                 }
             }
             else
@@ -366,13 +435,34 @@ namespace spb
                 const bool col_lo = lane < 8, col_on = (lane < 16) && (ccj < nj_t);
                 const int  cci = col_lo ? -1 : ni_t;
                 const int co_r0 = cell_off(lane, -1), co_r1 = cell_off(lane, nj_t), co_c = cell_off(cci, ccj);
+                // z-neighbours (k-1, k) of the edge cells roll through registers: v,w for the row cells, u,w for the column cell
+                double r0m[2], r00[2], r1m[2], r10[2], ccm[2], cc0[2];
+                {
+                    const double* pa = ring; const double* pb = ring + PLANE_STRIDE;
+                    r0m[0] = pa[co_r0 + 3]; r0m[1] = pa[co_r0 + 4]; r00[0] = pb[co_r0 + 3]; r00[1] = pb[co_r0 + 4];
+                    r1m[0] = pa[co_r1 + 3]; r1m[1] = pa[co_r1 + 4]; r10[0] = pb[co_r1 + 3]; r10[1] = pb[co_r1 + 4];
+                    ccm[0] = pa[co_c + 2];  ccm[1] = pa[co_c + 4];  cc0[0] = pb[co_c + 2];  cc0[1] = pb[co_c + 4];
+                }
+                __syncthreads();                                                // (0) plane 0 consumed
+                if (lane == 0 && NP < nplanes)
+                {
+                    mbar_arrive_expect_tx(&bars[0], PLANE_BYTES);
+                    tma_load_4d(ring, &tmap_q, &bars[0], c0, c1, c2base + NP, (int)lb);
+                }
+                int sk = 1, sp = 2;
                 for (int k = 0; k <= nz; ++k)
                 {
                     const int pk = k + 1;
-                    const double* plm = ring + ((pk - 1) & (NP - 1))*PLANE_STRIDE;
-                    const double* plk = ring + (pk & (NP - 1))*PLANE_STRIDE;
-                    const double* plp = ring + ((pk + 1) & (NP - 1))*PLANE_STRIDE;
-                    if (pk + 1 < nplanes) mbar_wait(&bars[(pk + 1) & (NP - 1)], ((pk + 1)/NP) & 1);
+                    const double* plk = ring + sk*PLANE_STRIDE;
+                    const double* plp = ring + sp*PLANE_STRIDE;
+                    double r0p[2] = {0.0, 0.0}, r1p[2] = {0.0, 0.0}, ccp[2] = {0.0, 0.0};
+                    if (pk + 1 < nplanes)
+                    {
+                        mbar_wait(&bars[sp], ((pk + 1)/NP) & 1);
+                        r0p[0] = plp[co_r0 + 3]; r0p[1] = plp[co_r0 + 4];
+                        r1p[0] = plp[co_r1 + 3]; r1p[1] = plp[co_r1 + 4];
+                        ccp[0] = plp[co_c + 2];  ccp[1] = plp[co_c + 4];
+                    }
                     // ---- before (1): publish the lower halo, and prepare what the upper faces need from their R cells
                     double uCY = 0.0, uDzv = 0.0, uDxv = 0.0, xCX = 0.0, xDyu = 0.0, xDzu = 0.0;
                     double uRho = 1.0, xRho = 1.0;
@@ -385,11 +475,11 @@ namespace spb
                             uRho = density(P.R, plk[co_r1], plk[co_r1 + 1]);
                             if (VISC)
                             {
-                                pub[P_CY*PSZ + po]  = H.c2*(plp[co_r0 + 4] - plm[co_r0 + 4]) + H.c0*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
-                                pub[P_DZV*PSZ + po] = H.c2*(plp[co_r0 + 3] - plm[co_r0 + 3]);
+                                pub[P_CY*PSZ + po]  = H.c2*(r0p[1] - r0m[1]) + H.c0*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
+                                pub[P_DZV*PSZ + po] = H.c2*(r0p[0] - r0m[0]);
                                 pub[P_DXV*PSZ + po] = H.c0*(plk[co_r0 + 5 + 3] - plk[co_r0 - 5 + 3]);
-                                uCY  = H.c2*(plp[co_r1 + 4] - plm[co_r1 + 4]) + H.c0*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
-                                uDzv = H.c2*(plp[co_r1 + 3] - plm[co_r1 + 3]);
+                                uCY  = H.c2*(r1p[1] - r1m[1]) + H.c0*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
+                                uDzv = H.c2*(r1p[0] - r1m[0]);
                                 uDxv = H.c0*(plk[co_r1 + 5 + 3] - plk[co_r1 - 5 + 3]);
                             }
                         }
@@ -398,9 +488,9 @@ namespace spb
                             xRho = density(P.R, plk[co_c], plk[co_c + 1]);
                             if (VISC)
                             {
-                                xCX  = H.c1*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]) + H.c2*(plp[co_c + 4] - plm[co_c + 4]);
+                                xCX  = H.c1*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]) + H.c2*(ccp[1] - ccm[1]);
                                 xDyu = H.c1*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
-                                xDzu = H.c2*(plp[co_c + 2] - plm[co_c + 2]);
+                                xDzu = H.c2*(ccp[0] - ccm[0]);
                             }
                             if (col_lo)
                             {
@@ -411,22 +501,11 @@ namespace spb
                         }
                     }
                     __syncthreads();                                            // (1)
-                    if (lane == 0)
+                    if (lane == 0 && G.tma_store && k >= 1)
                     {
-                        if (G.tma_store && k >= 1)
-                        {
-                            tma_store_4d(&tmap_rhs, stage, 5*i0, j0, k - 1, (int)lb);
-                            tma_store_commit();
-                        }
-                        // plane k-1 (index pk-1) is only read before (1) (compute warps keep their column in registers):
-                        // refill its slot with plane pk-1+NP, three planes ahead of its first use
-                        const int pnew = pk - 1 + NP;
-                        if (pnew < nplanes)
-                        {
-                            const int s = (pk - 1) & (NP - 1);
-                            mbar_arrive_expect_tx(&bars[s], PLANE_BYTES);
-                            tma_load_4d(ring + s*PLANE_STRIDE, &tmap_q, &bars[s], c0, c1, c2base + pnew, (int)lb);
-                        }
+                        if (!FUSED || S.has_out) tma_store_4d(&tmap_rhs, stage_k, 5*i0, j0, k - 1, (int)lb);
+                        if (FUSED) tma_store_4d(&tmap_qout, stage_q, 5*i0, j0, k - 1, (int)lb);
+                        tma_store_commit();
                     }
                     if (k < nz)
                     {
@@ -457,50 +536,94 @@ namespace spb
                             for (int v = 0; v < 5; ++v) Fx[(ccj*(TI + 1) + ni_t)*5 + v] = F[v];
                         }
                     }
-                    if (lane == 0 && G.tma_store) tma_store_wait_read<0>();     // staging tile is rewritten after (2)
+                    if (lane == 0 && G.tma_store) tma_store_wait_read<0>();     // staging tiles are rewritten after (2)
                     __syncthreads();                                            // (2)
+                    if (FUSED && lane == 0 && S.nin > 0 && k < nz)
+                    {
+                        // input tiles of cell plane k (its rhs completes in the next step) land in the staging tiles, which
+                        // the stores of plane k-1 have finished reading (wait_read above)
+                        mbar_arrive_expect_tx(&bars[NP], (uint32_t)(STAGE_DOUBLES*8*S.nin));
+                        tma_load_4d(stage_q, &tmap_in0, &bars[NP], 5*i0, j0, k, (int)lb);
+                        if (S.nin > 1) tma_load_4d(stage_k, &tmap_in1, &bars[NP], 5*i0, j0, k, (int)lb);
+                        if (k + 1 < nz)                                          // next plane's tiles: into L2 now
+                        {
+                            tma_prefetch_4d(&tmap_in0, 5*i0, j0, k + 1, (int)lb);
+                            if (S.nin > 1) tma_prefetch_4d(&tmap_in1, 5*i0, j0, k + 1, (int)lb);
+                        }
+                    }
+                    if (lane == 0)
+                    {
+                        // plane pk has been consumed by every thread: re-arm its slot with plane pk + NP
+                        const int pnew = pk + NP;
+                        if (pnew < nplanes)
+                        {
+                            mbar_arrive_expect_tx(&bars[sk], PLANE_BYTES);
+                            tma_load_4d(ring + sk*PLANE_STRIDE, &tmap_q, &bars[sk], c0, c1, c2base + pnew, (int)lb);
+                            if (pnew + 1 < nplanes) tma_prefetch_4d(&tmap_q, c0, c1, c2base + pnew + 1, (int)lb);   // and the one after into L2
+                        }
+                    }
+                    r0m[0] = r00[0]; r0m[1] = r00[1]; r00[0] = r0p[0]; r00[1] = r0p[1];
+                    r1m[0] = r10[0]; r1m[1] = r10[1]; r10[0] = r1p[0]; r10[1] = r1p[1];
+                    ccm[0] = cc0[0]; ccm[1] = cc0[1]; cc0[0] = ccp[0]; cc0[1] = ccp[1];
+                    sk = sp; sp = (sp + 1 == NP) ? 0 : sp + 1;
                 }
                 if (lane == 0 && G.tma_store) tma_store_wait<0>();
             }
         }
+
+        static int make_map(CUtensorMap* m, const void* base, const cuuint64_t dims[4], const cuuint64_t strides[3],
+                            const cuuint32_t box[4], CUtensorMapL2promotion prom, const char* what)
+        {
+            encode_tiled_fn enc = get_encode_tiled();
+            if (!enc) { set_error("spb_flux_div: cuTensorMapEncodeTiled not available from the driver"); return SPB_ERR_DRIVER; }
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult cr = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) { set_error(std::string("spb_flux_div: cuTensorMapEncodeTiled(") + what + ") failed with CUresult " + std::to_string((int)cr)); return SPB_ERR_DRIVER; }
+            return 0;
+        }
     }
 
+    // stage == nullptr: plain flux_div; otherwise the fused RK stage (q_out, stage description)
     template <int CONV, int VISC>
     int launch_fdiv_narrow(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
-                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream)
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const nrw::Stage* stage)
     {
         using namespace nrw;
         for (int d = 0; d < 3; ++d)
             if (g->ng[d] < 1) { set_error("spb_flux_div: scheme needs 1 exchange cell"); return SPB_ERR_BAD_ARG; }
         if ((5*g->np[0]) % 2 != 0) { set_error("spb_flux_div: n0 + 2*g0 must be even (16-byte TMA row pitch)"); return SPB_ERR_UNSUPPORTED; }
-        encode_tiled_fn enc = get_encode_tiled();
-        if (!enc) { set_error("spb_flux_div: cuTensorMapEncodeTiled not available from the driver"); return SPB_ERR_DRIVER; }
 
-        CUtensorMap tq, tr;
-        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUtensorMap tq, tr, tqo, ti0, ti1;
+        const cuuint64_t strides[3] = {(cuuint64_t)40*g->np[0], (cuuint64_t)40*g->np[0]*g->np[1], (cuuint64_t)8*g->block_stride};
         {
-            const cuuint64_t dims[4]    = {(cuuint64_t)5*g->np[0], (cuuint64_t)g->np[1], (cuuint64_t)g->np[2], (cuuint64_t)g->nlb};
-            const cuuint64_t strides[3] = {(cuuint64_t)40*g->np[0], (cuuint64_t)40*g->np[0]*g->np[1], (cuuint64_t)8*g->block_stride};
-            const cuuint32_t box[4]     = {(cuuint32_t)(5*TIp), (cuuint32_t)TJp, 1, 1};
-            CUresult cr = enc(&tq, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)q, dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (cr != CUDA_SUCCESS) { set_error("spb_flux_div: cuTensorMapEncodeTiled(q) failed with CUresult " + std::to_string((int)cr)); return SPB_ERR_DRIVER; }
+            const cuuint64_t dims[4] = {(cuuint64_t)5*g->np[0], (cuuint64_t)g->np[1], (cuuint64_t)g->np[2], (cuuint64_t)g->nlb};
+            const cuuint32_t box[4]  = {(cuuint32_t)(5*TIp), (cuuint32_t)TJp, 1, 1};
+            int rc = make_map(&tq, q, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "q"); if (rc) return rc;
         }
-        // interior-only view of rhs for the tensor store: the hardware clips ragged tiles to the interior
+        // interior-only views for the tensor stores: the hardware clips ragged tiles to the interior
         const long long org = 5ll*(g->ng[0] + (long long)g->np[0]*(g->ng[1] + (long long)g->np[1]*g->ng[2]));
-        int tma_store = (!increment && (org % 2 == 0) && (((uintptr_t)rhs) % 16 == 0)) ? 1 : 0;
-        if (tma_store)
-        {
-            const cuuint64_t dims[4]    = {(cuuint64_t)5*g->nx[0], (cuuint64_t)g->nx[1], (cuuint64_t)g->nx[2], (cuuint64_t)g->nlb};
-            const cuuint64_t strides[3] = {(cuuint64_t)40*g->np[0], (cuuint64_t)40*g->np[0]*g->np[1], (cuuint64_t)8*g->block_stride};
-            const cuuint32_t box[4]     = {(cuuint32_t)(5*TI), (cuuint32_t)TJ, 1, 1};
-            CUresult cr = enc(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)(rhs + org), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (cr != CUDA_SUCCESS) tma_store = 0;
-        }
+        const cuuint64_t idims[4] = {(cuuint64_t)5*g->nx[0], (cuuint64_t)g->nx[1], (cuuint64_t)g->nx[2], (cuuint64_t)g->nlb};
+        const cuuint32_t ibox[4]  = {(cuuint32_t)(5*TI), (cuuint32_t)TJ, 1, 1};
+        const bool aligned = (org % 2 == 0);
+        int tma_store = (!increment && aligned && rhs && (((uintptr_t)rhs) % 16 == 0)) ? 1 : 0;
+        if (tma_store && make_map(&tr, rhs + org, idims, strides, ibox, CU_TENSOR_MAP_L2_PROMOTION_NONE, "rhs")) tma_store = 0;
         if (!tma_store) tr = tq;
+        tqo = tq;
+        if (stage)
+        {
+            if (!aligned || !q_out || (((uintptr_t)q_out) % 16 != 0) || (stage->has_out && !tma_store))
+            { set_error("spb_flux_div_rk_stage: arrays must be 16-byte aligned with an even interior origin"); return SPB_ERR_UNSUPPORTED; }
+            int rc = make_map(&tqo, q_out + org, idims, strides, ibox, CU_TENSOR_MAP_L2_PROMOTION_NONE, "q_out"); if (rc) return rc;
+            tma_store = 1;
+        }
+        ti0 = tq; ti1 = tq;
+        if (stage)
+            for (int a = 0; a < stage->nin; ++a)
+            {
+                if (((uintptr_t)stage->in[a]) % 16 != 0) { set_error("spb_flux_div_rk_stage: input arrays must be 16-byte aligned"); return SPB_ERR_UNSUPPORTED; }
+                int rc = make_map(a == 0 ? &ti0 : &ti1, stage->in[a] + org, idims, strides, ibox, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "in"); if (rc) return rc;
+            }
 
         Dims G;
         for (int d = 0; d < 3; ++d) { G.nx[d] = g->nx[d]; G.ng[d] = g->ng[d]; G.np[d] = g->np[d]; }
@@ -516,18 +639,21 @@ namespace spb
         for (int64_t b = lb_begin; b < lb_end && uniform; ++b)
             for (int d = 0; d < 3; ++d) uniform = uniform && (g->inv_dx_host[3*b + d] == g->inv_dx_host[3*lb_begin + d]);
         for (int d = 0; d < 3; ++d) { G.idx[d] = g->inv_dx_host[3*lb_begin + d]; G.cdx[d] = 0.25*G.idx[d]; }
+        Stage S{};
+        if (stage) S = *stage;
         auto go = [&](auto kern) -> int
         {
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, rhs, P, G, g->inv_dx_dev);
+            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev);
             SPB_LAUNCH_CHECK();
             return 0;
         };
-        return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true>) : go(flux_div_narrow_kernel<CONV, VISC, false>);
+        if (stage) return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, true>) : go(flux_div_narrow_kernel<CONV, VISC, false, true>);
+        return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, false>) : go(flux_div_narrow_kernel<CONV, VISC, false, false>);
     }
 
-    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t);
-    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 0>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t);
-    template int launch_fdiv_narrow<SPB_CONV_NONE, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t);
+    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*);
+    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 0>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*);
+    template int launch_fdiv_narrow<SPB_CONV_NONE, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*);
 }

@@ -59,6 +59,12 @@ namespace spb
             "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
             :: "l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
     }
+    // global -> L2 only (no shared memory, no barrier): warms the tile a step before the real load
+    __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tmap, int c0, int c1, int c2, int c3)
+    {
+        asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+            :: "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    }
     __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
     template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
     template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }

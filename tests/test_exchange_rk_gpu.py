@@ -77,7 +77,7 @@ def test_reductions():
     assert sp.transform_reduce(qa, sp.FN_ABSVAR, sp.RED_MAX, gas, ivar=4) == np.abs(qi[..., 4]).max()
 
 
-def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1)):
+def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1), fused=False):
     sp, blocks, grid = product_setup(nb, n, ng)
     gas = sp.ideal_gas_t(GAMMA, RGAS)
     qa = sp.grid_array.from_host(grid, q)
@@ -86,9 +86,10 @@ def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1)
     flux = sp.flux_desc(product_flux(scheme))
     alg = {0: sp.rk4_t, 1: sp.ssprk3_opt, 2: sp.ssprk3_t, 3: sp.rk2_t}[integ]
     data = sp.integrator_data_t(qa, ra, alg)
-    ti = sp.integrator_t(sp.time_axis_t(0.0, dt), alg, data,
-                         lambda r, qq, t: sp.flux_div(qq, r, flux, sp.overwrite),
+    rhs_calc = sp.flux_div_rhs_t(flux, sp.overwrite) if fused else (lambda r, qq, t: sp.flux_div(qq, r, flux, sp.overwrite))
+    ti = sp.integrator_t(sp.time_axis_t(0.0, dt), alg, data, rhs_calc,
                          lambda qq, t: ex.exchange(qq), sp.state_transform_t(gas))
+    assert (ti._plan is not None) == fused
     for _ in range(nsteps):
         ti.advance()
     return ti.solution().to_host()
@@ -107,6 +108,25 @@ def test_rk_trajectory_matches_oracle(integ):
     got = _advance_product(nb, n, ng, q0, 0, integ, dt, 5)
     assert rel_l2(got, want) < 1e-12
     assert rel_l2(got - q0, want - q0) < 1e-9      # the increment itself, not just the state
+
+
+@pytest.mark.parametrize("integ", [0, 2, 3])
+@pytest.mark.parametrize("scheme", [0, 3, 4])
+def test_fused_stage_kernel_trajectory_matches_oracle(integ, scheme):
+    """flux_div + RK stage update in one kernel (spb_flux_div_rk_stage), rk4 (with the pre-combined final update),
+    ssprk3 (odd number of stages: result ends in the second buffer) and rk2; blocks that are not multiples of the tile."""
+    from oracle import port
+    nb, n, ng = (2, 1, 2), (40, 12, 8), 2
+    q0 = make_state(nb, n, ng, seed=23)
+    cfg = oracle_cfg(nb, n, ng, scheme=scheme, integrator=integ)
+    q0 = port.exchange(cfg, q0.ravel()).reshape(q0.shape)
+    dt = 0.2 * (2 * np.pi / 80) / port.reduce_umax(cfg, q0.ravel())
+    want = port.advance(cfg, q0.ravel(), dt, 3).reshape(q0.shape)
+    got = _advance_product(nb, n, ng, q0, scheme, integ, dt, 3, fused=True)
+    assert rel_l2(got, want) < 1e-12
+    assert rel_l2(got - q0, want - q0) < 1e-9
+    unfused = _advance_product(nb, n, ng, q0, scheme, integ, dt, 3, fused=False)
+    assert rel_l2(got, unfused) < 1e-13
 
 
 def test_rk4_hybrid_weno_trajectory_and_conservation():

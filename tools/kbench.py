@@ -69,8 +69,28 @@ def main():
         kp = (C.c_void_p * nk)(*[k.data.data_ptr() for k in ks[:nk]])
         sp.check(lib.spb_rk_update(q.h, C.c_void_p(q.data.data_ptr()), kp, nk, coeff, gas.gamma, gas.R, None))
 
+    import ctypes as C
+    lib = sp.lib()
     timeit(f"flux_div[{a.scheme}]", lambda: sp.flux_div(q, ks[0], flux, sp.overwrite), 80.0)
     timeit(f"flux_div_incr[{a.scheme}]", lambda: sp.flux_div(q, ks[0], flux, sp.increment), 120.0)
+    q2 = q.clone()
+    from spade_b200._lib import StageDesc
+
+    def fused(nin, out):
+        sd = StageDesc()
+        sd.nin = nin
+        for i in range(nin):
+            sd.inp[i] = ks[i].data.data_ptr()
+            sd.cq[i] = dt
+            sd.co[i] = 0.5
+        sd.cq_self, sd.co_self = dt, 1.0
+        sd.out = ks[2].data.data_ptr() if out else None
+        sp.check(lib.spb_flux_div_rk_stage(q.h, C.c_void_p(q.data.data_ptr()), C.c_void_p(q2.data.data_ptr()), C.byref(flux),
+                                           C.byref(sd), 0, grid.num_local_blocks, None))
+
+    if a.scheme in ("central", "euler"):
+        for nin, out in ((0, 1), (1, 1), (2, 1), (1, 0)):
+            timeit(f"fused_stage[nin={nin},out={out}]", lambda nin=nin, out=out: fused(nin, out), 80.0 + 40.0 * nin + 40.0 * out)
     timeit("exchange", lambda: ex.exchange(q), 80.0 * ghost_frac)
     for nk in (1, 2, 4):
         timeit(f"rk_update[nk={nk}]", lambda nk=nk: rk(nk), 80.0 + 40.0 * nk)
