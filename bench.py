@@ -31,6 +31,9 @@ STAGES = 4
 BLOCK = 32          # cells per block edge
 NG = 2
 LATTICE_1GPU = (16, 16, 16)
+# dram__bytes_read.sum + dram__bytes_write.sum per interior cell from the committed `ncu --set full` capture of the
+# dominant kernel (profiles/), None until a capture exists for that kernel
+TRAFFIC_PER_CELL = {"fused": None, "rhs": None}
 
 
 def parse():
@@ -41,6 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lattice", type=int, nargs=3, default=None, help="blocks per GPU (default 16 16 16)")
     ap.add_argument("--scheme", default="central", choices=["central", "hybrid"])
+    ap.add_argument("--unfused", action="store_true", help="two kernels per stage (flux_div, then rk_update) instead of the fused stage kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -227,19 +231,25 @@ def ours(args):
 
     ev_pairs = []
     timing_on = [False]
+    fused = (not args.unfused) and args.scheme == "central"
 
-    def calc_rhs(r, qq, t):
+    def calc_rhs_unfused(r, qq, t):
         if timing_on[0]:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             sp.flux_div(qq, r, flux, sp.overwrite)
             e1.record()
-            ev_pairs.append((e0, e1))
+            ev_pairs.append((e0, e1, 80.0))
         else:
             sp.flux_div(qq, r, flux, sp.overwrite)
 
-    def bc(qq, t):
-        handle.exchange(qq)
+    # the usual SPADE rhs callback (flux_div with the overwrite trait); as a flux_div_rhs_t the integrator recognises it and
+    # runs flux_div + stage update as ONE kernel per stage
+    calc_rhs = sp.flux_div_rhs_t(flux, sp.overwrite) if fused else calc_rhs_unfused
+
+    # the usual periodic boundary callback (exchange only); as an exchange_bc_t the integrator can send the ghost messages of
+    # the rank-boundary blocks while it advances the rank-interior blocks
+    bc = sp.exchange_bc_t(handle)
 
     alg = sp.rk4_t
     data = sp.integrator_data_t(q, rhs, alg)
@@ -258,6 +268,8 @@ def ours(args):
         sampler.start()
     launches0 = sp.launch_count()
     timing_on[0] = True
+    if fused:
+        ti.stage_events = ev_pairs
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
@@ -266,10 +278,12 @@ def ours(args):
     t1.record()
     barrier()
     timing_on[0] = False
+    ti.stage_events = None
     ms = t0.elapsed_time(t1)
     launches = sp.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    fdiv_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(1, len(ev_pairs))
+    fdiv_ms = sum(a.elapsed_time(b) for a, b, _ in ev_pairs) / max(1, len(ev_pairs))
+    fdiv_bpc = sum(c for _, _, c in ev_pairs) / max(1, len(ev_pairs))      # algorithmic bytes per cell, mean over launches
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -282,15 +296,33 @@ def ours(args):
     total_cells = local_cells * n
     value = total_cells * STAGES * args.steps / (ms * 1e-3)
 
-    # roofline of the dominant kernel (flux_div): 80 algorithmic bytes per interior cell
+    # roofline of the dominant kernel. Algorithmic bytes per interior cell: plain flux_div reads q and
+    # writes rhs = 80 B; the fused stage kernel reads q, writes q' and reads/writes the residual registers its stage needs:
+    # rk4 = 120, 160, 200, 120 B (mean 150 B per launch).
     peak, peak_src = measured_peak_hbm()
-    fdiv_bytes = 80.0 * local_cells
+    fdiv_bytes = fdiv_bpc * local_cells
     achieved = fdiv_bytes / (fdiv_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "flux_div_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "ms_per_launch": fdiv_ms, "launches_timed": len(ev_pairs),
+    roofline = {"bound": "hbm", "kernel": "flux_div_narrow_kernel<FUSED stage>" if fused else "flux_div kernel (rhs only)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": TRAFFIC_PER_CELL.get("fused" if fused else "rhs") and
+                TRAFFIC_PER_CELL["fused" if fused else "rhs"] * local_cells, "peak_source": peak_src,
+                "alg_bytes_per_cell": fdiv_bpc, "ms_per_launch": fdiv_ms, "launches_timed": len(ev_pairs),
                 "cell_evals_per_s": local_cells / (fdiv_ms * 1e-3),
                 "step_share": fdiv_ms * STAGES * args.steps / ms}
+    # the RHS alone (pde_algs::flux_div with the overwrite trait, 80 B per cell), timed after the run for the record
+    for _ in range(2):
+        sp.flux_div(q, rhs, flux, sp.overwrite)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    r0.record()
+    for _ in range(5):
+        sp.flux_div(q, rhs, flux, sp.overwrite)
+    r1.record()
+    torch.cuda.synchronize()
+    rhs_ms = r0.elapsed_time(r1) / 5
+    roofline["rhs_only"] = {"kernel": "flux_div (overwrite)", "alg_bytes_per_cell": 80.0, "ms_per_launch": rhs_ms,
+                            "achieved": 80.0 * local_cells / (rhs_ms * 1e-3) / 1e9,
+                            "frac": 80.0 * local_cells / (rhs_ms * 1e-3) / 1e9 / peak}
 
     # end to end through the public API with host buffers: every step the state comes from pinned host memory
     # and the step's metric (max wavespeed for the CFL number, as in development/cuda-tgv/main.cc:228) goes back

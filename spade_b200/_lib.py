@@ -23,6 +23,9 @@ class StageDesc(C.Structure):
                 ("out", C.c_void_p), ("co_self", C.c_double), ("co", C.c_double * 2)]
 
 
+SPB_ERR_BAD_ARG, SPB_ERR_UNSUPPORTED, SPB_ERR_NO_DEVICE, SPB_ERR_DRIVER = 10001, 10002, 10003, 10004
+
+
 class SpbError(RuntimeError):
     pass
 
@@ -43,6 +46,8 @@ SYMBOLS = {
                                       C.c_int64, C.c_int64, C.c_void_p]),
     "spb_flux_div_rk_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.POINTER(StageDesc),
                                         C.c_int64, C.c_int64, C.c_void_p]),
+    "spb_flux_div_rk_stage_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.POINTER(StageDesc),
+                                                 C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "spb_rk_update": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, _dp, C.c_double,
                                 C.c_double, C.c_void_p]),
     "spb_ssprk3_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

@@ -391,6 +391,7 @@ class arr_exchange_t:
         self.send_cells = [int(lib().spb_exchange_send_cells(self._h, p)) for p in range(self.pool.size())]
         self.recv_cells = [int(lib().spb_exchange_recv_cells(self._h, p)) for p in range(self.pool.size())]
         self._sendbuf, self._recvbuf = {}, {}
+        self._runs, self._reqs = None, []
 
     def __del__(self):
         try:
@@ -430,20 +431,73 @@ class arr_exchange_t:
             ops.append(dist.P2POp(dist.isend, sendbufs[p], p, group=self.pool.group))
         return dist.batch_isend_irecv(ops) if ops else []
 
-    def exchange(self, array, pool=None):
-        st = _stream_ptr()
+    def boundary_block_runs(self):
+        """Local block ranges [b0, b1) that own a cell another rank needs (the source blocks of the off-rank send
+        transactions), as sorted disjoint runs, and the complementary runs: the stage kernel runs on the first set, its
+        messages leave, and the second set is computed while they are in flight."""
+        if self._runs is None:
+            send, _, _ = self.tables()
+            nlb = self.grid.num_local_blocks
+            me = self.pool.rank()
+            mark = np.zeros(nlb + 1, dtype=bool)
+            off = send[send[:, 2] != me]
+            mark[off[:, 8]] = True
+            mark[nlb] = False
+
+            def runs(flag):
+                out, b = [], 0
+                while b < nlb:
+                    if mark[b] == flag:
+                        e = b
+                        while e < nlb and mark[e] == flag:
+                            e += 1
+                        out.append((b, e))
+                        b = e
+                    else:
+                        b += 1
+                return out
+            self._runs = (runs(True), runs(False))
+        return self._runs
+
+    def begin(self, array):
+        """First half of exchange(): pack the off-rank messages and post the sends/receives (NCCL runs them on its own
+        stream, ordered after the packs). Kernels launched after this call overlap the NVLink transfers."""
+        self._reqs = []
         if self.pool.size() > 1:
+            st = _stream_ptr()
             self._buffers()
             for p, buf in self._sendbuf.items():
                 check(lib().spb_exchange_pack(self._h, _dptr(array.data), p, _dptr(buf), st))
-            reqs = self.sendrecv(self._sendbuf, self._recvbuf)
-            check(lib().spb_exchange_local(self._h, _dptr(array.data), st))      # overlaps the NVLink transfers
-            for r in reqs:
-                r.wait()
+            self._reqs = self.sendrecv(self._sendbuf, self._recvbuf)
+
+    def finish(self, array, local=True):
+        """Second half: same-rank ghost copies, then wait for the messages and unpack them."""
+        st = _stream_ptr()
+        if local:
+            check(lib().spb_exchange_local(self._h, _dptr(array.data), st))
+        for r in self._reqs:
+            r.wait()
+        self._reqs = []
+        if self.pool.size() > 1:
             for p, buf in self._recvbuf.items():
                 check(lib().spb_exchange_unpack(self._h, _dptr(array.data), p, _dptr(buf), st))
-        else:
-            check(lib().spb_exchange_local(self._h, _dptr(array.data), st))
+
+    def exchange(self, array, pool=None):
+        self.begin(array)
+        self.finish(array)          # the same-rank copies overlap the NVLink transfers
+
+
+class exchange_bc_t:
+    """The usual boundary callback of a periodic SPADE solver, `[&](auto& q, const auto& t) { handle.exchange(q, pool); }`
+    (development/cuda-tgv/main.cc:188-191), as an object the integrator can recognise: with a fused stage plan the
+    rank-boundary blocks are advanced first, their ghost messages leave over NVLink, and the rank-interior blocks are
+    advanced while the messages are in flight."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __call__(self, q, t):
+        self.handle.exchange(q)
 
 
 def make_exchange(array, periodic):
@@ -546,11 +600,13 @@ class integrator_t:
     (flux_div + stage update, spb_flux_div_rk_stage) writing into a second solution buffer; `fused=False` forces the
     two-kernel path."""
 
-    def __init__(self, axis, scheme, data, rhs_calc, boundary_cond, trans, fused=True):
+    def __init__(self, axis, scheme, data, rhs_calc, boundary_cond, trans, fused=True, fuse_exchange=True):
         self.axis, self.scheme, self.data = axis, scheme, data
         self.rhs_calc, self.boundary_cond, self.trans = rhs_calc, boundary_cond, trans
         self._plan = None
         self._scratch = None
+        self._fuse_exchange = bool(fuse_exchange)
+        self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
         if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
             f = rhs_calc.flux
             if f.diss == DISS_NONE and f.conv in (CONV_NONE, CONV_TOTANI) and (f.conv != CONV_NONE or f.visc):
@@ -614,14 +670,42 @@ class integrator_t:
             sd.cq_self = st["cq_self"] * dt
             sd.out = d.residual(st["out"][1]).data.data_ptr() if st["out"] else None
             sd.co_self = st["co_self"]
-            check(lib().spb_flux_div_rk_stage(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd),
-                                              0, cur.grid.num_local_blocks, _stream_ptr()))
+            ex = self.boundary_cond.handle if isinstance(self.boundary_cond, exchange_bc_t) else None
+            overlap = ex is not None and ex.pool.size() > 1
+            runs_first, runs_second = ex.boundary_block_runs() if overlap else ([(0, cur.grid.num_local_blocks)], [])
+
+            def launch(b0, b1):
+                # with a recognised exchange handle the kernel also fills the same-rank ghost cells of q_out
+                if ex is not None and self._fuse_exchange:
+                    rc = lib().spb_flux_div_rk_stage_exchange(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd),
+                                                              ex._h, b0, b1, _stream_ptr())
+                    if rc != _lib.SPB_ERR_UNSUPPORTED:
+                        return check(rc)
+                    self._fuse_exchange = False                  # plan not canonical: separate same-rank copy from now on
+                check(lib().spb_flux_div_rk_stage(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd),
+                                                  b0, b1, _stream_ptr()))
+
+            if self.stage_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            for b0, b1 in runs_first:
+                launch(b0, b1)
+            if overlap:
+                ex.begin(nxt)
+                for b0, b1 in runs_second:
+                    launch(b0, b1)
+            if self.stage_events is not None:
+                e1.record()
+                self.stage_events.append((e0, e1, 80.0 + 40.0 * sd.nin + (40.0 if st["out"] else 0.0)))
             cur, nxt = nxt, cur
             tnext = ax.t + (float(s.dt[i + 1]) * dt if i + 1 < s.rows() else dt)
             if i + 1 == s.rows():
                 ax.t += dt
                 tnext = ax.t
-            self.boundary_cond(cur, tnext)
+            if ex is not None:
+                ex.finish(cur, local=not self._fuse_exchange)
+            else:
+                self.boundary_cond(cur, tnext)
         if cur is not d.solution(0):                       # odd number of stages: the result sits in the scratch buffer
             d.solution(0).data, self._scratch.data = self._scratch.data, d.solution(0).data
 

@@ -76,6 +76,7 @@ extern "C"
     {
         if (!g) return;
         if (g->inv_dx_dev) cudaFree(g->inv_dx_dev);
+        if (g->red_scratch) cudaFree(g->red_scratch);
         delete g;
     }
 

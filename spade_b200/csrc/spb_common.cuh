@@ -27,6 +27,16 @@ namespace spb
     encode_tiled_fn get_encode_tiled();
 }
 
+struct spb_exchange;
+namespace spb
+{
+    // Same-rank neighbour table of an exchange plan for the fused stage kernel (spb_exchange.cu): d_nbr[27*lb + e],
+    // e = (ex+1) + 3*(ey+1) + 9*(ez+1), is the local block whose ghost cells receive block lb's cells in direction
+    // (ex,ey,ez) through a same-rank transaction, -1 if there is none (off-rank, domain boundary, e = 13).
+    // SPB_ERR_UNSUPPORTED if a same-rank transaction is not one of the 26 canonical injection boxes.
+    int exchange_fuse_table(spb_exchange* e, const int nx[3], const int ng[3], int64_t nlb, const int** d_nbr);
+}
+
 #define SPB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return spb::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
 #define SPB_LAUNCH_CHECK() do { spb::g_launches.fetch_add(1, std::memory_order_relaxed); cudaError_t e__ = cudaGetLastError(); \
     if (e__ != cudaSuccess) return spb::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); } while (0)
@@ -43,4 +53,7 @@ struct spb_grid
     std::vector<double> inv_dx_host;  // [nlb][3]
     double* inv_dx_dev;               // [nlb][3]
     int     num_sms;
+    // scratch of spb_reduce (partials | result | counter), owned by the handle so a reduction never allocates
+    mutable double* red_scratch = nullptr;
+    mutable int64_t red_cap = 0;
 };

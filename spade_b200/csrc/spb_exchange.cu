@@ -43,6 +43,10 @@ struct spb_exchange
     spb::DevTrans* d_send = nullptr; spb::DevTrans* d_recv = nullptr;
     std::vector<std::vector<spb::WorkItem>> items_send, items_recv;   // per peer
     std::vector<spb::WorkItem*> d_items_send, d_items_recv;
+    // same-rank neighbour table for the fused stage kernel: 0 = not built, 1 = built, -1 = plan not canonical
+    int fuse_state = 0;
+    int* d_nbr = nullptr;
+    int64_t nbr_blocks = 0;
 };
 
 namespace spb
@@ -128,6 +132,52 @@ namespace spb
         rc = build(e->recv, e->recv_rank_off, e->recv_rank_cnt, false, &e->d_recv, e->items_recv, e->d_items_recv);
         if (rc) return rc;
         e->dev_ready = true;
+        return 0;
+    }
+
+    int exchange_fuse_table(spb_exchange* e, const int nx[3], const int ng[3], int64_t nlb, const int** d_nbr)
+    {
+        if (!e || !d_nbr) { set_error("exchange_fuse_table: null argument"); return SPB_ERR_BAD_ARG; }
+        for (int d = 0; d < 3; ++d)
+            if (e->nx[d] != nx[d] || e->ng[d] != ng[d]) { set_error("fused exchange: the plan was made for another block shape"); return SPB_ERR_BAD_ARG; }
+        if (e->fuse_state == 0 || (e->fuse_state == 1 && e->nbr_blocks != nlb))
+        {
+            if (e->d_nbr) { cudaFree(e->d_nbr); e->d_nbr = nullptr; }
+            std::vector<int> nbr(27*(size_t)std::max<int64_t>(nlb, 1), -1);
+            bool ok = true;
+            for (const auto& t: e->send)
+            {
+                if (t.f[2] != e->rank) continue;                       // off-rank: packed into a message
+                int code = 0, mul = 1;
+                for (int d = 0; d < 3 && ok; ++d)
+                {
+                    const int64_t smin = t.f[5+d], size = t.f[9+d], dmin = t.f[12+d];
+                    int ed;
+                    if (size == nx[d] && smin == 0 && dmin == 0) ed = 0;
+                    else if (size == ng[d] && smin == 0 && dmin == nx[d]) ed = -1;
+                    else if (size == ng[d] && smin == nx[d] - ng[d] && dmin == -ng[d]) ed = 1;
+                    else { ok = false; break; }
+                    code += (ed + 1)*mul; mul *= 3;
+                }
+                const int64_t src = t.f[8], dst = t.f[15];
+                if (!ok || code == 13 || src < 0 || src >= nlb || dst < 0 || dst >= nlb || nbr[27*src + code] != -1) { ok = false; break; }
+                nbr[27*src + code] = (int)dst;
+            }
+            if (!ok) e->fuse_state = -1;
+            else
+            {
+                SPB_CUDA(cudaMalloc((void**)&e->d_nbr, sizeof(int)*nbr.size()));
+                SPB_CUDA(cudaMemcpy(e->d_nbr, nbr.data(), sizeof(int)*nbr.size(), cudaMemcpyHostToDevice));
+                e->nbr_blocks = nlb;
+                e->fuse_state = 1;
+            }
+        }
+        if (e->fuse_state != 1)
+        {
+            set_error("fused exchange: the plan holds same-rank transactions that are not canonical injection boxes (use spb_exchange_local)");
+            return SPB_ERR_UNSUPPORTED;
+        }
+        *d_nbr = e->d_nbr;
         return 0;
     }
 
@@ -238,6 +288,7 @@ extern "C"
         if (!e) return;
         if (e->d_send) cudaFree(e->d_send);
         if (e->d_recv) cudaFree(e->d_recv);
+        if (e->d_nbr) cudaFree(e->d_nbr);
         for (auto p: e->d_items_send) if (p) cudaFree(p);
         for (auto p: e->d_items_recv) if (p) cudaFree(p);
         delete e;

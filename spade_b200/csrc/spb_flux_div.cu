@@ -259,7 +259,8 @@ namespace spb
 {
     template <int CONV, int VISC>
     int launch_fdiv_narrow(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
-                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage);     // spb_flux_div_narrow.cu
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage,
+                           spb_exchange* exch);     // spb_flux_div_narrow.cu
 
     static FluxParams make_params(const spb_flux_desc* f)
     {
@@ -286,7 +287,7 @@ extern "C"
 #define SPB_CASE(C, D, V) if (f->conv == C && f->diss == D && (f->visc != 0) == (V != 0)) \
             return launch_fdiv<C, D, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st)
 #define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
-            return launch_fdiv_narrow<C, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st, nullptr, nullptr)
+            return launch_fdiv_narrow<C, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st, nullptr, nullptr, nullptr)
         SPB_NARROW(SPB_CONV_TOTANI, 1);
         SPB_NARROW(SPB_CONV_TOTANI, 0);
         SPB_NARROW(SPB_CONV_NONE,   1);
@@ -305,6 +306,12 @@ extern "C"
     int spb_flux_div_rk_stage(const spb_grid* g, const double* q_in, double* q_out, const spb_flux_desc* f,
                               const spb_stage_desc* sd, int64_t lb_begin, int64_t lb_end, void* stream)
     {
+        return spb_flux_div_rk_stage_exchange(g, q_in, q_out, f, sd, nullptr, lb_begin, lb_end, stream);
+    }
+
+    int spb_flux_div_rk_stage_exchange(const spb_grid* g, const double* q_in, double* q_out, const spb_flux_desc* f,
+                                       const spb_stage_desc* sd, spb_exchange* exch, int64_t lb_begin, int64_t lb_end, void* stream)
+    {
         using namespace spb;
         if (!g || !q_in || !q_out || !f || !sd || q_in == q_out) { set_error("spb_flux_div_rk_stage: bad argument (q_out must differ from q_in)"); return SPB_ERR_BAD_ARG; }
         if (lb_begin < 0 || lb_end > g->nlb || lb_begin > lb_end) { set_error("spb_flux_div_rk_stage: bad block range"); return SPB_ERR_BAD_ARG; }
@@ -317,7 +324,7 @@ extern "C"
         S.gm1 = f->gamma - 1.0; S.inv_gm1 = 1.0/(f->gamma - 1.0); S.inv_R = 1.0/f->R;
         cudaStream_t st = (cudaStream_t)stream;
 #define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
-            return launch_fdiv_narrow<C, V>(g, q_in, sd->out, P, 0, lb_begin, lb_end, st, q_out, &S)
+            return launch_fdiv_narrow<C, V>(g, q_in, sd->out, P, 0, lb_begin, lb_end, st, q_out, &S, exch)
         SPB_NARROW(SPB_CONV_TOTANI, 1);
         SPB_NARROW(SPB_CONV_TOTANI, 0);
         SPB_NARROW(SPB_CONV_NONE,   1);

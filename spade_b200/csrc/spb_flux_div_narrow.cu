@@ -46,7 +46,18 @@ namespace spb
         constexpr int OFF_FX = OFF_STAGE_Q + STAGE_DOUBLES;
         constexpr int OFF_FY = OFF_FX + FX_DOUBLES;
         constexpr int OFF_BAR = OFF_FY + FY_DOUBLES;
-        constexpr int SMEM_BYTES = (OFF_BAR + NP + 1)*8 + 128;      // ring barriers + the input-tile barrier
+        // fused ghost exchange: the cells of the tile that feed the neighbours' LOW ghost cells sit at the high end of the
+        // tile, and TMA stores fault on negative coordinates (measured on B200, tools/probes/tma_store_probe.cu), so a store
+        // cannot be shifted left/down and clipped. x: those cells are copied into a dense mini tile (XHI: all rows, XHC: the
+        // rows that also feed a y-low ghost box); y: the source pointer is advanced by whole rows (1280 B, stays 128-aligned).
+        constexpr int GMAX = 4;                         // exchange cells supported by the mini tiles
+        constexpr int OFF_XHI = (OFF_BAR + NP + 1 + 15)/16*16;
+        constexpr int XHI_DOUBLES = TJ*5*GMAX;          // 1280 B
+        constexpr int OFF_XLO = OFF_XHI + XHI_DOUBLES;  // x-low source cells, dense, so their store does not walk the whole tile
+        constexpr int XC_DOUBLES = (GMAX*5*GMAX + 15)/16*16;
+        constexpr int OFF_XHC = OFF_XLO + XHI_DOUBLES;  // corner copies: the y-high rows of XHI / XLO
+        constexpr int OFF_XLC = OFF_XHC + XC_DOUBLES;
+        constexpr int SMEM_BYTES = (OFF_XLC + XC_DOUBLES)*8 + 128;
 
         enum { P_RHO = 0, P_CX /* Dy.v + Dz.w */, P_DYU, P_DZU, P_CY /* Dz.w + Dx.u */, P_DZV, P_DXV };
 
@@ -58,8 +69,14 @@ namespace spb
             long long lb0;
             int increment;
             int tma_store;
+            int ghost;                      // fused stage: also store the finished q planes into the same-rank neighbours' ghost cells
             double idx[3], cdx[3];          // uniform lattice: 1/dx and 0.25/dx
         };
+
+        // One tensor map per neighbour direction e = (ex+1) + 3*(ey+1) + 9*(ez+1): a view of q_out whose extents are exactly
+        // the destination ghost box of that direction (get_transaction.h:54-86), so a whole staged tile can be stored at a
+        // shifted coordinate and the hardware clips everything that is not a ghost cell of that box.
+        struct GhostMaps { CUtensorMap m[27]; };
 
         using Stage = spb::StageParams;
 
@@ -159,7 +176,8 @@ namespace spb
                                const __grid_constant__ CUtensorMap tmap_qout, const __grid_constant__ CUtensorMap tmap_in0,
                                const __grid_constant__ CUtensorMap tmap_in1, double* __restrict__ rhs,
                                const __grid_constant__ FluxParams P, const __grid_constant__ Dims G,
-                               const __grid_constant__ Stage S, const double* __restrict__ inv_dx_tab)
+                               const __grid_constant__ Stage S, const double* __restrict__ inv_dx_tab,
+                               const __grid_constant__ GhostMaps GM, const int* __restrict__ nbr_tab)
         {
             extern __shared__ __align__(128) double smem_raw[];
             double*   ring    = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
@@ -169,6 +187,10 @@ namespace spb
             double*   Fx      = ring + OFF_FX;
             double*   Fy      = ring + OFF_FY;
             uint64_t* bars    = (uint64_t*)(ring + OFF_BAR);
+            double*   xhi     = ring + OFF_XHI;         // fused ghost exchange: x-high source cells of the q_out plane, dense
+            double*   xlo     = ring + OFF_XLO;         // ... x-low source cells
+            double*   xhc     = ring + OFF_XHC;         // ... and the rows of XHI / XLO that are also y-high source cells
+            double*   xlc     = ring + OFF_XLC;
 
             const int tid = threadIdx.x;
             const int lane = tid & 31, warp = tid >> 5;
@@ -320,9 +342,35 @@ namespace spb
                                 const double ir = fast_rcp(active ? rho : 1.0);
                                 const double un = ir*mx, vn = ir*my, wn = ir*mz;
                                 const double pn = S.gm1*fma(-0.5*rho, fma(un, un, fma(vn, vn, wn*wn)), rhoE);
+                                const double Tn = pn*ir*S.inv_R;
                                 stage_q[so + 0] = pn;
-                                stage_q[so + 1] = pn*ir*S.inv_R;
+                                stage_q[so + 1] = Tn;
                                 stage_q[so + 2] = un; stage_q[so + 3] = vn; stage_q[so + 4] = wn;
+                                if (G.ghost)
+                                {
+                                    // tile-local start of the x-high / y-high source cells (get_transaction.h:54-86, edge = +1)
+                                    const int ti_ = (int)(blockIdx.x % G.tiles_i);
+                                    const int xi = il - (G.nx[0] - G.ng[0] - ti_*TI);
+                                    const bool lo = (ti_ == 0) && (il < G.ng[0]), hi = (unsigned)xi < (unsigned)G.ng[0];
+                                    if (lo || hi)
+                                    {
+                                        const int rowp = 5*G.ng[0];
+                                        const int yj = jl - (G.nx[1] - G.ng[1] - (int)((blockIdx.x / G.tiles_i) % G.tiles_j)*TJ);
+                                        const bool yh = (unsigned)yj < (unsigned)G.ng[1];
+                                        if (lo)
+                                        {
+                                            double* d = xlo + jl*rowp + 5*il;
+                                            d[0] = pn; d[1] = Tn; d[2] = un; d[3] = vn; d[4] = wn;
+                                            if (yh) { double* c = xlc + yj*rowp + 5*il; c[0] = pn; c[1] = Tn; c[2] = un; c[3] = vn; c[4] = wn; }
+                                        }
+                                        if (hi)
+                                        {
+                                            double* d = xhi + jl*rowp + 5*xi;
+                                            d[0] = pn; d[1] = Tn; d[2] = un; d[3] = vn; d[4] = wn;
+                                            if (yh) { double* c = xhc + yj*rowp + 5*xi; c[0] = pn; c[1] = Tn; c[2] = un; c[3] = vn; c[4] = wn; }
+                                        }
+                                    }
+                                }
                             }
                             else if (G.tma_store)
                             {
@@ -443,6 +491,29 @@ namespace spb
                     r1m[0] = pa[co_r1 + 3]; r1m[1] = pa[co_r1 + 4]; r10[0] = pb[co_r1 + 3]; r10[1] = pb[co_r1 + 4];
                     ccm[0] = pa[co_c + 2];  ccm[1] = pa[co_c + 4];  cc0[0] = pb[co_c + 2];  cc0[1] = pb[co_c + 4];
                 }
+                // fused ghost exchange: lane e < 27 owns neighbour direction e. The (ex, ey) part of "does this tile hold cells
+                // of the source box" is fixed per CTA, the ez part depends on the plane.
+                int gdst = -1, gc0 = 0, gc1 = 0, gzs = 0, gez = 0;
+                const double* gsrc = stage_q;
+                if (FUSED && G.ghost && lane < 27 && lane != 13)
+                {
+                    const int ex = lane % 3 - 1, ey = (lane/3) % 3 - 1;
+                    gez = lane/9 - 1;
+                    const int xhi0 = G.nx[0] - G.ng[0] - i0, yhi0 = G.nx[1] - G.ng[1] - j0;      // tile-local start of the +1 source cells
+                    const bool need_x = (ex == 0) || (ex < 0 ? (i0 < G.ng[0]) : (xhi0 >= 0 && xhi0 < TI));
+                    const bool need_y = (ey == 0) || (ey < 0 ? (j0 < G.ng[1]) : (yhi0 >= 0 && yhi0 < TJ));
+                    if (need_x && need_y) gdst = nbr_tab[27*lb + lane];
+                    // destination views start at the ghost box (host side), so coordinates are never negative:
+                    //   ex == 0: rows of the staged tile (ey > 0: from the first y-high row), clipped on the right by the view
+                    //   ex != 0: the dense mini tiles (ey > 0: their corner copies)
+                    // and the box of each view holds only the rows it can use (TJ rows, or ng[1] rows for ey != 0)
+                    gc0 = ex == 0 ? 5*i0 : 0;
+                    gc1 = ey > 0 ? 0 : j0;
+                    gsrc = ex == 0 ? (ey > 0 ? stage_q + yhi0*(5*TI) : stage_q)
+                                   : (ex > 0 ? (ey > 0 ? xhc : xhi) : (ey > 0 ? xlc : xlo));
+                    gzs = gez > 0 ? nz - G.ng[2] : 0;
+                    prefetch_tmap(&GM.m[lane]);
+                }
                 __syncthreads();                                                // (0) plane 0 consumed
                 if (lane == 0 && NP < nplanes)
                 {
@@ -507,6 +578,16 @@ namespace spb
                         if (FUSED) tma_store_4d(&tmap_qout, stage_q, 5*i0, j0, k - 1, (int)lb);
                         tma_store_commit();
                     }
+                    if (FUSED && gdst >= 0 && k >= 1)
+                    {
+                        const int kk = k - 1;                                    // plane of q_out sitting in stage_q
+                        const bool need_z = (gez == 0) || (gez < 0 ? (kk < G.ng[2]) : (kk >= nz - G.ng[2]));
+                        if (need_z)
+                        {
+                            tma_store_4d(&GM.m[lane], gsrc, gc0, gc1, kk - gzs, gdst);
+                            tma_store_commit();
+                        }
+                    }
                     if (k < nz)
                     {
                         if (row_on)                                              // upper y-face (lane, nj_t)
@@ -536,7 +617,7 @@ namespace spb
                             for (int v = 0; v < 5; ++v) Fx[(ccj*(TI + 1) + ni_t)*5 + v] = F[v];
                         }
                     }
-                    if (lane == 0 && G.tma_store) tma_store_wait_read<0>();     // staging tiles are rewritten after (2)
+                    if (G.tma_store && (lane == 0 || gdst >= 0)) tma_store_wait_read<0>();     // staging tiles are rewritten after (2)
                     __syncthreads();                                            // (2)
                     if (FUSED && lane == 0 && S.nin > 0 && k < nz)
                     {
@@ -567,7 +648,7 @@ namespace spb
                     ccm[0] = cc0[0]; ccm[1] = cc0[1]; cc0[0] = ccp[0]; cc0[1] = ccp[1];
                     sk = sp; sp = (sp + 1 == NP) ? 0 : sp + 1;
                 }
-                if (lane == 0 && G.tma_store) tma_store_wait<0>();
+                if (G.tma_store && (lane == 0 || gdst >= 0)) tma_store_wait<0>();
             }
         }
 
@@ -587,7 +668,8 @@ namespace spb
     // stage == nullptr: plain flux_div; otherwise the fused RK stage (q_out, stage description)
     template <int CONV, int VISC>
     int launch_fdiv_narrow(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
-                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const nrw::Stage* stage)
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const nrw::Stage* stage,
+                           spb_exchange* exch)
     {
         using namespace nrw;
         for (int d = 0; d < 3; ++d)
@@ -625,8 +707,41 @@ namespace spb
                 int rc = make_map(a == 0 ? &ti0 : &ti1, stage->in[a] + org, idims, strides, ibox, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "in"); if (rc) return rc;
             }
 
+        // fused same-rank ghost exchange: q_out's ghost boxes as 26 clipped views (reference boxes: get_transaction.h:54-86)
+        static thread_local GhostMaps GM;
+        const int* nbr_tab = nullptr;
+        if (stage && exch)
+        {
+            if (g->ng[0] % 2 != 0) { set_error("fused exchange: an odd number of exchange cells along i breaks the 16-byte TMA alignment (use spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
+            int rc = exchange_fuse_table(exch, g->nx, g->ng, g->nlb, &nbr_tab); if (rc) return rc;
+            for (int d = 0; d < 2; ++d)
+            {
+                const int T = d == 0 ? TI : TJ;
+                if (g->ng[d] > GMAX || g->ng[d] > g->nx[d] || (g->nx[d] - g->ng[d])/T != (g->nx[d] - 1)/T)
+                { set_error("fused exchange: the high source box straddles two tiles or has more than 4 exchange cells (use spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
+            }
+            const long long cstride[3] = {5ll, 5ll*g->np[0], 5ll*g->np[0]*g->np[1]};
+            // box of a view: x: the staged tile row (ex = 0) or a dense mini tile row; y: TJ rows, or only the ng[1] source rows
+            for (int e = 0; e < 27; ++e)
+            {
+                if (e == 13) { GM.m[e] = tqo; continue; }
+                const int ed[3] = {e % 3 - 1, (e/3) % 3 - 1, e/9 - 1};
+                long long shift = 0;
+                cuuint64_t gd[4];
+                for (int d = 0; d < 3; ++d)
+                {
+                    shift += cstride[d]*(ed[d] == 0 ? 0 : (ed[d] < 0 ? g->nx[d] : -g->ng[d]));
+                    gd[d] = (cuuint64_t)(ed[d] == 0 ? g->nx[d] : g->ng[d]);
+                }
+                gd[0] *= 5; gd[3] = (cuuint64_t)g->nlb;
+                const cuuint32_t gbox[4] = {(cuuint32_t)(ed[0] == 0 ? 5*TI : 5*g->ng[0]), (cuuint32_t)(ed[1] == 0 ? TJ : g->ng[1]), 1, 1};
+                rc = make_map(&GM.m[e], q_out + org + shift, gd, strides, gbox, CU_TENSOR_MAP_L2_PROMOTION_NONE, "q_out ghost box"); if (rc) return rc;
+            }
+        }
+
         Dims G;
         for (int d = 0; d < 3; ++d) { G.nx[d] = g->nx[d]; G.ng[d] = g->ng[d]; G.np[d] = g->np[d]; }
+        G.ghost = nbr_tab ? 1 : 0;
         G.tiles_i = (g->nx[0] + TI - 1)/TI;
         G.tiles_j = (g->nx[1] + TJ - 1)/TJ;
         G.block_stride = g->block_stride;
@@ -635,9 +750,15 @@ namespace spb
         G.tma_store = tma_store;
         const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
         if (nblk <= 0) return 0;
+        // A lattice counts as uniform when the per-block spacings agree to 8 ulp: box.size/num_cell formed block by block
+        // (cartesian_grid.h:134-135) wobbles in the last bit with the block origin, which is 1e-16 relative in the rhs.
         bool uniform = true;
         for (int64_t b = lb_begin; b < lb_end && uniform; ++b)
-            for (int d = 0; d < 3; ++d) uniform = uniform && (g->inv_dx_host[3*b + d] == g->inv_dx_host[3*lb_begin + d]);
+            for (int d = 0; d < 3; ++d)
+            {
+                const double a = g->inv_dx_host[3*b + d], r = g->inv_dx_host[3*lb_begin + d];
+                uniform = uniform && (fabs(a - r) <= 8.0*2.220446049250313e-16*fabs(r));
+            }
         for (int d = 0; d < 3; ++d) { G.idx[d] = g->inv_dx_host[3*lb_begin + d]; G.cdx[d] = 0.25*G.idx[d]; }
         Stage S{};
         if (stage) S = *stage;
@@ -645,7 +766,7 @@ namespace spb
         {
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev);
+            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev, GM, nbr_tab);
             SPB_LAUNCH_CHECK();
             return 0;
         };
@@ -653,7 +774,7 @@ namespace spb
         return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, false>) : go(flux_div_narrow_kernel<CONV, VISC, false, false>);
     }
 
-    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*);
-    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 0>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*);
-    template int launch_fdiv_narrow<SPB_CONV_NONE, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*);
+    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*, spb_exchange*);
+    template int launch_fdiv_narrow<SPB_CONV_TOTANI, 0>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*, spb_exchange*);
+    template int launch_fdiv_narrow<SPB_CONV_NONE, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*, spb_exchange*);
 }

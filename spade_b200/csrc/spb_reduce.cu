@@ -76,8 +76,13 @@ extern "C" int spb_reduce(const spb_grid* g, const double* q_dev, int op, int fn
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    double* scratch = nullptr;                       // partials[nb] | result | counter
-    SPB_CUDA(cudaMallocAsync((void**)&scratch, sizeof(double)*(nb + 2), st));
+    if (g->red_cap < nb + 2)                         // partials[nb] | result | counter, kept in the grid handle
+    {
+        if (g->red_scratch) { SPB_CUDA(cudaFree(g->red_scratch)); g->red_scratch = nullptr; g->red_cap = 0; }
+        SPB_CUDA(cudaMalloc((void**)&g->red_scratch, sizeof(double)*(nb + 2)));
+        g->red_cap = nb + 2;
+    }
+    double* scratch = g->red_scratch;
     double* result = scratch + nb;
     unsigned int* counter = (unsigned int*)(scratch + nb + 1);
     SPB_CUDA(cudaMemsetAsync(counter, 0, sizeof(double), st));
@@ -85,11 +90,10 @@ extern "C" int spb_reduce(const spb_grid* g, const double* q_dev, int op, int fn
     SPB_RCASE(SPB_RED_MAX, SPB_FN_WAVESPEED); else SPB_RCASE(SPB_RED_MAX, SPB_FN_VAR); else SPB_RCASE(SPB_RED_MAX, SPB_FN_ABSVAR);
     else SPB_RCASE(SPB_RED_MAX, SPB_FN_KINETIC); else SPB_RCASE(SPB_RED_SUM, SPB_FN_WAVESPEED); else SPB_RCASE(SPB_RED_SUM, SPB_FN_VAR);
     else SPB_RCASE(SPB_RED_SUM, SPB_FN_ABSVAR); else SPB_RCASE(SPB_RED_SUM, SPB_FN_KINETIC);
-    else { cudaFreeAsync(scratch, st); set_error("spb_reduce: unknown op/fn"); return SPB_ERR_BAD_ARG; }
+    else { set_error("spb_reduce: unknown op/fn"); return SPB_ERR_BAD_ARG; }
 #undef SPB_RCASE
     SPB_LAUNCH_CHECK();
     SPB_CUDA(cudaMemcpyAsync(out_host, result, sizeof(double), cudaMemcpyDeviceToHost, st));
-    SPB_CUDA(cudaFreeAsync(scratch, st));
     SPB_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

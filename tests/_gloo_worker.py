@@ -85,6 +85,16 @@ def main():
     assert np.array_equal(q, want[first:first + nloc]), f"rank {rank}: exchanged ghosts differ from the oracle"
     lib().spb_exchange_destroy(h)
 
+    # --- overlap schedule: the runs of rank-boundary blocks are exactly the source blocks of the off-rank sends
+    blocks = sp.cartesian_blocks_t(nb, [0.0, 1.0] * 3)
+    grid = sp.cartesian_grid_t(n, blocks, sp.identity(), pool)
+    handle = sp.arr_exchange_t(grid, (ng,) * 3, periodic)
+    first_runs, second_runs = handle.boundary_block_runs()
+    covered = sorted(b for b0, b1 in first_runs for b in range(b0, b1))
+    assert covered == sorted(set(int(t[8]) for t in send if t[2] != rank))
+    rest = sorted(b for b0, b1 in second_runs for b in range(b0, b1))
+    assert sorted(covered + rest) == list(range(nloc)) and not set(covered) & set(rest)
+
     # --- pool_t.reduce (compute_pool.h:247-284) and sync
     assert pool.reduce(float(rank + 1), sp.RED_MAX) == float(world)
     assert pool.reduce(float(rank + 1), sp.RED_SUM) == world * (world + 1) / 2

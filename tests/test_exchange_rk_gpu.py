@@ -77,7 +77,7 @@ def test_reductions():
     assert sp.transform_reduce(qa, sp.FN_ABSVAR, sp.RED_MAX, gas, ivar=4) == np.abs(qi[..., 4]).max()
 
 
-def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1), fused=False):
+def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1), fused=False, bc_object=False):
     sp, blocks, grid = product_setup(nb, n, ng)
     gas = sp.ideal_gas_t(GAMMA, RGAS)
     qa = sp.grid_array.from_host(grid, q)
@@ -88,10 +88,14 @@ def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1)
     data = sp.integrator_data_t(qa, ra, alg)
     rhs_calc = sp.flux_div_rhs_t(flux, sp.overwrite) if fused else (lambda r, qq, t: sp.flux_div(qq, r, flux, sp.overwrite))
     ti = sp.integrator_t(sp.time_axis_t(0.0, dt), alg, data, rhs_calc,
-                         lambda qq, t: ex.exchange(qq), sp.state_transform_t(gas))
+                         sp.exchange_bc_t(ex) if bc_object else (lambda qq, t: ex.exchange(qq)), sp.state_transform_t(gas))
     assert (ti._plan is not None) == fused
+    n0 = sp.launch_count()
     for _ in range(nsteps):
         ti.advance()
+    if bc_object and fused:
+        # one kernel per stage: no separate same-rank exchange launch, and the fused path was not abandoned
+        assert ti._fuse_exchange and sp.launch_count() - n0 == nsteps * alg.rows()
     return ti.solution().to_host()
 
 
@@ -127,6 +131,28 @@ def test_fused_stage_kernel_trajectory_matches_oracle(integ, scheme):
     assert rel_l2(got - q0, want - q0) < 1e-9
     unfused = _advance_product(nb, n, ng, q0, scheme, integ, dt, 3, fused=False)
     assert rel_l2(got, unfused) < 1e-13
+
+
+@pytest.mark.parametrize("nb,n,periodic", [((2, 1, 2), (40, 12, 8), (1, 1, 1)), ((2, 2, 2), (16, 16, 16), (1, 1, 1)),
+                                           ((1, 1, 1), (32, 32, 32), (1, 1, 1)), ((3, 2, 1), (32, 8, 16), (1, 0, 1)),
+                                           ((2, 2, 3), (64, 16, 6), (0, 1, 0))])
+@pytest.mark.parametrize("integ", [0, 2])
+def test_fused_stage_kernel_fills_same_rank_ghosts_bit_exact(nb, n, periodic, integ):
+    """spb_flux_div_rk_stage_exchange: the stage kernel also stores its q_out planes into the neighbour blocks' ghost
+    cells. The ghosts must be bit-identical to an exchange of the result (make_exchange.h:166-203), the interior
+    bit-identical to the fused stage kernel followed by a separate exchange, and the trajectory within 1e-12 of the
+    oracle. Ragged tiles, 16^3 blocks, a block that is its own neighbour, walls (ghosts there stay untouched)."""
+    from oracle import port
+    ng = 2
+    q0 = make_state(nb, n, ng, seed=29)
+    cfg = oracle_cfg(nb, n, ng, scheme=0, integrator=integ, periodic=periodic)
+    dt = 0.2 * (2 * np.pi / (nb[0] * n[0])) / port.reduce_umax(cfg, q0.ravel())
+    want = port.advance(cfg, q0.ravel(), dt, 2).reshape(q0.shape)
+    got = _advance_product(nb, n, ng, q0, 0, integ, dt, 2, periodic=periodic, fused=True, bc_object=True)
+    sep = _advance_product(nb, n, ng, q0, 0, integ, dt, 2, periodic=periodic, fused=True, bc_object=False)
+    assert np.array_equal(got, sep)                                      # interior and ghosts, bit for bit
+    assert np.array_equal(got, port.exchange(cfg, got.ravel()).reshape(got.shape))   # ghosts == exchange(interior)
+    assert rel_l2(interior(got, ng), interior(want, ng)) < 1e-12
 
 
 def test_rk4_hybrid_weno_trajectory_and_conservation():

@@ -76,7 +76,7 @@ def main():
     q2 = q.clone()
     from spade_b200._lib import StageDesc
 
-    def fused(nin, out):
+    def fused(nin, out, ghost=False):
         sd = StageDesc()
         sd.nin = nin
         for i in range(nin):
@@ -85,12 +85,15 @@ def main():
             sd.co[i] = 0.5
         sd.cq_self, sd.co_self = dt, 1.0
         sd.out = ks[2].data.data_ptr() if out else None
-        sp.check(lib.spb_flux_div_rk_stage(q.h, C.c_void_p(q.data.data_ptr()), C.c_void_p(q2.data.data_ptr()), C.byref(flux),
-                                           C.byref(sd), 0, grid.num_local_blocks, None))
+        sp.check(lib.spb_flux_div_rk_stage_exchange(q.h, C.c_void_p(q.data.data_ptr()), C.c_void_p(q2.data.data_ptr()), C.byref(flux),
+                                                    C.byref(sd), ex._h if ghost else None, 0, grid.num_local_blocks, None))
 
     if a.scheme in ("central", "euler"):
         for nin, out in ((0, 1), (1, 1), (2, 1), (1, 0)):
             timeit(f"fused_stage[nin={nin},out={out}]", lambda nin=nin, out=out: fused(nin, out), 80.0 + 40.0 * nin + 40.0 * out)
+        for nin, out in ((0, 1), (1, 1), (2, 1), (1, 0)):
+            timeit(f"fused_stage+ghosts[nin={nin},out={out}]", lambda nin=nin, out=out: fused(nin, out, True),
+                   80.0 + 40.0 * nin + 40.0 * out + 40.0 * ghost_frac)
     timeit("exchange", lambda: ex.exchange(q), 80.0 * ghost_frac)
     for nk in (1, 2, 4):
         timeit(f"rk_update[nk={nk}]", lambda nk=nk: rk(nk), 80.0 + 40.0 * nk)
