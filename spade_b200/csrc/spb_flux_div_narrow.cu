@@ -27,7 +27,7 @@ namespace spb
     {
         constexpr int TI = 32, TJ = 8;
         constexpr int NCOMPUTE = TI*TJ;                 // 8 warps
-        constexpr int NTHREADS = NCOMPUTE + 32;         // + edge warp
+        constexpr int NTHREADS = NCOMPUTE + 64;         // + edge warp + ghost warp
         constexpr int TIp = TI + 2 + 2;                 // halo + 16-byte TMA start alignment slack
         constexpr int TJp = TJ + 2;
         constexpr int NP = 3;                           // ring slots: planes k, k+1 resident, k+2 in flight
@@ -46,18 +46,9 @@ namespace spb
         constexpr int OFF_FX = OFF_STAGE_Q + STAGE_DOUBLES;
         constexpr int OFF_FY = OFF_FX + FX_DOUBLES;
         constexpr int OFF_BAR = OFF_FY + FY_DOUBLES;
-        // fused ghost exchange: the cells of the tile that feed the neighbours' LOW ghost cells sit at the high end of the
-        // tile, and TMA stores fault on negative coordinates (measured on B200, tools/probes/tma_store_probe.cu), so a store
-        // cannot be shifted left/down and clipped. x: those cells are copied into a dense mini tile (XHI: all rows, XHC: the
-        // rows that also feed a y-low ghost box); y: the source pointer is advanced by whole rows (1280 B, stays 128-aligned).
-        constexpr int GMAX = 4;                         // exchange cells supported by the mini tiles
-        constexpr int OFF_XHI = (OFF_BAR + NP + 1 + 15)/16*16;
-        constexpr int XHI_DOUBLES = TJ*5*GMAX;          // 1280 B
-        constexpr int OFF_XLO = OFF_XHI + XHI_DOUBLES;  // x-low source cells, dense, so their store does not walk the whole tile
-        constexpr int XC_DOUBLES = (GMAX*5*GMAX + 15)/16*16;
-        constexpr int OFF_XHC = OFF_XLO + XHI_DOUBLES;  // corner copies: the y-high rows of XHI / XLO
-        constexpr int OFF_XLC = OFF_XHC + XC_DOUBLES;
-        constexpr int SMEM_BYTES = (OFF_XLC + XC_DOUBLES)*8 + 128;
+        // fused ghost exchange: the same-rank neighbour table of this block (27 ints)
+        constexpr int OFF_NBR = (OFF_BAR + NP + 1 + 15)/16*16;
+        constexpr int SMEM_BYTES = (OFF_NBR + 16)*8 + 128;
 
         enum { P_RHO = 0, P_CX /* Dy.v + Dz.w */, P_DYU, P_DZU, P_CY /* Dz.w + Dx.u */, P_DZV, P_DXV };
 
@@ -177,7 +168,8 @@ namespace spb
                                const __grid_constant__ CUtensorMap tmap_in1, double* __restrict__ rhs,
                                const __grid_constant__ FluxParams P, const __grid_constant__ Dims G,
                                const __grid_constant__ Stage S, const double* __restrict__ inv_dx_tab,
-                               const __grid_constant__ GhostMaps GM, const int* __restrict__ nbr_tab)
+                               const __grid_constant__ GhostMaps GM, const int* __restrict__ nbr_tab,
+                               double* __restrict__ qout_raw)
         {
             extern __shared__ __align__(128) double smem_raw[];
             double*   ring    = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
@@ -187,14 +179,11 @@ namespace spb
             double*   Fx      = ring + OFF_FX;
             double*   Fy      = ring + OFF_FY;
             uint64_t* bars    = (uint64_t*)(ring + OFF_BAR);
-            double*   xhi     = ring + OFF_XHI;         // fused ghost exchange: x-high source cells of the q_out plane, dense
-            double*   xlo     = ring + OFF_XLO;         // ... x-low source cells
-            double*   xhc     = ring + OFF_XHC;         // ... and the rows of XHI / XLO that are also y-high source cells
-            double*   xlc     = ring + OFF_XLC;
+            int*      nbr_s   = (int*)(ring + OFF_NBR); // fused ghost exchange: destination block per neighbour direction
 
             const int tid = threadIdx.x;
             const int lane = tid & 31, warp = tid >> 5;
-            const bool is_edge = (warp == TJ);
+            const bool is_edge = (warp == TJ), is_ghost = (warp == TJ + 1);
 
             int t = blockIdx.x;
             const int ti = t % G.tiles_i; t /= G.tiles_i;
@@ -244,7 +233,7 @@ namespace spb
             // Ring: plane p lives in slot p % 3. At step k (plane index pk = k + 1) planes pk and pk+1 are resident and
             // pk+2 is in flight; plane pk is last read before barrier (2) of step k, after which its slot is re-armed
             // with plane pk+3 (one full step ahead of its first use). Plane 0 (k = -1) is consumed by the prologue.
-            if (!is_edge)
+            if (!is_edge && !is_ghost)
             {
                 // ======================= compute warps: one cell column per thread =======================
                 const int il = lane, jl = warp;
@@ -346,31 +335,6 @@ namespace spb
                                 stage_q[so + 0] = pn;
                                 stage_q[so + 1] = Tn;
                                 stage_q[so + 2] = un; stage_q[so + 3] = vn; stage_q[so + 4] = wn;
-                                if (G.ghost)
-                                {
-                                    // tile-local start of the x-high / y-high source cells (get_transaction.h:54-86, edge = +1)
-                                    const int ti_ = (int)(blockIdx.x % G.tiles_i);
-                                    const int xi = il - (G.nx[0] - G.ng[0] - ti_*TI);
-                                    const bool lo = (ti_ == 0) && (il < G.ng[0]), hi = (unsigned)xi < (unsigned)G.ng[0];
-                                    if (lo || hi)
-                                    {
-                                        const int rowp = 5*G.ng[0];
-                                        const int yj = jl - (G.nx[1] - G.ng[1] - (int)((blockIdx.x / G.tiles_i) % G.tiles_j)*TJ);
-                                        const bool yh = (unsigned)yj < (unsigned)G.ng[1];
-                                        if (lo)
-                                        {
-                                            double* d = xlo + jl*rowp + 5*il;
-                                            d[0] = pn; d[1] = Tn; d[2] = un; d[3] = vn; d[4] = wn;
-                                            if (yh) { double* c = xlc + yj*rowp + 5*il; c[0] = pn; c[1] = Tn; c[2] = un; c[3] = vn; c[4] = wn; }
-                                        }
-                                        if (hi)
-                                        {
-                                            double* d = xhi + jl*rowp + 5*xi;
-                                            d[0] = pn; d[1] = Tn; d[2] = un; d[3] = vn; d[4] = wn;
-                                            if (yh) { double* c = xhc + yj*rowp + 5*xi; c[0] = pn; c[1] = Tn; c[2] = un; c[3] = vn; c[4] = wn; }
-                                        }
-                                    }
-                                }
                             }
                             else if (G.tma_store)
                             {
@@ -473,7 +437,7 @@ namespace spb
                     sk = sp; sp = (sp + 1 == NP) ? 0 : sp + 1;
                 }
             }
-            else
+            else if (is_edge)
             {
                 // ======================= edge warp: halo ring + upper-edge faces + TMA traffic =======================
                 // row job (lanes 0..31): cell (lane, -1) is published, cell (lane, nj_t) is the R cell of the upper y-face
@@ -490,29 +454,6 @@ namespace spb
                     r0m[0] = pa[co_r0 + 3]; r0m[1] = pa[co_r0 + 4]; r00[0] = pb[co_r0 + 3]; r00[1] = pb[co_r0 + 4];
                     r1m[0] = pa[co_r1 + 3]; r1m[1] = pa[co_r1 + 4]; r10[0] = pb[co_r1 + 3]; r10[1] = pb[co_r1 + 4];
                     ccm[0] = pa[co_c + 2];  ccm[1] = pa[co_c + 4];  cc0[0] = pb[co_c + 2];  cc0[1] = pb[co_c + 4];
-                }
-                // fused ghost exchange: lane e < 27 owns neighbour direction e. The (ex, ey) part of "does this tile hold cells
-                // of the source box" is fixed per CTA, the ez part depends on the plane.
-                int gdst = -1, gc0 = 0, gc1 = 0, gzs = 0, gez = 0;
-                const double* gsrc = stage_q;
-                if (FUSED && G.ghost && lane < 27 && lane != 13)
-                {
-                    const int ex = lane % 3 - 1, ey = (lane/3) % 3 - 1;
-                    gez = lane/9 - 1;
-                    const int xhi0 = G.nx[0] - G.ng[0] - i0, yhi0 = G.nx[1] - G.ng[1] - j0;      // tile-local start of the +1 source cells
-                    const bool need_x = (ex == 0) || (ex < 0 ? (i0 < G.ng[0]) : (xhi0 >= 0 && xhi0 < TI));
-                    const bool need_y = (ey == 0) || (ey < 0 ? (j0 < G.ng[1]) : (yhi0 >= 0 && yhi0 < TJ));
-                    if (need_x && need_y) gdst = nbr_tab[27*lb + lane];
-                    // destination views start at the ghost box (host side), so coordinates are never negative:
-                    //   ex == 0: rows of the staged tile (ey > 0: from the first y-high row), clipped on the right by the view
-                    //   ex != 0: the dense mini tiles (ey > 0: their corner copies)
-                    // and the box of each view holds only the rows it can use (TJ rows, or ng[1] rows for ey != 0)
-                    gc0 = ex == 0 ? 5*i0 : 0;
-                    gc1 = ey > 0 ? 0 : j0;
-                    gsrc = ex == 0 ? (ey > 0 ? stage_q + yhi0*(5*TI) : stage_q)
-                                   : (ex > 0 ? (ey > 0 ? xhc : xhi) : (ey > 0 ? xlc : xlo));
-                    gzs = gez > 0 ? nz - G.ng[2] : 0;
-                    prefetch_tmap(&GM.m[lane]);
                 }
                 __syncthreads();                                                // (0) plane 0 consumed
                 if (lane == 0 && NP < nplanes)
@@ -578,16 +519,6 @@ namespace spb
                         if (FUSED) tma_store_4d(&tmap_qout, stage_q, 5*i0, j0, k - 1, (int)lb);
                         tma_store_commit();
                     }
-                    if (FUSED && gdst >= 0 && k >= 1)
-                    {
-                        const int kk = k - 1;                                    // plane of q_out sitting in stage_q
-                        const bool need_z = (gez == 0) || (gez < 0 ? (kk < G.ng[2]) : (kk >= nz - G.ng[2]));
-                        if (need_z)
-                        {
-                            tma_store_4d(&GM.m[lane], gsrc, gc0, gc1, kk - gzs, gdst);
-                            tma_store_commit();
-                        }
-                    }
                     if (k < nz)
                     {
                         if (row_on)                                              // upper y-face (lane, nj_t)
@@ -617,7 +548,7 @@ namespace spb
                             for (int v = 0; v < 5; ++v) Fx[(ccj*(TI + 1) + ni_t)*5 + v] = F[v];
                         }
                     }
-                    if (G.tma_store && (lane == 0 || gdst >= 0)) tma_store_wait_read<0>();     // staging tiles are rewritten after (2)
+                    if (lane == 0 && G.tma_store) tma_store_wait_read<0>();     // staging tiles are rewritten after (2)
                     __syncthreads();                                            // (2)
                     if (FUSED && lane == 0 && S.nin > 0 && k < nz)
                     {
@@ -648,7 +579,86 @@ namespace spb
                     ccm[0] = cc0[0]; ccm[1] = cc0[1]; cc0[0] = ccp[0]; cc0[1] = ccp[1];
                     sk = sp; sp = (sp + 1 == NP) ? 0 : sp + 1;
                 }
-                if (G.tma_store && (lane == 0 || gdst >= 0)) tma_store_wait<0>();
+                if (lane == 0 && G.tma_store) tma_store_wait<0>();
+            }
+            else
+            {
+                // ======================= ghost warp: same-rank ghost exchange of the finished q_out plane =======================
+                // A cell of the source box of direction e = (ex,ey,ez) goes to cell (i - ex n0, j - ey n1, k - ez n2) of the
+                // neighbour block (get_transaction.h:54-86). Directions with ex = 0 are whole rows of the staged tile: TMA stores
+                // through the clipped views GM.m[e] (lane e). Directions with ex != 0 are 2-cell pieces of a row: read from the
+                // staged tile and stored with plain 8-byte stores, 10 consecutive doubles per row (TMA stores cannot start at a
+                // negative coordinate, tools/probes/tma_store_probe.cu, and 80-byte boxes cost a TMA operation each).
+                const bool on = FUSED && G.ghost;
+                const int xhi0 = G.nx[0] - G.ng[0] - i0, yhi0 = G.nx[1] - G.ng[1] - j0;      // tile-local start of the +1 source cells
+                if (on && lane < 27) nbr_s[lane] = nbr_tab[27*lb + lane];
+                int gdst = -1, gc1 = 0, gzs = 0, gez = 0;
+                const double* gsrc = stage_q;
+                if (on && lane < 27 && lane != 13 && (lane % 3) == 1)
+                {
+                    const int ey = (lane/3) % 3 - 1;
+                    gez = lane/9 - 1;
+                    const bool need_y = (ey == 0) || (ey < 0 ? (j0 < G.ng[1]) : (yhi0 >= 0 && yhi0 < TJ));
+                    if (need_y) gdst = nbr_tab[27*lb + lane];
+                    gc1 = ey > 0 ? 0 : j0;                                   // ey > 0: source advanced to the first y-high row
+                    gsrc = ey > 0 ? stage_q + yhi0*(5*TI) : stage_q;
+                    gzs = gez > 0 ? nz - G.ng[2] : 0;
+                    prefetch_tmap(&GM.m[lane]);
+                }
+                // x pieces: lane = (half h, piece p): piece p = (side, row r) is 10 consecutive doubles = 5 double2; half 0 moves
+                // double2 0, 2, 4 and half 1 moves 1, 3. Everything that does not depend on the plane is computed here.
+                const int xp = lane & 15, xh = lane >> 4;
+                const int xside = xp >> 3, xr = xp & 7;
+                const bool x_on = on && (xr < nj_t) && (xside ? (xhi0 >= 0 && xhi0 < TI) : (i0 == 0));
+                const int xsm = xr*(5*TI) + (xside ? 5*xhi0 : 0) + 2*xh;                       // first double2 of this lane in stage_q
+                const int xj = j0 + xr;
+                const int xip = (xside ? xhi0 + i0 - G.nx[0] : i0 + G.nx[0]) + G.ng[0];       // padded i of the first destination cell
+                const bool y_lo = x_on && (xj < G.ng[1]), y_hi = x_on && (xj >= G.nx[1] - G.ng[1]);
+                const long long xrow = 5ll*G.np[0], xplane = 5ll*G.np[0]*G.np[1];
+                __syncthreads();                                                // (0)
+                for (int k = 0; k <= nz; ++k)
+                {
+                    __syncthreads();                                            // (1) stage_q holds plane k - 1 of q_out
+                    if (on && k >= 1)
+                    {
+                        const int kk = k - 1;
+                        if (gdst >= 0)
+                        {
+                            const bool need_z = (gez == 0) || (gez < 0 ? (kk < G.ng[2]) : (kk >= nz - G.ng[2]));
+                            if (need_z)
+                            {
+                                tma_store_4d(&GM.m[lane], gsrc, 5*i0, gc1, kk - gzs, gdst);
+                                tma_store_commit();
+                            }
+                        }
+                        if (x_on)
+                        {
+                            const double2 a0 = *reinterpret_cast<const double2*>(stage_q + xsm);
+                            const double2 a1 = *reinterpret_cast<const double2*>(stage_q + xsm + 4);
+                            const double2 a2 = xh ? a0 : *reinterpret_cast<const double2*>(stage_q + xsm + 8);
+                            #pragma unroll
+                            for (int ez = -1; ez <= 1; ++ez)
+                            {
+                                if (!(ez == 0 || (ez < 0 ? (kk < G.ng[2]) : (kk >= nz - G.ng[2])))) continue;     // uniform
+                                #pragma unroll
+                                for (int ey = -1; ey <= 1; ++ey)
+                                {
+                                    if (!(ey == 0 || (ey < 0 ? y_lo : y_hi))) continue;
+                                    const int dst = nbr_s[2*xside + 3*(ey + 1) + 9*(ez + 1)];
+                                    if (dst < 0) continue;
+                                    double* o = qout_raw + dst*G.block_stride + 5ll*xip + xrow*(xj - ey*G.nx[1] + G.ng[1])
+                                                + xplane*(kk - ez*nz + G.ng[2]) + 2*xh;
+                                    *reinterpret_cast<double2*>(o) = a0;
+                                    *reinterpret_cast<double2*>(o + 4) = a1;
+                                    if (!xh) *reinterpret_cast<double2*>(o + 8) = a2;
+                                }
+                            }
+                        }
+                    }
+                    if (gdst >= 0) tma_store_wait_read<0>();                    // stage_q is refilled after (2)
+                    __syncthreads();                                            // (2)
+                }
+                if (gdst >= 0) tma_store_wait<0>();
             }
         }
 
@@ -712,20 +722,19 @@ namespace spb
         const int* nbr_tab = nullptr;
         if (stage && exch)
         {
-            if (g->ng[0] % 2 != 0) { set_error("fused exchange: an odd number of exchange cells along i breaks the 16-byte TMA alignment (use spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
             int rc = exchange_fuse_table(exch, g->nx, g->ng, g->nlb, &nbr_tab); if (rc) return rc;
+            if (g->ng[0] != 2) { set_error("fused exchange: implemented for 2 exchange cells along i (use spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
             for (int d = 0; d < 2; ++d)
             {
                 const int T = d == 0 ? TI : TJ;
-                if (g->ng[d] > GMAX || g->ng[d] > g->nx[d] || (g->nx[d] - g->ng[d])/T != (g->nx[d] - 1)/T)
-                { set_error("fused exchange: the high source box straddles two tiles or has more than 4 exchange cells (use spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
+                if (g->ng[d] > g->nx[d] || (g->nx[d] - g->ng[d])/T != (g->nx[d] - 1)/T)
+                { set_error("fused exchange: the high source box straddles two tiles (use spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
             }
             const long long cstride[3] = {5ll, 5ll*g->np[0], 5ll*g->np[0]*g->np[1]};
-            // box of a view: x: the staged tile row (ex = 0) or a dense mini tile row; y: TJ rows, or only the ng[1] source rows
             for (int e = 0; e < 27; ++e)
             {
-                if (e == 13) { GM.m[e] = tqo; continue; }
                 const int ed[3] = {e % 3 - 1, (e/3) % 3 - 1, e/9 - 1};
+                if (e == 13 || ed[0] != 0) { GM.m[e] = tqo; continue; }       // ex != 0: plain stores by the ghost warp
                 long long shift = 0;
                 cuuint64_t gd[4];
                 for (int d = 0; d < 3; ++d)
@@ -734,7 +743,8 @@ namespace spb
                     gd[d] = (cuuint64_t)(ed[d] == 0 ? g->nx[d] : g->ng[d]);
                 }
                 gd[0] *= 5; gd[3] = (cuuint64_t)g->nlb;
-                const cuuint32_t gbox[4] = {(cuuint32_t)(ed[0] == 0 ? 5*TI : 5*g->ng[0]), (cuuint32_t)(ed[1] == 0 ? TJ : g->ng[1]), 1, 1};
+                // box: whole tile rows; TJ rows, or only the ng[1] source rows for ey != 0
+                const cuuint32_t gbox[4] = {(cuuint32_t)(5*TI), (cuuint32_t)(ed[1] == 0 ? TJ : g->ng[1]), 1, 1};
                 rc = make_map(&GM.m[e], q_out + org + shift, gd, strides, gbox, CU_TENSOR_MAP_L2_PROMOTION_NONE, "q_out ghost box"); if (rc) return rc;
             }
         }
@@ -766,7 +776,7 @@ namespace spb
         {
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev, GM, nbr_tab);
+            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev, GM, nbr_tab, q_out);
             SPB_LAUNCH_CHECK();
             return 0;
         };
