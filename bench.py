@@ -33,7 +33,9 @@ NG = 2
 LATTICE_1GPU = (16, 16, 16)
 # dram__bytes_read.sum + dram__bytes_write.sum per interior cell from the committed `ncu --set full` capture of the
 # dominant kernel (profiles/), None until a capture exists for that kernel
-TRAFFIC_PER_CELL = {"fused": None, "rhs": None}
+# profiles/r01_ncu_full_stage_kernels_512cube.txt: the four rk4 stage kernels of one step move 20.23 + 26.17 + 32.17 + 20.37 GB
+# for 134.2 M cells -> 184.3 B per cell per launch (algorithmic 166.9); profiles/r01_ncu_full_rhs_...: 1.535 GB / 16.8 M cells
+TRAFFIC_PER_CELL = {"fused": 184.3, "rhs": 91.5}
 
 
 def parse():
@@ -297,8 +299,9 @@ def ours(args):
     value = total_cells * STAGES * args.steps / (ms * 1e-3)
 
     # roofline of the dominant kernel. Algorithmic bytes per interior cell: plain flux_div reads q and
-    # writes rhs = 80 B; the fused stage kernel reads q, writes q' and reads/writes the residual registers its stage needs:
-    # rk4 = 120, 160, 200, 120 B (mean 150 B per launch).
+    # writes rhs = 80 B; the fused stage kernel reads q, writes q', reads/writes the residual registers its stage needs
+    # (rk4 = 120, 160, 200, 120 B, mean 150 B per launch) and writes the same-rank ghost cells (40 B x 0.4238 ghost cells per
+    # interior cell at n = 32, g = 2 = 17 B).
     peak, peak_src = measured_peak_hbm()
     fdiv_bytes = fdiv_bpc * local_cells
     achieved = fdiv_bytes / (fdiv_ms * 1e-3) / 1e9

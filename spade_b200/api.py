@@ -696,7 +696,12 @@ class integrator_t:
                     launch(b0, b1)
             if self.stage_events is not None:
                 e1.record()
-                self.stage_events.append((e0, e1, 80.0 + 40.0 * sd.nin + (40.0 if st["out"] else 0.0)))
+                # algorithmic bytes per interior cell of this launch: q in, q out, residual registers read / written, and one
+                # 40-byte write per same-rank ghost cell when the ghost exchange is fused into the kernel
+                ghost = 0.0
+                if ex is not None and self._fuse_exchange:
+                    ghost = 40.0 * ex.send_cells[ex.pool.rank()] / max(1, cur.grid.local_cells())
+                self.stage_events.append((e0, e1, 80.0 + 40.0 * sd.nin + (40.0 if st["out"] else 0.0) + ghost))
             cur, nxt = nxt, cur
             tnext = ax.t + (float(s.dt[i + 1]) * dt if i + 1 < s.rows() else dt)
             if i + 1 == s.rows():
