@@ -19,7 +19,7 @@ namespace spb
 {
     struct FluxParams
     {
-        double gamma, R, gm1, cv;     // cv = R/(gamma-1)
+        double gamma, R, gm1, cv, inv_gm1;     // cv = R/(gamma-1)
         double mu, beta, two_mu, kappa;
         double eps;
         int    blend;                 // SPB_BLEND_*
@@ -37,6 +37,36 @@ namespace spb
         double gm1, inv_gm1, inv_R;
     };
 
+    // 1/a with a MUFU.RCP64H seed and two Newton steps: relative error ~1e-16, no slow-path call (div.rn.f64 is ~3x the
+    // instructions and keeps a subroutine alive that costs registers). Arguments here are densities, sound speeds and
+    // smoothness sums: positive and far from the denormal range.
+    __device__ __forceinline__ double rcp_nr(const double a)
+    {
+        double x;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+        double e = fma(-a, x, 1.0);
+        x = fma(x, e, x);
+        e = fma(-a, x, 1.0);
+        x = fma(x, e, x);
+        return x;
+    }
+
+    // sqrt(a) for a > 0 from a MUFU.RSQ64H seed: two Newton steps on 1/sqrt(a), then one correction of the root
+    // (relative error ~1e-16, no slow-path call).
+    __device__ __forceinline__ double sqrt_nr(const double a)
+    {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+        const double h = 0.5*a;
+        double t = fma(-h*y, y, 0.5);
+        y = fma(y, t, y);
+        t = fma(-h*y, y, 0.5);
+        y = fma(y, t, y);
+        double s = a*y;
+        const double r = fma(-s, s, a);
+        return fma(0.5*y, r, s);
+    }
+
     // q_v at offset (sD along D, sT1 along (D+1)%3, sT2 along (D+2)%3) from the face's right cell
     template <int D, class A>
     __device__ __forceinline__ double qrel(const A& a, int v, int sD, int sT1, int sT2)
@@ -51,8 +81,8 @@ namespace spb
     template <int D>
     __device__ __forceinline__ void flux_totani(const FluxParams& P, const double (&qL)[5], const double (&qR)[5], double (&F)[5])
     {
-        const double rhoL = qL[0]/(P.R*qL[1]);
-        const double rhoR = qR[0]/(P.R*qR[1]);
+        const double rhoL = qL[0]*rcp_nr(P.R*qL[1]);
+        const double rhoR = qR[0]*rcp_nr(P.R*qR[1]);
         const double unL = qL[2+D], unR = qR[2+D];
         const double C = (rhoL + rhoR)*(unL + unR);                 // 4c
         double S = P.cv*(qL[1] + qR[1]);                            // e_L + e_R
@@ -75,7 +105,7 @@ namespace spb
         const double* q[4] = {c0, c1, c2, c3};
         double rho[4], eng[4];
         #pragma unroll
-        for (int i = 0; i < 4; ++i) { rho[i] = q[i][0]/(P.R*q[i][1]); eng[i] = P.cv*q[i][1]; }
+        for (int i = 0; i < 4; ++i) { rho[i] = q[i][0]*rcp_nr(P.R*q[i][1]); eng[i] = P.cv*q[i][1]; }
         double cc = 0.0, m[3] = {0.0, 0.0, 0.0}, g = 0.0, k = 0.0, ie = 0.0, pd = 0.0;
         auto pair = [&](const double a, const int i0, const int i1)
         {
@@ -114,8 +144,8 @@ namespace spb
         a1 = fma(a1, a1, eps); a1 *= a1;
         a2 = fma(a2, a2, eps); a2 *= a2;
         a3 = fma(a3, a3, eps); a3 *= a3;
-        const double w0 = a1/(a0 + a0 + a1);
-        const double w3 = a2/(a3 + a3 + a2);
+        const double w0 = a1*rcp_nr(a0 + a0 + a1);
+        const double w3 = a2*rcp_nr(a3 + a3 + a2);
         // w0 r0 + (1-w0) r1 + (1-w3) r2 + w3 r3
         return fma(w0, r0 - r1, r1) + fma(w3, r3 - r2, r2);
     }
@@ -132,8 +162,8 @@ namespace spb
             a[i]   = P.R*q[i][1];
             const double u2 = fma(q[i][2], q[i][2], fma(q[i][3], q[i][3], q[i][4]*q[i][4]));
             ke[i]  = 0.5*u2;
-            rho[i] = q[i][0]/a[i];
-            hsr[i] = 0.5*rho[i]*(sqrt(u2) + sqrt(a[i]*P.gamma));
+            rho[i] = q[i][0]*rcp_nr(a[i]);
+            hsr[i] = 0.5*rho[i]*(sqrt_nr(fmax(u2, 1e-300)) + sqrt_nr(a[i]*P.gamma));      // |u| = 0 becomes 1e-150
             fm[i]  = 0.5*rho[i]*q[i][2+D];
         }
         // continuity
@@ -142,7 +172,7 @@ namespace spb
         #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
-            const double engy = ke[i] + a[i]/P.gm1;
+            const double engy = fma(a[i], P.inv_gm1, ke[i]);
             fl[i] = fm[i]*(engy + a[i]);
             ds[i] = hsr[i]*engy;
         }
@@ -212,7 +242,7 @@ namespace spb
                 const double w1 = g[2][0] - g[0][2];
                 const double w2 = g[0][1] - g[1][0];
                 const double vort = fma(w0, w0, fma(w1, w1, w2*w2));
-                const double alpha = th2/(th2 + vort + P.eps);
+                const double alpha = th2*rcp_nr(th2 + vort + P.eps);
                 double F1[5];
                 flux_fweno<D>(P, qLL, qL, qR, qRR, F1);
                 const double coeff0 = (P.blend == SPB_BLEND_FULL_FLUX) ? (1.0 - alpha) : 1.0;

@@ -265,7 +265,7 @@ namespace spb
     static FluxParams make_params(const spb_flux_desc* f)
     {
         FluxParams P;
-        P.gamma = f->gamma; P.R = f->R; P.gm1 = f->gamma - 1.0; P.cv = f->R/(f->gamma - 1.0);
+        P.gamma = f->gamma; P.R = f->R; P.gm1 = f->gamma - 1.0; P.cv = f->R/(f->gamma - 1.0); P.inv_gm1 = 1.0/(f->gamma - 1.0);
         P.mu = f->mu; P.beta = f->beta; P.two_mu = 2.0*f->mu;
         // reference viscous.h:64-68: cond = (gamma R/(gamma-1)) * (mu * prandtl_inv)
         P.kappa = (f->gamma*f->R/(f->gamma - 1.0))*(f->mu*f->prandtl_inv);
