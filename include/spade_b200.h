@@ -180,6 +180,39 @@ int spb_exchange_unpack(spb_exchange* e, double* q_dev, int peer, const double* 
  * cudaDeviceEnablePeerAccess). Same element order as spb_exchange_pack. */
 int spb_exchange_pack_peer(spb_exchange* e, const double* q_dev, int peer, double* peer_recvbuf_dev, void* stream);
 
+/* ---- domain-boundary ghost fill: replaces algs::boundary_fill(arr, boundaries, kern) ------------
+ * reference src/grid/boundary_fill.h:32-133. One call fills ONE boundary (idir, pm): pm = 0 the lower, 1 the upper
+ * face of the block lattice along idir. `blocks_host` lists the local blocks on that face
+ * (grid_geometry_t::boundary_blocks[2*idir+pm], reference src/grid/cartesian_grid.h:139-146). Every cell beyond the
+ * face is written, including the exchange cells of the two tangential directions, exactly like the reference; the
+ * caller fills several boundaries in the reference's order xmin, xmax, ymin, ymax, zmin, zmax (a later boundary reads
+ * ghosts an earlier one wrote). The user kernel is one of a closed set:
+ *   SPB_BC_MIRROR  kern(image, idir): ghost[v] = a[v]*image[v] + b[v] with image the mirror cell through the face
+ *                  (-1 - i below, 2 n - (i + 1) above); if use_normal the velocity component along idir uses a_normal.
+ *                  no-slip isothermal wall: a = (1,-1,-1,-1,-1), b = (0, 2 T_wall, 0, 0, 0); no-slip adiabatic:
+ *                  a = (1,1,-1,-1,-1); symmetry / slip: a = 1, a_normal = -1; Dirichlet: a = 0, b = value.
+ *   SPB_BC_EXTRAP  boundary::extrapolate<order>: Lagrange extrapolation through the order+1 cells next to the face.
+ * Ghost values are bit-identical to the reference's CPU result (no FMA contraction in the kernel). */
+enum { SPB_BC_MIRROR = 0, SPB_BC_EXTRAP = 1 };
+typedef struct spb_bc_desc
+{
+    int    kind;          /* SPB_BC_* */
+    int    order;         /* SPB_BC_EXTRAP */
+    double a[5], b[5];    /* SPB_BC_MIRROR */
+    int    use_normal;
+    double a_normal;
+} spb_bc_desc;
+int spb_boundary_fill(const spb_grid* g, double* q_dev, int idir, int pm, const int64_t* blocks_host, int64_t nblocks,
+                      const spb_bc_desc* bc, void* stream);
+
+/* ---- source term: replaces pde_algs::source_term(q, rhs, source_term_func) ----------------------
+ * reference src/pde-algs/source_term.h:25-51: rhs(cell) += S(q(cell))/jac on interior cells (jac = 1). Closed set:
+ *   SPB_SRC_BODY_FORCE  S = (0, f.u, f[0], f[1], f[2])   (the forcing of a channel run)
+ *   SPB_SRC_CONSTANT    S = f[0..4] */
+enum { SPB_SRC_BODY_FORCE = 0, SPB_SRC_CONSTANT = 1 };
+typedef struct spb_source_desc { int kind; double f[5]; } spb_source_desc;
+int spb_source_term(const spb_grid* g, const double* q_dev, double* rhs_dev, const spb_source_desc* src, void* stream);
+
 /* ---- utilities ---------------------------------------------------------------------------------- */
 const char* spb_last_error(void);
 int  spb_device_count(void);

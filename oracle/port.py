@@ -4,7 +4,7 @@ import ctypes as C
 import os
 import subprocess
 import numpy as np
-from .ref import RefCfg, make_cfg  # same struct layout (spo_cfg == ref_cfg)
+from .ref import RefBc, RefCfg, make_bc, make_cfg  # same struct layouts (spo_cfg == ref_cfg, spo_bc == ref_bc)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
@@ -66,6 +66,25 @@ def reduce_umax(cfg, q):
 def advance(cfg, q, dt, nsteps):
     out = np.array(q, dtype=np.float64, copy=True)
     assert lib().spo_advance(C.byref(cfg), _ptr(out), C.c_double(dt), int(nsteps)) == 0
+    return out
+
+
+def boundary_fill(cfg, bc, q):
+    out = np.array(q, dtype=np.float64, copy=True)
+    assert lib().spo_boundary_fill(C.byref(cfg), C.byref(bc), _ptr(out)) == 0
+    return out
+
+
+def source_term(cfg, bc, q, rhs):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.array(rhs, dtype=np.float64, copy=True)
+    assert lib().spo_source_term(C.byref(cfg), C.byref(bc), _ptr(q), _ptr(out)) == 0
+    return out
+
+
+def advance_channel(cfg, bc, q, dt, nsteps):
+    out = np.array(q, dtype=np.float64, copy=True)
+    assert lib().spo_advance_channel(C.byref(cfg), C.byref(bc), _ptr(out), C.c_double(dt), int(nsteps)) == 0
     return out
 
 

@@ -16,6 +16,24 @@ class RefCfg(C.Structure):
                 ("integrator", C.c_int)]
 
 
+class RefBc(C.Structure):
+    """ref_bc / spo_bc: boundary_fill kernel + body force of a channel run."""
+    _fields_ = [("mask", C.c_int * 6), ("kind", C.c_int), ("order", C.c_int), ("a", C.c_double * 5), ("b", C.c_double * 5),
+                ("use_normal", C.c_int), ("a_normal", C.c_double), ("force", C.c_double * 3)]
+
+
+def make_bc(mask, kind=0, order=0, a=(1, 1, 1, 1, 1), b=(0, 0, 0, 0, 0), a_normal=None, force=(0, 0, 0)):
+    bc = RefBc()
+    bc.mask[:] = [int(m) for m in mask]
+    bc.kind, bc.order = int(kind), int(order)
+    bc.a[:] = [float(x) for x in a]
+    bc.b[:] = [float(x) for x in b]
+    bc.use_normal = 0 if a_normal is None else 1
+    bc.a_normal = 0.0 if a_normal is None else float(a_normal)
+    bc.force[:] = [float(x) for x in force]
+    return bc
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -86,6 +104,26 @@ def advance(cfg, q, dt, nsteps):
     out = np.array(q, dtype=np.float64, copy=True)
     sec = C.c_double(0.0)
     _check(lib().ref_advance(C.byref(cfg), _ptr(out), C.c_double(dt), int(nsteps), C.byref(sec)))
+    return out, sec.value
+
+
+def boundary_fill(cfg, bc, q):
+    out = np.array(q, dtype=np.float64, copy=True)
+    _check(lib().ref_boundary_fill(C.byref(cfg), C.byref(bc), _ptr(out)))
+    return out
+
+
+def source_term(cfg, bc, q, rhs):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.array(rhs, dtype=np.float64, copy=True)
+    _check(lib().ref_source_term(C.byref(cfg), C.byref(bc), _ptr(q), _ptr(out)))
+    return out
+
+
+def advance_channel(cfg, bc, q, dt, nsteps):
+    out = np.array(q, dtype=np.float64, copy=True)
+    sec = C.c_double(0.0)
+    _check(lib().ref_advance_channel(C.byref(cfg), C.byref(bc), _ptr(out), C.c_double(dt), int(nsteps), C.byref(sec)))
     return out, sec.value
 
 

@@ -62,9 +62,65 @@ extern "C"
     };
 }
 
+extern "C"
+{
+    // the other half of a channel run's boundary callback and its forcing (same layout as spo_bc)
+    struct ref_bc
+    {
+        int    mask[6];      // xmin xmax ymin ymax zmin zmax
+        int    kind;         // 0: mirror kernel ghost[v] = a[v]*image[v] + b[v]; 1: boundary::extrapolate<order> (order 1 or 2)
+        int    order;
+        double a[5], b[5];
+        int    use_normal;
+        double a_normal;
+        double force[3];
+    };
+}
+
 namespace
 {
     std::string g_last_error;
+
+    // algs::boundary_fill (reference src/grid/boundary_fill.h:32-133) with the kernels of ref_bc
+    template <typename arr_t>
+    void apply_boundary_fill(arr_t& prim, const ref_bc& bc)
+    {
+        spade::boundary::identifier_t which(bool(bc.mask[0]), bool(bc.mask[1]), bool(bc.mask[2]), bool(bc.mask[3]), bool(bc.mask[4]), bool(bc.mask[5]));
+        if (bc.kind == 1)
+        {
+            if (bc.order == 1)      spade::algs::boundary_fill(prim, which, spade::boundary::extrapolate<1>);
+            else if (bc.order == 2) spade::algs::boundary_fill(prim, which, spade::boundary::extrapolate<2>);
+            else throw std::runtime_error("ref_driver: extrapolation order 1 or 2");
+            return;
+        }
+        const ref_bc b = bc;
+        auto kern = [b](const prim_t& q_image, const int idir)
+        {
+            prim_t g;
+            for (int v = 0; v < 5; ++v) g[v] = b.a[v]*q_image[v] + b.b[v];
+            if (b.use_normal) g[2+idir] = b.a_normal*q_image[2+idir] + b.b[2+idir];
+            return g;
+        };
+        spade::algs::boundary_fill(prim, which, kern);
+    }
+
+    // pde_algs::source_term (reference src/pde-algs/source_term.h:25-51) with a body force
+    template <typename arr_t, typename rhs_t>
+    void apply_source_term(const arr_t& prim, rhs_t& rhs, const ref_bc& bc)
+    {
+        const real_t fx = bc.force[0], fy = bc.force[1], fz = bc.force[2];
+        auto src = [=](const prim_t& q)
+        {
+            flux_t out;
+            out.continuity() = 0.0;
+            out.energy()     = fx*q.u() + fy*q.v() + fz*q.w();
+            out.x_momentum() = fx;
+            out.y_momentum() = fy;
+            out.z_momentum() = fz;
+            return out;
+        };
+        spade::pde_algs::source_term(prim, rhs, src);
+    }
 
     template <typename func_t>
     void with_scheme(const ref_cfg& c, const func_t& func)
@@ -215,7 +271,14 @@ extern "C"
     // nsteps of integrator_t::advance() with bc = exchange, rhs = flux_div(basic, overwrite).
     // q must enter with ghosts filled. If seconds != nullptr it receives the wall time of the
     // advance() loop (max over ranks, barriers on both sides).
+    int ref_advance_channel(const ref_cfg* c, const ref_bc* bcd, double* q, double dt, int nsteps, double* seconds);
     int ref_advance(const ref_cfg* c, double* q, double dt, int nsteps, double* seconds)
+    {
+        return ref_advance_channel(c, nullptr, q, dt, nsteps, seconds);
+    }
+
+    // the same with boundary = exchange + boundary_fill and rhs = flux_div + source_term (bcd != nullptr)
+    int ref_advance_channel(const ref_cfg* c, const ref_bc* bcd, double* q, double dt, int nsteps, double* seconds)
     {
         return guarded([&]
         {
@@ -227,10 +290,11 @@ extern "C"
                 spade::fluid_state::ideal_gas_t<real_t> air(c->gamma, c->R);
                 with_scheme(*c, [&](const auto& flux_func)
                 {
-                    auto bc = [&](auto& qq, const auto& t) { handle.exchange(qq, pool); };
+                    auto bc = [&](auto& qq, const auto& t) { handle.exchange(qq, pool); if (bcd) apply_boundary_fill(qq, *bcd); };
                     auto calc_rhs = [&](auto& rr, const auto& qq, const auto& t)
                     {
                         spade::pde_algs::flux_div(qq, rr, flux_func, spade::algs::make_traits(spade::pde_algs::basic, spade::pde_algs::overwrite));
+                        if (bcd) apply_source_term(qq, rr, *bcd);
                     };
                     cons_t transform_state;
                     spade::fluid_state::state_transform_t trans(transform_state, air);
@@ -260,6 +324,35 @@ extern "C"
                 });
             });
             if (seconds) *seconds = tmax;
+        });
+    }
+
+    // algs::boundary_fill in place (q enters with whatever ghosts the caller set)
+    int ref_boundary_fill(const ref_cfg* c, const ref_bc* bc, double* q)
+    {
+        return guarded([&]
+        {
+            with_setup(*c, [&](auto& pool, auto& grid, auto& prim, auto& rhs, auto& handle, std::size_t off, std::size_t cnt)
+            {
+                std::copy(q + off, q + off + cnt, prim.data.begin());
+                apply_boundary_fill(prim, *bc);
+                std::copy(prim.data.begin(), prim.data.end(), q + off);
+            });
+        });
+    }
+
+    // rhs += S(q)
+    int ref_source_term(const ref_cfg* c, const ref_bc* bc, const double* q, double* rhs_io)
+    {
+        return guarded([&]
+        {
+            with_setup(*c, [&](auto& pool, auto& grid, auto& prim, auto& rhs, auto& handle, std::size_t off, std::size_t cnt)
+            {
+                std::copy(q + off, q + off + cnt, prim.data.begin());
+                std::copy(rhs_io + off, rhs_io + off + cnt, rhs.data.begin());
+                apply_source_term(prim, rhs, *bc);
+                std::copy(rhs.data.begin(), rhs.data.end(), rhs_io + off);
+            });
         });
     }
 

@@ -26,6 +26,17 @@ class StageDesc(C.Structure):
 SPB_ERR_BAD_ARG, SPB_ERR_UNSUPPORTED, SPB_ERR_NO_DEVICE, SPB_ERR_DRIVER = 10001, 10002, 10003, 10004
 
 
+class BcDesc(C.Structure):
+    """spb_bc_desc (include/spade_b200.h)."""
+    _fields_ = [("kind", C.c_int), ("order", C.c_int), ("a", C.c_double * 5), ("b", C.c_double * 5),
+                ("use_normal", C.c_int), ("a_normal", C.c_double)]
+
+
+class SourceDesc(C.Structure):
+    """spb_source_desc (include/spade_b200.h)."""
+    _fields_ = [("kind", C.c_int), ("f", C.c_double * 5)]
+
+
 class SpbError(RuntimeError):
     pass
 
@@ -69,6 +80,8 @@ SYMBOLS = {
     "spb_exchange_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "spb_exchange_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "spb_exchange_pack_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "spb_boundary_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _i64p, C.c_int64, C.POINTER(BcDesc), C.c_void_p]),
+    "spb_source_term": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SourceDesc), C.c_void_p]),
     "spb_last_error": (C.c_char_p, []),
     "spb_device_count": (C.c_int, []),
     "spb_sync": (C.c_int, [C.c_void_p]),

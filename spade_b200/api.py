@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FluxDesc, SpbError, StageDesc, check, int3, lib
+from ._lib import BcDesc, FluxDesc, SourceDesc, SpbError, StageDesc, check, int3, lib
 
 NVAR = 5
 
@@ -132,6 +132,7 @@ class cartesian_grid_t:
         self._bbox = np.array([blocks.get_block_box(self.first_block + l) for l in range(self.num_local_blocks)],
                               dtype=np.float64).reshape(-1)
         self._handles = {}
+        self._bnd = {}
 
     def handle(self, num_exch):
         """spb_grid for arrays with `num_exch` exchange cells (device image of grid_geometry_t)."""
@@ -153,6 +154,15 @@ class cartesian_grid_t:
 
     def group(self):
         return self._group
+
+    def boundary_blocks(self, ibndy):
+        """grid_geometry_t::boundary_blocks[ibndy] (cartesian_grid.h:139-146): local blocks on face ibndy of the lattice."""
+        if ibndy not in self._bnd:
+            idir, pm = ibndy // 2, ibndy % 2
+            want = self.blocks.num_blocks[idir] - 1 if pm else 0
+            self._bnd[ibndy] = np.array([l for l in range(self.num_local_blocks)
+                                         if self.blocks.block_index(self.first_block + l)[idir] == want], dtype=np.int64)
+        return self._bnd[ibndy]
 
     def get_num_local_blocks(self):
         return self.num_local_blocks
@@ -502,6 +512,122 @@ class exchange_bc_t:
 
 def make_exchange(array, periodic):
     return arr_exchange_t(array.grid, array.num_exch, periodic)
+
+
+# ---- domain boundaries (reference src/grid/boundary_fill.h) -------------------------------------------------------
+class identifier_t:
+    """boundary::identifier_t = bound_box_t<bool, 3>: which of xmin xmax ymin ymax zmin zmax; `a || b` is `a | b` here."""
+
+    def __init__(self, *flags):
+        self.flags = tuple(bool(f) for f in flags)
+        assert len(self.flags) == 6
+
+    def __or__(self, other):
+        return identifier_t(*[a or b for a, b in zip(self.flags, other.flags)])
+
+    def __call__(self, idir, pm):
+        return self.flags[2 * idir + pm]
+
+
+class boundary:
+    xmin = identifier_t(1, 0, 0, 0, 0, 0)
+    xmax = identifier_t(0, 1, 0, 0, 0, 0)
+    ymin = identifier_t(0, 0, 1, 0, 0, 0)
+    ymax = identifier_t(0, 0, 0, 1, 0, 0)
+    zmin = identifier_t(0, 0, 0, 0, 1, 0)
+    zmax = identifier_t(0, 0, 0, 0, 0, 1)
+
+    class extrap_t:
+        """boundary::extrapolate<order> (boundary_fill.h:17-27)"""
+
+        def __init__(self, order):
+            self.order = int(order)
+
+        def desc(self):
+            d = BcDesc()
+            d.kind, d.order = 1, self.order
+            return d
+
+    @staticmethod
+    def extrapolate(order):
+        return boundary.extrap_t(order)
+
+
+class mirror_kernel_t:
+    """The boundary_fill kernels `[=](const prim_t& q_image, int idir) -> prim_t` that are linear per variable:
+    ghost[v] = a[v]*image[v] + b[v]; with a_normal the velocity component along idir uses that factor instead."""
+
+    def __init__(self, a, b=(0.0,) * 5, a_normal=None):
+        self.a, self.b, self.a_normal = [float(x) for x in a], [float(x) for x in b], a_normal
+
+    def desc(self):
+        d = BcDesc()
+        d.kind, d.order = 0, 0
+        d.a[:] = self.a
+        d.b[:] = self.b
+        d.use_normal = 0 if self.a_normal is None else 1
+        d.a_normal = 0.0 if self.a_normal is None else float(self.a_normal)
+        return d
+
+
+def noslip_isothermal_wall(t_wall):
+    """ghost = (p, 2 T_wall - T, -u, -v, -w)"""
+    return mirror_kernel_t((1, -1, -1, -1, -1), (0, 2.0 * t_wall, 0, 0, 0))
+
+
+def noslip_adiabatic_wall():
+    return mirror_kernel_t((1, 1, -1, -1, -1))
+
+
+def symmetry_plane():
+    return mirror_kernel_t((1, 1, 1, 1, 1), a_normal=-1.0)
+
+
+def boundary_fill(arr, boundaries, kern):
+    """algs::boundary_fill(arr, boundaries, kern), boundary_fill.h:32-133: the listed boundaries in the order
+    xmin xmax ymin ymax zmin zmax, each over the local blocks on that face of the block lattice."""
+    d = kern.desc()
+    grid = arr.grid
+    for ib in range(6):
+        idir, pm = ib // 2, ib % 2
+        if not boundaries(idir, pm):
+            continue
+        blocks = grid.boundary_blocks(ib)
+        if len(blocks) == 0:
+            continue
+        check(lib().spb_boundary_fill(arr.h, _dptr(arr.data), idir, pm, blocks.ctypes.data_as(C.POINTER(C.c_int64)),
+                                      len(blocks), C.byref(d), _stream_ptr()))
+
+
+# ---- source term (reference src/pde-algs/source_term.h) ------------------------------------------------------------
+class body_force_t:
+    """source_term_func `[=](const prim_t& q) -> flux_t {0, f.u, fx, fy, fz}`: the forcing of a channel run"""
+
+    def __init__(self, fx, fy=0.0, fz=0.0):
+        self.f = (float(fx), float(fy), float(fz))
+
+    def desc(self):
+        d = SourceDesc()
+        d.kind = 0
+        d.f[:] = list(self.f) + [0.0, 0.0]
+        return d
+
+
+class constant_source_t:
+    def __init__(self, values):
+        self.values = [float(x) for x in values]
+
+    def desc(self):
+        d = SourceDesc()
+        d.kind = 1
+        d.f[:] = self.values
+        return d
+
+
+def source_term(q, rhs, source_term_func):
+    """pde_algs::source_term(q, rhs, source_term_func): rhs += S(q)/jac on interior cells"""
+    d = source_term_func.desc()
+    check(lib().spb_source_term(q.h, _dptr(q.data), _dptr(rhs.data), C.byref(d), _stream_ptr()))
 
 
 # ---- algs ----------------------------------------------------------------------------------------------------

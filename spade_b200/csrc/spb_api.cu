@@ -77,6 +77,7 @@ extern "C"
         if (!g) return;
         if (g->inv_dx_dev) cudaFree(g->inv_dx_dev);
         if (g->red_scratch) cudaFree(g->red_scratch);
+        for (int i = 0; i < 6; ++i) if (g->bnd_blocks_dev[i]) cudaFree(g->bnd_blocks_dev[i]);
         delete g;
     }
 

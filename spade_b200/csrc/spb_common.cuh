@@ -56,4 +56,7 @@ struct spb_grid
     // scratch of spb_reduce (partials | result | counter), owned by the handle so a reduction never allocates
     mutable double* red_scratch = nullptr;
     mutable int64_t red_cap = 0;
+    // device copies of the block lists of the six domain boundaries last passed to spb_boundary_fill
+    mutable std::vector<int64_t> bnd_blocks_host[6];
+    mutable int64_t* bnd_blocks_dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };

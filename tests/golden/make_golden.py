@@ -18,6 +18,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from util import make_state, oracle_cfg, zero_ghosts  # noqa: E402
 from oracle import ref  # noqa: E402
 
+CHANNEL_WALL_T = 310.0
+CHANNEL_FORCE = (40.0, -0.5, 0.25)
+CHANNEL_BCS = {
+    "noslip_isothermal_y": dict(mask=(0, 0, 1, 1, 0, 0), a=(1, -1, -1, -1, -1), b=(0, 2 * CHANNEL_WALL_T, 0, 0, 0)),
+    "adiabatic_all": dict(mask=(1, 1, 1, 1, 1, 1), a=(1, 1, -1, -1, -1)),
+    "symmetry_x_z": dict(mask=(1, 1, 0, 0, 1, 1), a=(1, 1, 1, 1, 1), a_normal=-1.0),
+    "extrap2_all": dict(mask=(1, 1, 1, 1, 1, 1), kind=1, order=2),
+}
 NB, N, NG = (2, 1, 2), (8, 4, 4), 2   # multiples of 4: the reference's transform_inplace tiles are 4^3 (transform_inplace.h:34-96)
 
 
@@ -58,7 +66,27 @@ def main():
                 tabs[f"recv_{nranks}_{tag}_{rank}"] = r
                 tabs[f"offs_{nranks}_{tag}_{rank}"] = o
     np.savez_compressed(os.path.join(HERE, "exchange_tables.npz"), **tabs)
-    for f in ("hotpath_small.npz", "exchange_tables.npz"):
+    # (v) channel: boundary_fill kernels, source_term and a wall-bounded forced RK trajectory (boundary_fill.h:32-133,
+    #     source_term.h:25-51)
+    ch = {}
+    nb, n = (2, 2, 1), (8, 4, 4)
+    q = make_state(nb, n, NG, seed=51)
+    ch["q"] = q
+    cfgw = oracle_cfg(nb, n, NG, periodic=(0, 0, 0))
+    for name, o in CHANNEL_BCS.items():
+        ch[f"fill_{name}"] = ref.boundary_fill(cfgw, ref.make_bc(**o), q.ravel()).reshape(q.shape)
+    rhs0 = np.random.default_rng(5).standard_normal(q.shape)
+    ch["src_rhs0"] = rhs0
+    ch["src_rhs1"] = ref.source_term(cfgw, ref.make_bc(mask=(0,) * 6, force=CHANNEL_FORCE), q.ravel(), rhs0.ravel()).reshape(q.shape)
+    cfgc = oracle_cfg(nb, n, NG, scheme=0, integrator=0, periodic=(1, 0, 1))
+    bc = ref.make_bc(force=CHANNEL_FORCE, **CHANNEL_BCS["noslip_isothermal_y"])
+    q0 = ref.boundary_fill(cfgc, bc, ref.exchange(cfgc, q.ravel()))
+    umax = ref.reduce_umax(cfgc, q0)
+    dt = 0.2 * (2 * np.pi / 16) / umax
+    q3, _ = ref.advance_channel(cfgc, bc, q0, dt, 3)
+    ch["adv_q0"], ch["adv_q3"], ch["adv_dt"] = q0.reshape(q.shape), q3.reshape(q.shape), np.array([dt, umax])
+    np.savez_compressed(os.path.join(HERE, "channel_small.npz"), **ch)
+    for f in ("hotpath_small.npz", "exchange_tables.npz", "channel_small.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -141,3 +141,82 @@ def test_cuda_trajectory(gold, integ, name):
     for _ in range(3):
         ti.advance()
     assert rel_l2(ti.solution().to_host(), gold[f"adv_q3_{name}"]) < 1e-12
+
+
+# ---------------------------------------------------------------- channel rows: boundary_fill, source_term
+CH_NB, CH_N = (2, 2, 1), (8, 4, 4)
+
+
+@pytest.fixture(scope="module")
+def chan():
+    return np.load(os.path.join(HERE, "golden", "channel_small.npz"))
+
+
+CHANNEL_WALL_T = 310.0
+CHANNEL_FORCE = (40.0, -0.5, 0.25)
+CHANNEL_BCS = {
+    "noslip_isothermal_y": dict(mask=(0, 0, 1, 1, 0, 0), a=(1, -1, -1, -1, -1), b=(0, 2 * CHANNEL_WALL_T, 0, 0, 0)),
+    "adiabatic_all": dict(mask=(1, 1, 1, 1, 1, 1), a=(1, 1, -1, -1, -1)),
+    "symmetry_x_z": dict(mask=(1, 1, 0, 0, 1, 1), a=(1, 1, 1, 1, 1), a_normal=-1.0),
+    "extrap2_all": dict(mask=(1, 1, 1, 1, 1, 1), kind=1, order=2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CHANNEL_BCS))
+def test_oracle_boundary_fill(chan, name):
+    from oracle import port, ref
+    q = chan["q"]
+    got = port.boundary_fill(oracle_cfg(CH_NB, CH_N, NG, periodic=(0, 0, 0)), ref.make_bc(**CHANNEL_BCS[name]), q.ravel())
+    assert np.array_equal(got.reshape(q.shape), chan[f"fill_{name}"])
+
+
+def test_oracle_source_term_and_channel_trajectory(chan):
+    from oracle import port, ref
+    q = chan["q"]
+    cfgw = oracle_cfg(CH_NB, CH_N, NG, periodic=(0, 0, 0))
+    got = port.source_term(cfgw, ref.make_bc(mask=(0,) * 6, force=CHANNEL_FORCE), q.ravel(), chan["src_rhs0"].ravel())
+    assert np.array_equal(got.reshape(q.shape), chan["src_rhs1"])
+    cfgc = oracle_cfg(CH_NB, CH_N, NG, scheme=0, integrator=0, periodic=(1, 0, 1))
+    bc = ref.make_bc(force=CHANNEL_FORCE, **CHANNEL_BCS["noslip_isothermal_y"])
+    dt, umax = chan["adv_dt"]
+    assert port.reduce_umax(cfgc, chan["adv_q0"].ravel()) == umax
+    got = port.advance_channel(cfgc, bc, chan["adv_q0"].ravel(), float(dt), 3).reshape(q.shape)
+    assert rel_l2(got, chan["adv_q3"]) < 1e-14
+
+
+@pytest.mark.gpu
+def test_gpu_channel_golden(chan):
+    """boundary_fill / source_term / wall-bounded forced rk4 trajectory of the CUDA path against the reference's own output"""
+    sp, blocks, grid = product_setup(CH_NB, CH_N, NG)
+    q = chan["q"]
+    kern = {"noslip_isothermal_y": (sp.boundary.ymin | sp.boundary.ymax, sp.noslip_isothermal_wall(CHANNEL_WALL_T)),
+            "adiabatic_all": (sp.identifier_t(1, 1, 1, 1, 1, 1), sp.noslip_adiabatic_wall()),
+            "symmetry_x_z": (sp.boundary.xmin | sp.boundary.xmax | sp.boundary.zmin | sp.boundary.zmax, sp.symmetry_plane()),
+            "extrap2_all": (sp.identifier_t(1, 1, 1, 1, 1, 1), sp.boundary.extrapolate(2))}
+    for name, (which, k) in kern.items():
+        qa = sp.grid_array.from_host(grid, q)
+        sp.boundary_fill(qa, which, k)
+        assert np.array_equal(qa.to_host(), chan[f"fill_{name}"]), name
+    qa, ra = sp.grid_array.from_host(grid, q), sp.grid_array.from_host(grid, chan["src_rhs0"])
+    sp.source_term(qa, ra, sp.body_force_t(*CHANNEL_FORCE))
+    assert np.array_equal(ra.to_host(), chan["src_rhs1"])
+
+    gas = sp.ideal_gas_t(GAMMA, RGAS)
+    flux = sp.flux_desc(product_flux(0))
+    qa, ra = sp.grid_array.from_host(grid, chan["adv_q0"]), sp.grid_array(grid, 0.0)
+    ex = sp.make_exchange(qa, (1, 0, 1))
+    wall, force = sp.noslip_isothermal_wall(CHANNEL_WALL_T), sp.body_force_t(*CHANNEL_FORCE)
+
+    def calc_rhs(r, qq, t):
+        sp.flux_div(qq, r, flux, sp.overwrite)
+        sp.source_term(qq, r, force)
+
+    def boundary_cond(qq, t):
+        ex.exchange(qq)
+        sp.boundary_fill(qq, sp.boundary.ymin | sp.boundary.ymax, wall)
+
+    ti = sp.integrator_t(sp.time_axis_t(0.0, float(chan["adv_dt"][0])), sp.rk4_t, sp.integrator_data_t(qa, ra, sp.rk4_t),
+                         calc_rhs, boundary_cond, sp.state_transform_t(gas))
+    for _ in range(3):
+        ti.advance()
+    assert rel_l2(ti.solution().to_host(), chan["adv_q3"]) < 1e-12

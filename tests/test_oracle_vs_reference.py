@@ -132,3 +132,55 @@ def test_partition_matches_reference_tables(ref_lib, nglob, nranks):
             assert np.array_equal(g2r[s[:, 3]], s[:, 1]) and np.array_equal(g2r[s[:, 4]], s[:, 2])
             assert np.array_equal(g2l[s[:, 3]], s[:, 8])          # local id of the source block on the sender
             assert np.array_equal(g2l[r[:, 4]], r[:, 15])
+
+
+# ---- "next" rows: boundary_fill and source_term (channel runs) --------------------------------------------------
+WALL_T = 310.0
+BCS = {
+    "noslip_isothermal_y": dict(mask=(0, 0, 1, 1, 0, 0), a=(1, -1, -1, -1, -1), b=(0, 2 * WALL_T, 0, 0, 0)),
+    "adiabatic_all": dict(mask=(1, 1, 1, 1, 1, 1), a=(1, 1, -1, -1, -1)),
+    "symmetry_x_z": dict(mask=(1, 1, 0, 0, 1, 1), a=(1, 1, 1, 1, 1), a_normal=-1.0),
+    "extrap1_ymax": dict(mask=(0, 0, 0, 1, 0, 0), kind=1, order=1),
+    "extrap2_all": dict(mask=(1, 1, 1, 1, 1, 1), kind=1, order=2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(BCS))
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_boundary_fill_bit_exact(ref_lib, name, nranks):
+    """oracle restatement of algs::boundary_fill (src/grid/boundary_fill.h:32-133) against the reference itself"""
+    from oracle import port, ref
+    nb, n, ng = (2, 3, 2), (8, 4, 8), 2
+    q = make_state(nb, n, ng, seed=41)
+    bc = ref.make_bc(**BCS[name])
+    cfg = oracle_cfg(nb, n, ng, periodic=(0, 0, 0), nranks=nranks)
+    want = ref_lib.boundary_fill(cfg, bc, q.ravel())
+    got = port.boundary_fill(cfg, bc, q.ravel())
+    assert np.array_equal(got, want)
+    assert not np.array_equal(got, q.ravel())
+
+
+def test_source_term_bit_exact(ref_lib):
+    from oracle import port, ref
+    nb, n, ng = (2, 1, 2), (8, 8, 4), 2
+    q = make_state(nb, n, ng, seed=42)
+    rhs0 = np.random.default_rng(3).standard_normal(q.size)
+    bc = ref.make_bc(mask=(0,) * 6, force=(3.5, -0.25, 0.125))
+    cfg = oracle_cfg(nb, n, ng)
+    assert np.array_equal(port.source_term(cfg, bc, q.ravel(), rhs0), ref_lib.source_term(cfg, bc, q.ravel(), rhs0))
+
+
+@pytest.mark.parametrize("integ", [0, 2])
+def test_channel_trajectory(ref_lib, integ):
+    """x/z periodic, isothermal no-slip walls in y, body force: exchange + boundary_fill + flux_div + source_term + RK"""
+    from oracle import port, ref
+    nb, n, ng = (2, 2, 2), (8, 8, 8), 2
+    periodic = (1, 0, 1)
+    q0 = make_state(nb, n, ng, seed=43)
+    cfg = oracle_cfg(nb, n, ng, scheme=0, integrator=integ, periodic=periodic, nranks=2)
+    bc = ref.make_bc(force=(40.0, 0.0, 0.0), **BCS["noslip_isothermal_y"])
+    q0 = port.boundary_fill(cfg, bc, port.exchange(cfg, q0.ravel()))
+    dt = 0.2 * (2 * np.pi / 16) / port.reduce_umax(cfg, q0)
+    want, _ = ref_lib.advance_channel(cfg, bc, q0, dt, 3)
+    got = port.advance_channel(cfg, bc, q0, dt, 3)
+    assert rel_l2(got, want) < 1e-14
