@@ -158,6 +158,15 @@ int  spb_exchange_create(spb_exchange** out, const int nblocks[3], const int nx[
  * src.min[0..3], src.size[0..2], dst.min[0..3]   (index 3 = local block id, -1 if not owned). */
 int  spb_exchange_create_from_tables(spb_exchange** out, const int nx[3], const int ng[3], int rank, int nranks,
                                      const int64_t* send, int64_t nsend, const int64_t* recv, int64_t nrecv);
+/* AMR (reference src/grid/get_transaction.h:100-263, transactions.h:136-234): adds the interpolation transactions
+ * (patch_fill_t lists exchange_config_t::send_data[1] / recv_data[1]) to a plan made from tables. 26 int64 each: the 16
+ * fields above with source = the donor region, then dest.size[0..2], i_coeff[0..2], i_incr[0..2], 0. A destination cell
+ * (ix,iy,iz) of the box is 1/8 of the sum of the 2^3 donors at source.min + ((ix << (i_coeff+1)) >> 1) + d*i_incr
+ * (fine -> coarse: mean of the covering fine cells; coarse -> fine: injection), make_exchange.h:208-314. In a peer message
+ * the interpolation section follows the injection section. Call before the first device call of the plan. */
+int  spb_exchange_add_interp(spb_exchange* e, const int64_t* send, int64_t nsend, const int64_t* recv, int64_t nrecv);
+int64_t spb_exchange_num_interp_send(const spb_exchange* e);
+int64_t spb_exchange_num_interp_recv(const spb_exchange* e);
 void spb_exchange_destroy(spb_exchange* e);
 int64_t spb_exchange_num_send(const spb_exchange* e);
 int64_t spb_exchange_num_recv(const spb_exchange* e);

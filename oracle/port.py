@@ -88,6 +88,34 @@ def advance_channel(cfg, bc, q, dt, nsteps):
     return out
 
 
+class SpoAmr(C.Structure):
+    _fields_ = [("nblocks", C.c_int64), ("bbox", C.POINTER(C.c_double)), ("inj", C.POINTER(C.c_int64)), ("ninj", C.c_int64),
+                ("itp", C.POINTER(C.c_int64)), ("nitp", C.c_int64)]
+
+
+_amr_keep = None
+
+
+def set_amr(boxes=None, inj=None, itp=None):
+    """AMR grid description for the following calls (block boxes + the reference's own transaction tables, all ranks'
+    send lists concatenated); set_amr() returns to the uniform lattice."""
+    global _amr_keep
+    if boxes is None:
+        lib().spo_set_amr(None)
+        _amr_keep = None
+        return
+    boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+    inj = np.ascontiguousarray(inj, dtype=np.int64).reshape(-1, 16)
+    itp = np.ascontiguousarray(itp, dtype=np.int64).reshape(-1, 26)
+    a = SpoAmr()
+    a.nblocks = boxes.shape[0]
+    a.bbox = boxes.ctypes.data_as(C.POINTER(C.c_double))
+    a.inj, a.ninj = inj.ctypes.data_as(C.POINTER(C.c_int64)), inj.shape[0]
+    a.itp, a.nitp = itp.ctypes.data_as(C.POINTER(C.c_int64)), itp.shape[0]
+    _amr_keep = (boxes, inj, itp, a)
+    lib().spo_set_amr(C.byref(a))
+
+
 def exchange_tables(cfg, rank, cap=1 << 16):
     send = np.zeros((cap, 16), dtype=np.int64)
     recv = np.zeros((cap, 16), dtype=np.int64)

@@ -127,6 +127,36 @@ def advance_channel(cfg, bc, q, dt, nsteps):
     return out, sec.value
 
 
+def set_amr(passes):
+    """AMR: the following calls build the grid on amr_blocks_t and refine, pass by pass, the listed global blocks in all
+    directions (constraint factor2). `passes` = list of lists of global block ids; [] returns to the uniform lattice.
+    Buffers are then sized by block_boxes()[0] blocks in global block order."""
+    counts = np.array([len(p) for p in passes], dtype=np.int64)
+    ids = np.array([b for p in passes for b in p], dtype=np.int64)
+    i64 = C.POINTER(C.c_int64)
+    lib().ref_set_amr(len(passes), counts.ctypes.data_as(i64), ids.ctypes.data_as(i64))
+
+
+def block_boxes(cfg, cap=4096):
+    n = C.c_int64(0)
+    boxes = np.zeros((cap, 6))
+    _check(lib().ref_block_boxes(C.byref(cfg), C.byref(n), _ptr(boxes), C.c_int64(cap)))
+    assert n.value <= cap
+    return int(n.value), boxes[:n.value].copy()
+
+
+def interp_tables(cfg, rank, cap=1 << 16):
+    send = np.zeros((cap, 26), dtype=np.int64)
+    recv = np.zeros((cap, 26), dtype=np.int64)
+    ns, nr = C.c_int64(0), C.c_int64(0)
+    offs = np.zeros((cfg.nranks, 6), dtype=np.int64)
+    i64 = C.POINTER(C.c_int64)
+    _check(lib().ref_interp_tables(C.byref(cfg), int(rank), send.ctypes.data_as(i64), recv.ctypes.data_as(i64),
+                                   C.c_int64(cap), C.byref(ns), C.byref(nr), offs.ctypes.data_as(i64)))
+    assert ns.value <= cap and nr.value <= cap
+    return send[:ns.value].copy(), recv[:nr.value].copy(), offs
+
+
 def exchange_tables(cfg, rank, cap=1 << 16):
     send = np.zeros((cap, 16), dtype=np.int64)
     recv = np.zeros((cap, 16), dtype=np.int64)

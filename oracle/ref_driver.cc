@@ -80,6 +80,8 @@ extern "C"
 namespace
 {
     std::string g_last_error;
+    // refinement passes (lists of global block ids) applied by with_setup; empty = uniform cartesian lattice
+    std::vector<std::vector<std::size_t>> g_amr_refine;
 
     // algs::boundary_fill (reference src/grid/boundary_fill.h:32-133) with the kernels of ref_bc
     template <typename arr_t>
@@ -177,18 +179,36 @@ namespace
             spade::bound_box_t<real_t, 3> bounds;
             for (int d = 0; d < 3; ++d) { bounds.min(d) = c.bounds[2*d]; bounds.max(d) = c.bounds[2*d+1]; }
             spade::coords::identity<real_t> coords;
-            spade::grid::cartesian_blocks_t blocks(num_blocks, bounds);
-            spade::grid::cartesian_grid_t grid(cells_in_block, blocks, coords, pool);
-            prim_t fill1 = 0.0;
-            flux_t fill2 = 0.0;
-            spade::grid::grid_array prim(grid, fill1, exchange_cells, spade::device::cpu);
-            spade::grid::grid_array rhs (grid, fill2, exchange_cells, spade::device::cpu);
             spade::ctrs::array<bool, 3> periodic(bool(c.periodic[0]), bool(c.periodic[1]), bool(c.periodic[2]));
-            auto handle = spade::grid::make_exchange(prim, periodic);
-            const std::size_t per_block = prim.data.size()/std::max<std::size_t>(1, grid.get_num_local_blocks());
-            std::size_t first_glob = grid.get_num_local_blocks() > 0
-                ? grid.get_partition().to_global(spade::utils::tag[spade::partition::local](std::size_t(0))).value : 0;
-            func(pool, grid, prim, rhs, handle, first_glob*per_block, prim.data.size());
+            auto body = [&](auto& grid)
+            {
+                prim_t fill1 = 0.0;
+                flux_t fill2 = 0.0;
+                spade::grid::grid_array prim(grid, fill1, exchange_cells, spade::device::cpu);
+                spade::grid::grid_array rhs (grid, fill2, exchange_cells, spade::device::cpu);
+                auto handle = spade::grid::make_exchange(prim, periodic);
+                const std::size_t per_block = prim.data.size()/std::max<std::size_t>(1, grid.get_num_local_blocks());
+                std::size_t first_glob = grid.get_num_local_blocks() > 0
+                    ? grid.get_partition().to_global(spade::utils::tag[spade::partition::local](std::size_t(0))).value : 0;
+                func(pool, grid, prim, rhs, handle, first_glob*per_block, prim.data.size());
+            };
+            if (g_amr_refine.empty())
+            {
+                spade::grid::cartesian_blocks_t blocks(num_blocks, bounds);
+                spade::grid::cartesian_grid_t grid(cells_in_block, blocks, coords, pool);
+                body(grid);
+            }
+            else
+            {
+                // AMR (reference src/amr/amr_blocks.h, src/grid/cartesian_grid.h:331-368): the grid is built on the unrefined
+                // tree and refined before any array exists; every listed global block is split in all directions
+                spade::amr::amr_blocks_t blocks(num_blocks, bounds);
+                spade::grid::cartesian_grid_t grid(cells_in_block, blocks, coords, pool);
+                using refine_t = typename decltype(blocks)::refine_type;
+                for (const auto& pass: g_amr_refine)
+                    grid.refine_blocks(pass, periodic, refine_t{true, true, true}, spade::amr::constraints::factor2);
+                body(grid);
+            }
         });
     }
 
@@ -205,12 +225,94 @@ extern "C"
 {
     const char* ref_last_error() { return g_last_error.c_str(); }
 
-    // doubles in the global padded array
+    // doubles in the global padded array (uniform lattice)
     int64_t ref_array_size(const ref_cfg* c)
     {
         int64_t n = 5;
         for (int d = 0; d < 3; ++d) n *= (int64_t)(c->ncells[d] + 2*c->ng)*c->nblocks[d];
         return n;
+    }
+
+    // AMR: subsequent calls build the grid on amr_blocks_t and apply these refinement passes (npass lists, each
+    // counts[p] global block ids, concatenated in `ids`); npass = 0 returns to the uniform lattice
+    void ref_set_amr(int npass, const int64_t* counts, const int64_t* ids)
+    {
+        g_amr_refine.clear();
+        for (int p = 0; p < npass; ++p)
+        {
+            g_amr_refine.emplace_back(ids, ids + counts[p]);
+            ids += counts[p];
+        }
+    }
+
+    // number of global blocks and their bounding boxes [nblocks][6] (global block order) of the current grid
+    int ref_block_boxes(const ref_cfg* c, int64_t* nblocks, double* boxes, int64_t cap)
+    {
+        return guarded([&]
+        {
+            with_setup(*c, [&](auto& pool, auto& grid, auto& prim, auto& rhs, auto& handle, std::size_t off, std::size_t cnt)
+            {
+                if (pool.rank() != 0) return;
+                const std::size_t n = grid.get_num_global_blocks();
+                *nblocks = (int64_t)n;
+                for (std::size_t lb = 0; lb < n && (int64_t)lb < cap; ++lb)
+                {
+                    const auto& bx = grid.get_blocks().get_block_box(lb);
+                    for (int d = 0; d < 3; ++d) { boxes[6*lb + 2*d] = bx.min(d); boxes[6*lb + 2*d + 1] = bx.max(d); }
+                }
+            });
+        });
+    }
+
+    // Interpolation (fine <-> coarse) transaction tables of rank `rank`: patch_fill_t lists send_data[1] / recv_data[1]
+    // (reference src/grid/transactions.h:136-234, get_transaction.h:100-263). 26 int64 per transaction: the 16 fields of
+    // ref_exchange_tables (source box = donor region), then dest.size(0..2), i_coeff[3], i_incr[3], 0.
+    // offs: per peer the 6 intrp_offsets entries in the order of ref_exchange_tables.
+    int ref_interp_tables(const ref_cfg* c, int rank, int64_t* out_send, int64_t* out_recv, int64_t cap,
+        int64_t* n_send, int64_t* n_recv, int64_t* offs)
+    {
+        return guarded([&]
+        {
+            with_setup(*c, [&](auto& pool, auto& grid, auto& prim, auto& rhs, auto& handle, std::size_t off, std::size_t cnt)
+            {
+                if (pool.rank() != rank) return;
+                using namespace spade::udci;
+                const auto& cfg = handle.config;
+                const auto dump = [&](const auto& list, int64_t* out, int64_t* n)
+                {
+                    *n = (int64_t)list.size();
+                    int64_t idx = 0;
+                    for (const auto& pf: list)
+                    {
+                        if (idx >= cap) break;
+                        const auto& tr = pf.patches;
+                        int64_t* o = out + 26*idx;
+                        o[0] = int64_t(pf.tag); o[1] = tr.rank_send; o[2] = tr.rank_recv;
+                        o[3] = int64_t(tr.glob_source_blk); o[4] = int64_t(tr.glob_dest_blk);
+                        for (int d = 0; d < 4; ++d) o[5+d]  = tr.source.min(d);
+                        for (int d = 0; d < 3; ++d) o[9+d]  = tr.source.size(d);
+                        for (int d = 0; d < 4; ++d) o[12+d] = tr.dest.min(d);
+                        for (int d = 0; d < 3; ++d) o[16+d] = tr.dest.size(d);
+                        for (int d = 0; d < 3; ++d) o[19+d] = pf.i_coeff[d];
+                        for (int d = 0; d < 3; ++d) o[22+d] = pf.i_incr[d];
+                        o[25] = 0;
+                        ++idx;
+                    }
+                };
+                dump(cfg.send_data[1_c], out_send, n_send);
+                dump(cfg.recv_data[1_c], out_recv, n_recv);
+                const auto& io = cfg.intrp_offsets;
+                for (int p = 0; p < c->nranks; ++p)
+                {
+                    offs[6*p+0] = int64_t(io.send_message_size[p]);
+                    offs[6*p+1] = int64_t(io.recv_message_size[p]);
+                    offs[6*p+2] = int64_t(io.send_rank_offsets[p]);
+                    offs[6*p+3] = int64_t(io.send_rank_sizes[p]);
+                    offs[6*p+4] = int64_t(io.recv_rank_offsets[p]);
+                    offs[6*p+5] = int64_t(io.recv_rank_sizes[p]);
+                }
+            });
+        });
     }
 
     // rhs (+)= flux_div(q); q must have its ghosts filled by the caller

@@ -68,6 +68,9 @@ SYMBOLS = {
     "spb_exchange_create": (C.c_int, [C.POINTER(C.c_void_p), _ip, _ip, _ip, _ip, C.c_int, C.c_int]),
     "spb_exchange_create_from_tables": (C.c_int, [C.POINTER(C.c_void_p), _ip, _ip, C.c_int, C.c_int, _i64p,
                                                   C.c_int64, _i64p, C.c_int64]),
+    "spb_exchange_add_interp": (C.c_int, [C.c_void_p, _i64p, C.c_int64, _i64p, C.c_int64]),
+    "spb_exchange_num_interp_send": (C.c_int64, [C.c_void_p]),
+    "spb_exchange_num_interp_recv": (C.c_int64, [C.c_void_p]),
     "spb_exchange_destroy": (None, [C.c_void_p]),
     "spb_exchange_num_send": (C.c_int64, [C.c_void_p]),
     "spb_exchange_num_recv": (C.c_int64, [C.c_void_p]),

@@ -134,6 +134,23 @@ class cartesian_grid_t:
         self._handles = {}
         self._bnd = {}
 
+    @staticmethod
+    def from_boxes(cells_in_block, boxes, group=None, first_block=0):
+        """A grid given by the bounding boxes of this rank's blocks ([nlb][6], local order): what SPADE's
+        cartesian_grid_t on amr::amr_blocks_t hands over after refine_blocks (cartesian_grid.h:331-368; every block keeps
+        the same cell count, only its box and so its dx differ). The refinement logic itself stays in SPADE (SURVEY 2 #18)."""
+        g = cartesian_grid_t.__new__(cartesian_grid_t)
+        g.num_cell = [int(x) for x in cells_in_block]
+        g.blocks = None
+        g._group = group if group is not None else pool_t()
+        g._boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 6)
+        g.num_local_blocks = g._boxes.shape[0]
+        g.first_block = int(first_block)
+        g._bbox = g._boxes.reshape(-1).copy()
+        g._handles = {}
+        g._bnd = {}
+        return g
+
     def handle(self, num_exch):
         """spb_grid for arrays with `num_exch` exchange cells (device image of grid_geometry_t)."""
         key = tuple(int(x) for x in num_exch)
@@ -174,7 +191,7 @@ class cartesian_grid_t:
         return self.num_cell if d is None else self.num_cell[d]
 
     def get_dx(self, d, lb=0):
-        box = self.blocks.get_block_box(self.first_block + lb)
+        box = self.blocks.get_block_box(self.first_block + lb) if self.blocks is not None else self._boxes[lb]
         return (box[2 * d + 1] - box[2 * d]) / self.num_cell[d]
 
     def get_grid_size(self):
@@ -391,13 +408,25 @@ class flux_div_rhs_t:
 class arr_exchange_t:
     """make_exchange(array, periodic) -> handle; handle.exchange(array, pool) (make_exchange.h:111-421)."""
 
-    def __init__(self, grid, num_exch, periodic):
+    def __init__(self, grid, num_exch, periodic, tables=None):
         self.grid = grid
         self.pool = grid.group()
         self._h = C.c_void_p()
-        check(lib().spb_exchange_create(C.byref(self._h), int3(grid.blocks.num_blocks), int3(grid.num_cell),
-                                        int3(num_exch), int3([int(bool(p)) for p in periodic]),
-                                        self.pool.rank(), self.pool.size()))
+        i64 = C.POINTER(C.c_int64)
+        if tables is None:
+            check(lib().spb_exchange_create(C.byref(self._h), int3(grid.blocks.num_blocks), int3(grid.num_cell),
+                                            int3(num_exch), int3([int(bool(p)) for p in periodic]),
+                                            self.pool.rank(), self.pool.size()))
+        else:
+            # transaction tables marshalled from SPADE's exchange_config_t (the C++ shim does the same): injection lists,
+            # and for AMR grids the interpolation lists
+            send, recv = (np.ascontiguousarray(t, dtype=np.int64).reshape(-1, 16) for t in tables[:2])
+            check(lib().spb_exchange_create_from_tables(C.byref(self._h), int3(grid.num_cell), int3(num_exch), self.pool.rank(),
+                                                        self.pool.size(), send.ctypes.data_as(i64), len(send),
+                                                        recv.ctypes.data_as(i64), len(recv)))
+            if len(tables) > 2:
+                isend, irecv = (np.ascontiguousarray(t, dtype=np.int64).reshape(-1, 26) for t in tables[2:4])
+                check(lib().spb_exchange_add_interp(self._h, isend.ctypes.data_as(i64), len(isend), irecv.ctypes.data_as(i64), len(irecv)))
         self.send_cells = [int(lib().spb_exchange_send_cells(self._h, p)) for p in range(self.pool.size())]
         self.recv_cells = [int(lib().spb_exchange_recv_cells(self._h, p)) for p in range(self.pool.size())]
         self._sendbuf, self._recvbuf = {}, {}
@@ -510,8 +539,10 @@ class exchange_bc_t:
         self.handle.exchange(q)
 
 
-def make_exchange(array, periodic):
-    return arr_exchange_t(array.grid, array.num_exch, periodic)
+def make_exchange(array, periodic, tables=None):
+    """make_exchange(array, periodic); `tables` = (send, recv[, interp_send, interp_recv]) builds the plan from transaction
+    tables produced by SPADE's own exchange_config_t (needed for AMR grids, whose topology stays in SPADE)."""
+    return arr_exchange_t(array.grid, array.num_exch, periodic, tables)
 
 
 # ---- domain boundaries (reference src/grid/boundary_fill.h) -------------------------------------------------------

@@ -13,7 +13,11 @@
 struct spb_trans
 {
     int64_t f[16];   // tag, rank_send, rank_recv, glob_src, glob_dst, src.min[4], src.size[3], dst.min[4]
-    int64_t cells() const { return f[9]*f[10]*f[11]; }
+    // interpolation (patch_fill_t) only: dest.size[3], i_coeff[3], i_incr[3]; the source box is then the donor region
+    int64_t dsize[3] = {0, 0, 0}, ic[3] = {0, 0, 0}, inc[3] = {0, 0, 0};
+    bool interp = false;
+    // cells of the message = destination volume (a patch_fill_t packs into the size the receiver expects, transactions.h:149-153)
+    int64_t cells() const { return interp ? dsize[0]*dsize[1]*dsize[2] : f[9]*f[10]*f[11]; }
 };
 
 namespace spb
@@ -23,7 +27,9 @@ namespace spb
         long long src_off;   // offset (doubles) of the source box origin in q, -1 if not local
         long long dst_off;   // offset (doubles) of the destination box origin in q, -1 if not local
         long long buf_off;   // offset (doubles) of this transaction inside its peer message
-        int bx, by, bz;
+        int bx, by, bz;      // destination box (= source box for injections)
+        int interp;          // 1: patch_fill_t (AMR): destination cell = mean of 2^3 donors of the source box
+        int ic[3], inc[3];   // i_coeff, i_incr of the patch_fill_t (reference src/grid/transactions.h:147)
     };
     struct WorkItem { int trans; int begin; };   // element range [begin, begin + ITEM) of a transaction
 
@@ -35,7 +41,9 @@ struct spb_exchange
     int nx[3], ng[3], np[3];
     int rank, nranks;
     int64_t nlocal, first_block;
-    std::vector<spb_trans> send, recv;                 // sorted like the reference
+    std::vector<spb_trans> send, recv;                 // injection lists, sorted like the reference
+    std::vector<spb_trans> isend, irecv;               // interpolation lists (AMR), same order rule; empty on uniform lattices
+    std::vector<int64_t> inj_send_cells, inj_recv_cells;   // per peer: the injection section that precedes the interpolation section
     std::vector<int64_t> send_rank_off, send_rank_cnt, recv_rank_off, recv_rank_cnt;
     std::vector<int64_t> send_cells, recv_cells;       // per peer message size in cells
     // device side (built lazily on the first device call)
@@ -70,17 +78,26 @@ namespace spb
     static void finish_plan(spb_exchange* e)
     {
         // stable sort by (peer asc, tag desc): reference src/grid/exchange_config.h:379-397
-        std::stable_sort(e->send.begin(), e->send.end(), [](const spb_trans& a, const spb_trans& b)
-            { if (a.f[2] != b.f[2]) return a.f[2] < b.f[2]; if (a.f[0] != b.f[0]) return a.f[0] > b.f[0]; return a.cells() < b.cells(); });
-        std::stable_sort(e->recv.begin(), e->recv.end(), [](const spb_trans& a, const spb_trans& b)
-            { if (a.f[1] != b.f[1]) return a.f[1] < b.f[1]; if (a.f[0] != b.f[0]) return a.f[0] > b.f[0]; return a.cells() < b.cells(); });
+        auto by_recv = [](const spb_trans& a, const spb_trans& b)
+            { if (a.f[2] != b.f[2]) return a.f[2] < b.f[2]; if (a.f[0] != b.f[0]) return a.f[0] > b.f[0]; return a.cells() < b.cells(); };
+        auto by_send = [](const spb_trans& a, const spb_trans& b)
+            { if (a.f[1] != b.f[1]) return a.f[1] < b.f[1]; if (a.f[0] != b.f[0]) return a.f[0] > b.f[0]; return a.cells() < b.cells(); };
+        std::stable_sort(e->send.begin(), e->send.end(), by_recv);
+        std::stable_sort(e->recv.begin(), e->recv.end(), by_send);
+        std::stable_sort(e->isend.begin(), e->isend.end(), by_recv);
+        std::stable_sort(e->irecv.begin(), e->irecv.end(), by_send);
         const int n = e->nranks;
         e->send_rank_off.assign(n, 0); e->send_rank_cnt.assign(n, 0); e->recv_rank_off.assign(n, 0); e->recv_rank_cnt.assign(n, 0);
         e->send_cells.assign(n, 0); e->recv_cells.assign(n, 0);
         for (const auto& t: e->send) { e->send_rank_cnt[t.f[2]]++; e->send_cells[t.f[2]] += t.cells(); }
         for (const auto& t: e->recv) { e->recv_rank_cnt[t.f[1]]++; e->recv_cells[t.f[1]] += t.cells(); }
+        e->inj_send_cells = e->send_cells; e->inj_recv_cells = e->recv_cells;
+        // a peer message = injection section, then interpolation section (make_exchange.h:133-135,208-209)
+        for (const auto& t: e->isend) e->send_cells[t.f[2]] += t.cells();
+        for (const auto& t: e->irecv) e->recv_cells[t.f[1]] += t.cells();
         int64_t so = 0, ro = 0;
         for (int p = 0; p < n; ++p) { e->send_rank_off[p] = so; so += e->send_rank_cnt[p]; e->recv_rank_off[p] = ro; ro += e->recv_rank_cnt[p]; }
+        e->dev_ready = false;
     }
 
     static long long box_origin(const spb_exchange* e, const int64_t* mn)   // mn = {i, j, k, lb}
@@ -89,37 +106,55 @@ namespace spb
         return 5ll*((mn[0] + e->ng[0]) + (long long)e->np[0]*((mn[1] + e->ng[1]) + (long long)e->np[1]*((mn[2] + e->ng[2]) + (long long)e->np[2]*mn[3])));
     }
 
+    static void free_device(spb_exchange* e)
+    {
+        if (e->d_send) cudaFree(e->d_send);
+        if (e->d_recv) cudaFree(e->d_recv);
+        for (auto p: e->d_items_send) if (p) cudaFree(p);
+        for (auto p: e->d_items_recv) if (p) cudaFree(p);
+        e->d_send = nullptr; e->d_recv = nullptr; e->d_items_send.clear(); e->d_items_recv.clear();
+    }
+
     static int build_device(spb_exchange* e)
     {
         if (e->dev_ready) return 0;
+        free_device(e);
         const int n = e->nranks;
-        auto build = [&](const std::vector<spb_trans>& list, const std::vector<int64_t>& roff, const std::vector<int64_t>& rcnt, bool peer_is_recv,
+        // device list = injection transactions followed by interpolation transactions; the work items of a peer run over
+        // its injection section first, then its interpolation section, like the reference's message layout
+        auto build = [&](const std::vector<spb_trans>& inj, const std::vector<spb_trans>& itp, bool is_send, const std::vector<int64_t>& inj_cells,
                          DevTrans** d_list, std::vector<std::vector<WorkItem>>& items, std::vector<WorkItem*>& d_items) -> int
         {
-            std::vector<DevTrans> h(list.size());
+            std::vector<DevTrans> h(inj.size() + itp.size());
             items.assign(n, {}); d_items.assign(n, nullptr);
-            for (int p = 0; p < n; ++p)
+            std::vector<long long> boff(n, 0);
+            auto add = [&](const spb_trans& tr, size_t t, long long base)
             {
-                long long boff = 0;
-                for (int64_t t = roff[p]; t < roff[p] + rcnt[p]; ++t)
-                {
-                    const spb_trans& tr = list[t];
-                    DevTrans& d = h[t];
-                    d.src_off = box_origin(e, &tr.f[5]);
-                    d.dst_off = box_origin(e, &tr.f[12]);
-                    d.buf_off = boff;
-                    d.bx = (int)tr.f[9]; d.by = (int)tr.f[10]; d.bz = (int)tr.f[11];
-                    const long long nel = 5ll*tr.cells();
-                    boff += nel;
-                    for (long long b = 0; b < nel; b += ITEM) items[p].push_back(WorkItem{(int)t, (int)b});
-                }
+                const int p = (int)(is_send ? tr.f[2] : tr.f[1]);
+                DevTrans& d = h[t];
+                d.src_off = box_origin(e, &tr.f[5]);
+                d.dst_off = box_origin(e, &tr.f[12]);
+                d.buf_off = base + boff[p];
+                d.interp = tr.interp ? 1 : 0;
+                for (int k = 0; k < 3; ++k) { d.ic[k] = (int)tr.ic[k]; d.inc[k] = (int)tr.inc[k]; }
+                d.bx = (int)(tr.interp ? tr.dsize[0] : tr.f[9]); d.by = (int)(tr.interp ? tr.dsize[1] : tr.f[10]); d.bz = (int)(tr.interp ? tr.dsize[2] : tr.f[11]);
+                const long long nel = 5ll*tr.cells();
+                boff[p] += nel;
+                for (long long b = 0; b < nel; b += ITEM) items[p].push_back(WorkItem{(int)t, (int)b});
+            };
+            for (size_t t = 0; t < inj.size(); ++t) add(inj[t], t, 0);
+            std::fill(boff.begin(), boff.end(), 0);
+            for (size_t t = 0; t < itp.size(); ++t)
+            {
+                const int p = (int)(is_send ? itp[t].f[2] : itp[t].f[1]);
+                add(itp[t], inj.size() + t, 5ll*inj_cells[p]);
+            }
+            for (int p = 0; p < n; ++p)
                 if (!items[p].empty())
                 {
                     SPB_CUDA(cudaMalloc((void**)&d_items[p], sizeof(WorkItem)*items[p].size()));
                     SPB_CUDA(cudaMemcpy(d_items[p], items[p].data(), sizeof(WorkItem)*items[p].size(), cudaMemcpyHostToDevice));
                 }
-            }
-            (void)peer_is_recv;
             if (!h.empty())
             {
                 SPB_CUDA(cudaMalloc((void**)d_list, sizeof(DevTrans)*h.size()));
@@ -127,9 +162,9 @@ namespace spb
             }
             return 0;
         };
-        int rc = build(e->send, e->send_rank_off, e->send_rank_cnt, true, &e->d_send, e->items_send, e->d_items_send);
+        int rc = build(e->send, e->isend, true, e->inj_send_cells, &e->d_send, e->items_send, e->d_items_send);
         if (rc) return rc;
-        rc = build(e->recv, e->recv_rank_off, e->recv_rank_cnt, false, &e->d_recv, e->items_recv, e->d_items_recv);
+        rc = build(e->recv, e->irecv, false, e->inj_recv_cells, &e->d_recv, e->items_recv, e->d_items_recv);
         if (rc) return rc;
         e->dev_ready = true;
         return 0;
@@ -140,6 +175,7 @@ namespace spb
         if (!e || !d_nbr) { set_error("exchange_fuse_table: null argument"); return SPB_ERR_BAD_ARG; }
         for (int d = 0; d < 3; ++d)
             if (e->nx[d] != nx[d] || e->ng[d] != ng[d]) { set_error("fused exchange: the plan was made for another block shape"); return SPB_ERR_BAD_ARG; }
+        if (!e->isend.empty() || !e->irecv.empty()) e->fuse_state = -1;          // AMR interpolation: separate exchange kernels
         if (e->fuse_state == 0 || (e->fuse_state == 1 && e->nbr_blocks != nlb))
         {
             if (e->d_nbr) { cudaFree(e->d_nbr); e->d_nbr = nullptr; }
@@ -197,9 +233,26 @@ namespace spb
             const int r = el / row, c = el - r*row;
             const int iz = r / tr.by, iy = r - iz*tr.by;
             const long long rel = c + iy*pitch_j + iz*pitch_k;
-            if (MODE == 0) q[tr.dst_off + rel] = qsrc[tr.src_off + rel];
-            if (MODE == 1) buf[tr.buf_off + el] = qsrc[tr.src_off + rel];
-            if (MODE == 2) q[tr.dst_off + rel] = bufsrc[tr.buf_off + el];
+            double val;
+            if (MODE == 2) val = bufsrc[tr.buf_off + el];
+            else if (!tr.interp) val = qsrc[tr.src_off + rel];
+            else
+            {
+                // patch_fill_t (make_exchange.h:233-256, transactions.h:176-201): donor offset ((ix << (i_coeff+1)) >> 1) + d*i_incr,
+                // the 2^3 donors are added in the order d0 fastest and the sum is multiplied by 1/8
+                const int ix = c / 5, v = c - 5*ix;
+                const int i0 = (ix << (tr.ic[0] + 1)) >> 1, j0 = (iy << (tr.ic[1] + 1)) >> 1, k0 = (iz << (tr.ic[2] + 1)) >> 1;
+                double sum = 0.0;
+                #pragma unroll
+                for (int iv = 0; iv < 8; ++iv)
+                {
+                    const int d0 = iv & 1, d1 = (iv >> 1) & 1, d2 = (iv >> 2) & 1;
+                    sum = __dadd_rn(sum, qsrc[tr.src_off + 5ll*(i0 + d0*tr.inc[0]) + (j0 + d1*tr.inc[1])*pitch_j + (k0 + d2*tr.inc[2])*pitch_k + v]);
+                }
+                val = sum*0.125;
+            }
+            if (MODE == 1) buf[tr.buf_off + el] = val;
+            else q[tr.dst_off + rel] = val;
         }
     }
 }
@@ -283,14 +336,43 @@ extern "C"
         return 0;
     }
 
+    int spb_exchange_add_interp(spb_exchange* e, const int64_t* send, int64_t nsend, const int64_t* recv, int64_t nrecv)
+    {
+        using namespace spb;
+        if (!e || nsend < 0 || nrecv < 0 || (nsend > 0 && !send) || (nrecv > 0 && !recv)) { set_error("spb_exchange_add_interp: bad argument"); return SPB_ERR_BAD_ARG; }
+        auto fill = [](std::vector<spb_trans>& list, const int64_t* tab, int64_t n)
+        {
+            list.resize(n);
+            for (int64_t i = 0; i < n; ++i)
+            {
+                const int64_t* r = tab + 26*i;
+                std::copy(r, r + 16, list[i].f);
+                for (int d = 0; d < 3; ++d) { list[i].dsize[d] = r[16+d]; list[i].ic[d] = r[19+d]; list[i].inc[d] = r[22+d]; }
+                list[i].interp = true;
+            }
+        };
+        for (int64_t i = 0; i < nsend + nrecv; ++i)
+        {
+            const int64_t* r = (i < nsend) ? send + 26*i : recv + 26*(i - nsend);
+            for (int d = 0; d < 3; ++d)
+                if (r[19+d] < -1 || r[19+d] > 1 || r[22+d] < 0 || r[22+d] > 1 || r[16+d] < 0) { set_error("spb_exchange_add_interp: bad i_coeff / i_incr / size"); return SPB_ERR_BAD_ARG; }
+            if (r[1] < 0 || r[1] >= e->nranks || r[2] < 0 || r[2] >= e->nranks) { set_error("spb_exchange_add_interp: rank out of range"); return SPB_ERR_BAD_ARG; }
+        }
+        fill(e->isend, send, nsend);
+        fill(e->irecv, recv, nrecv);
+        finish_plan(e);
+        e->fuse_state = 0;
+        return 0;
+    }
+
+    int64_t spb_exchange_num_interp_send(const spb_exchange* e) { return (int64_t)e->isend.size(); }
+    int64_t spb_exchange_num_interp_recv(const spb_exchange* e) { return (int64_t)e->irecv.size(); }
+
     void spb_exchange_destroy(spb_exchange* e)
     {
         if (!e) return;
-        if (e->d_send) cudaFree(e->d_send);
-        if (e->d_recv) cudaFree(e->d_recv);
+        spb::free_device(e);
         if (e->d_nbr) cudaFree(e->d_nbr);
-        for (auto p: e->d_items_send) if (p) cudaFree(p);
-        for (auto p: e->d_items_recv) if (p) cudaFree(p);
         delete e;
     }
 

@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from util import make_state, oracle_cfg, zero_ghosts  # noqa: E402
+from util import amr_state, make_state, oracle_cfg, zero_ghosts  # noqa: E402
 from oracle import ref  # noqa: E402
 
 CHANNEL_WALL_T = 310.0
@@ -86,7 +86,36 @@ def main():
     q3, _ = ref.advance_channel(cfgc, bc, q0, dt, 3)
     ch["adv_q0"], ch["adv_q3"], ch["adv_dt"] = q0.reshape(q.shape), q3.reshape(q.shape), np.array([dt, umax])
     np.savez_compressed(os.path.join(HERE, "channel_small.npz"), **ch)
-    for f in ("hotpath_small.npz", "exchange_tables.npz", "channel_small.npz"):
+    # (vi) AMR (config 5): 2x2x2 roots, block 0 refined in all directions (15 blocks; second case: a child refined again,
+    #      which drags its coarse neighbours along through the factor-2 constraint). Block boxes, the reference's own
+    #      injection + interpolation tables for 1 and 3 ranks, exchange, flux_div on per-block dx, an RK4 trajectory.
+    amr = {}
+    for case, roots, n_amr, passes in (("a", (2, 2, 2), (8, 4, 4), [[0]]), ("b", (3, 2, 1), (4, 4, 4), [[0], [0]])):
+        ref.set_amr(passes)
+        cfg1 = oracle_cfg(roots, n_amr, NG, scheme=0, integrator=0, periodic=(1, 1, 1), nranks=1)
+        nblk, boxes = ref.block_boxes(cfg1)
+        amr[f"{case}_boxes"] = boxes
+        q_in = zero_ghosts(amr_state(boxes, n_amr, NG, seed=61), NG)         # regenerated by the tests from the seed
+        qe = ref.exchange(cfg1, q_in.ravel())
+        amr[f"{case}_q_ex"] = qe.reshape(q_in.shape)
+        if case == "a":
+            amr[f"{case}_rhs"] = ref.flux_div(cfg1, qe).reshape(q_in.shape)
+            umax = ref.reduce_umax(cfg1, qe)
+            dt = 0.2 * (2 * np.pi / 64) / umax
+            q2, _ = ref.advance(cfg1, qe, dt, 2)
+            amr[f"{case}_q_adv"], amr[f"{case}_dt"] = q2.reshape(q_in.shape), np.array([dt, umax])
+        for nranks in (1, 3):
+            cfg = oracle_cfg(roots, n_amr, NG, periodic=(1, 1, 1), nranks=nranks)
+            assert np.array_equal(ref.exchange(cfg, q_in.ravel()), qe)       # the rank count does not matter
+            for rank in range(nranks):
+                s_, r_, o_ = ref.exchange_tables(cfg, rank)
+                si, ri, oi = ref.interp_tables(cfg, rank)
+                for nm, arr in (("send", s_), ("recv", r_), ("offs", o_), ("isend", si), ("irecv", ri), ("ioffs", oi)):
+                    amr[f"{case}_{nm}_{nranks}_{rank}"] = arr
+        ref.set_amr([])
+        print("amr case", case, nblk, "blocks")
+    np.savez_compressed(os.path.join(HERE, "amr_small.npz"), **amr)
+    for f in ("hotpath_small.npz", "exchange_tables.npz", "channel_small.npz", "amr_small.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -39,6 +39,20 @@ def make_state(nb, n, ng, seed=0, perturb=1e-2, bounds=None, jump=False):
     return q
 
 
+def amr_state(boxes, n, ng, seed):
+    """smooth positive state + seeded perturbation on blocks given by their boxes, all cells incl. ghosts analytic"""
+    q = np.zeros((boxes.shape[0], n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng, 5))
+    for lb in range(boxes.shape[0]):
+        ax = [boxes[lb, 2 * d] + (np.arange(-ng, n[d] + ng) + 0.5) * (boxes[lb, 2 * d + 1] - boxes[lb, 2 * d]) / n[d] for d in range(3)]
+        Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+        q[lb, ..., 0] = 101325.0 * (1 + 0.05 * np.cos(X) * np.cos(Y))
+        q[lb, ..., 1] = 300.0 * (1 + 0.02 * np.sin(X + 2 * Y - Z))
+        q[lb, ..., 2] = U0 * np.sin(X) * np.cos(Y) * np.cos(Z)
+        q[lb, ..., 3] = -U0 * np.cos(X) * np.sin(Y) * np.cos(Z)
+        q[lb, ..., 4] = 10.0 * np.sin(Z) * np.cos(X + Y)
+    return q * (1 + 1e-2 * np.random.default_rng(seed).uniform(-1, 1, q.shape))
+
+
 def zero_ghosts(q, ng):
     out = q.copy()
     mask = np.zeros(q.shape[1:4], dtype=bool)
