@@ -162,10 +162,29 @@ namespace spade::b200
             }
             return out;
         };
-        if (config.send_data[1_c].size() != 0 || config.recv_data[1_c].size() != 0)
-            throw except::sp_exception("spade_b200: AMR interpolation transactions are not implemented yet (SURVEY 8a23)");
+        // AMR grids: the patch_fill_t lists (transactions.h:136-234) as 26-field records
+        const auto flatten_interp = [&](const auto& list)
+        {
+            std::vector<int64_t> out; out.reserve(26*list.size());
+            for (const auto& pf: list)
+            {
+                const auto& tr = pf.patches;
+                out.push_back(int64_t(pf.tag)); out.push_back(tr.rank_send); out.push_back(tr.rank_recv);
+                out.push_back(int64_t(tr.glob_source_blk)); out.push_back(int64_t(tr.glob_dest_blk));
+                for (int d = 0; d < 4; ++d) out.push_back(tr.source.min(d));
+                for (int d = 0; d < 3; ++d) out.push_back(tr.source.size(d));
+                for (int d = 0; d < 4; ++d) out.push_back(tr.dest.min(d));
+                for (int d = 0; d < 3; ++d) out.push_back(tr.dest.size(d));
+                for (int d = 0; d < 3; ++d) out.push_back(pf.i_coeff[d]);
+                for (int d = 0; d < 3; ++d) out.push_back(pf.i_incr[d]);
+                out.push_back(0);
+            }
+            return out;
+        };
         const auto send = flatten(config.send_data[0_c]);
         const auto recv = flatten(config.recv_data[0_c]);
+        const auto isend = flatten_interp(config.send_data[1_c]);
+        const auto irecv = flatten_interp(config.recv_data[1_c]);
         const auto& grid = array.get_grid();
         const auto ngv = array.get_num_exchange();
         const int nx[3] = {grid.get_num_cells(0), grid.get_num_cells(1), grid.get_num_cells(2)};
@@ -174,7 +193,106 @@ namespace spade::b200
         out.rank = grid.group().rank(); out.size = grid.group().size();
         check(spb_exchange_create_from_tables(&out.plan, nx, ng, out.rank, out.size, send.data(), (int64_t)send.size()/16,
                                               recv.data(), (int64_t)recv.size()/16), "spb_exchange_create_from_tables");
+        if (!isend.empty() || !irecv.empty())
+            check(spb_exchange_add_interp(out.plan, isend.data(), (int64_t)isend.size()/26, irecv.data(), (int64_t)irecv.size()/26), "spb_exchange_add_interp");
         return out;
+    }
+
+    // ---------------------------------------------------------------- callbacks the integrator can recognise
+    // The usual rhs callback of a SPADE solver, `[&](auto& rhs, const auto& q, const auto& t) { flux_div(q, rhs, f, traits); }`
+    // (development/cuda-tgv/main.cc:174-186), and the usual periodic boundary callback `handle.exchange(q, pool)`, as named
+    // types. Passed to integrator_t they behave exactly like the lambdas; because their types are known, integrate_advance
+    // (below) runs flux_div + the RK stage update + the same-rank ghost exchange as ONE kernel per stage.
+    template <typename flux_func_t> struct flux_div_rhs_t
+    {
+        flux_func_t flux_func;
+        template <typename rhs_arr_t, typename sol_arr_t, typename time_t>
+        void operator()(rhs_arr_t& rhs, const sol_arr_t& q, const time_t&) const
+        {
+            require_supported_array<sol_arr_t>();
+            const spb_flux_desc d = flux_desc(flux_func);
+            check(spb_flux_div(grid_handle(q), dev_ptr(q), dev_ptr(rhs), &d, 0, nullptr), "spb_flux_div");
+            check(spb_sync(nullptr), "spb_sync");
+        }
+    };
+    template <typename flux_func_t> inline flux_div_rhs_t<flux_func_t> flux_div_rhs(const flux_func_t& f) { return flux_div_rhs_t<flux_func_t>{f}; }
+
+    template <typename handle_t, typename group_t> struct exchange_bc_t
+    {
+        handle_t* handle;
+        group_t*  group;
+        template <typename sol_arr_t, typename time_t>
+        void operator()(sol_arr_t& q, const time_t&) const { handle->exchange(q, *group); }
+    };
+    template <typename handle_t, typename group_t> inline exchange_bc_t<handle_t, group_t> exchange_bc(handle_t& h, group_t& g) { return exchange_bc_t<handle_t, group_t>{&h, &g}; }
+
+    template <typename T> struct is_flux_div_rhs : std::false_type {};
+    template <typename F> struct is_flux_div_rhs<flux_div_rhs_t<F>> : std::true_type {};
+    template <typename T> struct is_exchange_bc : std::false_type {};
+    template <typename H, typename G> struct is_exchange_bc<exchange_bc_t<H, G>> : std::true_type {};
+
+    // scratch solution buffer of the fused stage kernels (q_out must differ from q_in), one per thread (= per GPU) and size
+    inline double* scratch_buffer(std::size_t doubles)
+    {
+        thread_local std::map<std::size_t, double*> cache;
+        auto it = cache.find(doubles);
+        if (it != cache.end()) return it->second;
+        double* p = nullptr;
+        if (cudaMalloc((void**)&p, sizeof(double)*doubles) != cudaSuccess) throw except::sp_exception("spade_b200: cudaMalloc of the stage scratch buffer failed");
+        cache[doubles] = p;
+        return p;
+    }
+
+    // ---------------------------------------------------------------- boundary_fill / source_term
+    // algs::boundary_fill(arr, boundaries, kern) for the kernels that are linear per variable (boundary_fill.h:104-129):
+    // ghost[v] = a[v]*image[v] + b[v]; with use_normal the velocity component along the boundary normal uses a_normal
+    struct mirror_kernel
+    {
+        double a[5] = {1, 1, 1, 1, 1}, b[5] = {0, 0, 0, 0, 0};
+        bool use_normal = false; double a_normal = 1.0;
+        static mirror_kernel noslip_isothermal(const double t_wall) { mirror_kernel k; k.a[1] = k.a[2] = k.a[3] = k.a[4] = -1.0; k.b[1] = 2.0*t_wall; return k; }
+        static mirror_kernel noslip_adiabatic() { mirror_kernel k; k.a[2] = k.a[3] = k.a[4] = -1.0; return k; }
+        static mirror_kernel symmetry() { mirror_kernel k; k.use_normal = true; k.a_normal = -1.0; return k; }
+    };
+    template <typename arr_t> inline void boundary_fill_desc(arr_t& arr, const boundary::identifier_t& boundaries, const spb_bc_desc& d)
+    {
+        require_supported_array<arr_t>();
+        const auto& grid = arr.get_grid();
+        const auto& geom = grid.geometry(partition::local);
+        for (int ib = 0; ib < 6; ++ib)
+        {
+            if (!boundaries(ib/2, ib%2)) continue;
+            std::vector<int64_t> blocks;
+            for (const auto lb: geom.boundary_blocks[ib].data(device::cpu)) blocks.push_back((int64_t)lb);
+            if (blocks.empty()) continue;
+            check(spb_boundary_fill(grid_handle(arr), dev_ptr(arr), ib/2, ib%2, blocks.data(), (int64_t)blocks.size(), &d, nullptr), "spb_boundary_fill");
+        }
+        check(spb_sync(nullptr), "spb_sync");
+    }
+    template <typename arr_t> inline void boundary_fill(arr_t& arr, const boundary::identifier_t& boundaries, const mirror_kernel& k)
+    {
+        spb_bc_desc d{};
+        d.kind = SPB_BC_MIRROR;
+        for (int v = 0; v < 5; ++v) { d.a[v] = k.a[v]; d.b[v] = k.b[v]; }
+        d.use_normal = k.use_normal ? 1 : 0; d.a_normal = k.a_normal;
+        boundary_fill_desc(arr, boundaries, d);
+    }
+    template <typename arr_t, const int order> inline void boundary_fill(arr_t& arr, const boundary::identifier_t& boundaries, const boundary::extrap_t<order>&)
+    {
+        spb_bc_desc d{};
+        d.kind = SPB_BC_EXTRAP; d.order = order;
+        boundary_fill_desc(arr, boundaries, d);
+    }
+    // pde_algs::source_term(q, rhs, func) for the body-force kernel S = (0, f.u, fx, fy, fz) (source_term.h:25-51)
+    struct body_force { double f[3] = {0, 0, 0}; };
+    template <typename sol_arr_t, typename rhs_arr_t> inline void source_term(const sol_arr_t& q, rhs_arr_t& rhs, const body_force& bf)
+    {
+        require_supported_array<sol_arr_t>();
+        spb_source_desc d{};
+        d.kind = SPB_SRC_BODY_FORCE;
+        for (int i = 0; i < 3; ++i) d.f[i] = bf.f[i];
+        check(spb_source_term(grid_handle(q), dev_ptr(q), dev_ptr(rhs), &d, nullptr), "spb_source_term");
+        check(spb_sync(nullptr), "spb_sync");
     }
 
     // ---------------------------------------------------------------- reductions
@@ -289,5 +407,152 @@ namespace spade::time_integration
         update(typename scheme_t::table_type::elem_t<num_stages - 1>(), typename scheme_t::accum_type());
         axis.time() += dt;
         boundary(q, axis.time());
+    }
+
+    // The same call again, selected when the rhs callback is b200::flux_div_rhs_t (and, for the ghost fusion, the boundary
+    // callback b200::exchange_bc_t): one kernel per stage, spb_flux_div_rk_stage[_exchange] (include/spade_b200.h). The stage
+    // coefficients are the coefficient differences of advance.h:47-55,84-92 folded into at most two residual inputs and one
+    // output per stage; a final update that needs more than two earlier residuals gets their combination prepared by the stage
+    // before it (rk4: C = k0/6 + k1/3 - 2 k2/3). Falls back to the two-kernel path for schemes outside that pattern.
+    template <typename axis_t, typename var_state_t, typename rhs_state_t, typename scheme_t, typename flux_func_t, typename boundary_t,
+              typename state_t, typename gas_t>
+    requires (scheme_t::is_rk_specialization && b200::on_gpu<var_state_t>)
+    void integrate_advance(axis_t& axis, integrator_data_t<var_state_t, rhs_state_t, scheme_t>& data, const scheme_t& scheme,
+                           const b200::flux_div_rhs_t<flux_func_t>& rhs, const boundary_t& boundary,
+                           const fluid_state::state_transform_t<gas_t, state_t>& trans)
+    {
+        b200::require_supported_array<var_state_t>();
+        static_assert(std::same_as<state_t, fluid_state::cons_t<double>>, "spade_b200: the fused update integrates conserved variables");
+        constexpr int n = scheme_t::table_type::rows();
+        using numeric_type = typename axis_t::value_type;
+        const spb_flux_desc fd = b200::flux_desc(rhs.flux_func);
+        const bool narrow = fd.diss == SPB_DISS_NONE && (fd.conv == SPB_CONV_NONE || fd.conv == SPB_CONV_TOTANI) && (fd.conv != SPB_CONV_NONE || fd.visc);
+
+        // diffs[i][j]: coefficient of k_j in the update that follows stage i (last row: the accumulation row)
+        double diffs[n][n];
+        algs::static_for<0, n>([&](const auto& ii)
+        {
+            constexpr int i = ii.value;
+            algs::static_for<0, n>([&](const auto& jj)
+            {
+                constexpr int j = jj.value;
+                using prev_t = typename scheme_t::table_type::template elem_t<i>::template elem_t<j>;
+                if constexpr (i + 1 < n)
+                {
+                    using curr_t = typename scheme_t::table_type::template elem_t<i + 1>::template elem_t<j>;
+                    using diff_t = typename detail::ratio_diff_t<curr_t, prev_t>::type;
+                    diffs[i][j] = detail::nonzero_t<diff_t>::value ? double(detail::coeff_value_t<numeric_type, diff_t>::value()) : 0.0;
+                }
+                else
+                {
+                    using curr_t = typename scheme_t::accum_type::template elem_t<j>;
+                    using diff_t = typename detail::ratio_diff_t<curr_t, prev_t>::type;
+                    diffs[i][j] = detail::nonzero_t<diff_t>::value ? double(detail::coeff_value_t<numeric_type, diff_t>::value()) : 0.0;
+                }
+            });
+        });
+        struct stage_t { int nin = 0; int in[2] = {0, 0}; double cq[2] = {0, 0}, co[2] = {0, 0}; double cq_self = 0, co_self = 0; int out = -1; };
+        stage_t plan[n];
+        bool ok = narrow && n <= 4;
+        int nfinal = 0;
+        for (int j = 0; j + 1 < n; ++j) if (diffs[n-1][j] != 0.0) ++nfinal;
+        const bool use_c = nfinal > 2;
+        for (int i = 0; i < n && ok; ++i)
+        {
+            stage_t& st = plan[i];
+            st.cq_self = diffs[i][i];
+            if (i == n - 1 && use_c) { st.nin = 1; st.in[0] = n - 2; st.cq[0] = 1.0; continue; }   // register n-2 holds C
+            for (int j = 0; j < i; ++j)
+            {
+                const bool prior = diffs[i][j] != 0.0;
+                const bool extra = use_c && i == n - 2 && diffs[n-1][j] != 0.0;
+                if (!prior && !extra) continue;
+                if (st.nin == 2) { ok = false; break; }
+                st.in[st.nin] = j; st.cq[st.nin] = diffs[i][j]; st.co[st.nin] = 0.0; ++st.nin;
+            }
+            if (use_c && i == n - 2)
+            {
+                st.out = n - 2; st.co_self = diffs[n-1][i];
+                for (int a = 0; a < st.nin; ++a) st.co[a] = diffs[n-1][st.in[a]];
+            }
+            else
+            {
+                bool later = false;
+                for (int m = i + 1; m < n; ++m) later = later || diffs[m][i] != 0.0;
+                if (later) { st.out = i; st.co_self = 1.0; }
+            }
+        }
+        if (!ok)
+        {
+            // outside the fused pattern: same two-kernel path as for an opaque rhs callback
+            const auto as_lambda = [&](auto& rr, const auto& qq, const auto& t) { rhs(rr, qq, t); };
+            integrate_advance(axis, data, scheme, as_lambda, boundary, trans);
+            return;
+        }
+
+        // time at which the boundary callback after stage i is evaluated: t + c_{i+1} dt, t + dt after the last one (advance.h:264-279)
+        double tfrac[n];
+        algs::static_for<0, n>([&](const auto& ii)
+        {
+            constexpr int i = ii.value;
+            if constexpr (i + 1 < n) tfrac[i] = double(detail::coeff_value_t<numeric_type, typename scheme_t::dt_type::template elem_t<i + 1>>::value());
+            else tfrac[i] = 1.0;
+        });
+        const auto t_start = axis.time();
+
+        auto& q = data.solution(0);
+        spb_grid* gh = b200::grid_handle(q);
+        const std::size_t nd = q.data.size();
+        double* bufs[2] = {b200::dev_ptr(q), b200::scratch_buffer(nd)};
+        const double dt = double(axis.timestep());
+        const int64_t nlb = (int64_t)q.get_grid().get_num_local_blocks();
+        spb_exchange* fuse = nullptr;
+        if constexpr (b200::is_exchange_bc<boundary_t>::value) { if (boundary.group->size() == 1) fuse = boundary.handle->plan; }
+        thread_local bool fuse_refused = false;
+        int cur = 0;
+        for (int i = 0; i < n; ++i)
+        {
+            const stage_t& st = plan[i];
+            spb_stage_desc sd{};
+            sd.nin = st.nin;
+            for (int a = 0; a < st.nin; ++a) { sd.in[a] = b200::dev_ptr(data.residual(st.in[a])); sd.cq[a] = st.cq[a]*dt; sd.co[a] = st.co[a]; }
+            sd.cq_self = st.cq_self*dt; sd.co_self = st.co_self;
+            sd.out = st.out >= 0 ? b200::dev_ptr(data.residual(st.out)) : nullptr;
+            bool ghosts_done = false;
+            if (fuse && !fuse_refused)
+            {
+                const int rc = spb_flux_div_rk_stage_exchange(gh, bufs[cur], bufs[1 - cur], &fd, &sd, fuse, 0, nlb, nullptr);
+                if (rc == SPB_ERR_UNSUPPORTED) fuse_refused = true;          // e.g. AMR interpolation: separate exchange from now on
+                else { b200::check(rc, "spb_flux_div_rk_stage_exchange"); ghosts_done = true; }
+            }
+            if (!ghosts_done) b200::check(spb_flux_div_rk_stage(gh, bufs[cur], bufs[1 - cur], &fd, &sd, 0, nlb, nullptr), "spb_flux_div_rk_stage");
+            cur = 1 - cur;
+            axis.time() = t_start + tfrac[i]*dt;
+            if (cur == 0)
+            {
+                if (!ghosts_done) boundary(q, axis.time());
+            }
+            else
+            {
+                // the stage result sits in the scratch buffer: the boundary callback needs a SPADE array, so it is applied after
+                // the last stage only when the result is back in q; in between the fused ghost stores (or a device-side local
+                // exchange on the raw buffer) keep the ghosts current
+                if (!ghosts_done)
+                {
+                    if constexpr (b200::is_exchange_bc<boundary_t>::value)
+                        b200::check(spb_exchange_local(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local");
+                    else
+                    {
+                        // opaque boundary callback: bring the state back into q so that the callback sees a SPADE array
+                        cudaMemcpyAsync(bufs[0], bufs[1], sizeof(double)*nd, cudaMemcpyDeviceToDevice, nullptr);
+                        cur = 0;
+                        boundary(q, axis.time());
+                    }
+                }
+            }
+        }
+        if (cur == 1) cudaMemcpyAsync(bufs[0], bufs[1], sizeof(double)*nd, cudaMemcpyDeviceToDevice, nullptr);    // odd number of stages
+        axis.time() = t_start + dt;
+        b200::check(spb_sync(nullptr), "spb_sync");
     }
 }

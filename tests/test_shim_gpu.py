@@ -19,5 +19,6 @@ def test_spade_api_solver_through_the_shim(scheme):
     out = subprocess.run([BIN, "2", "16", "2", str(scheme)], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(BIN))
     assert out.returncode == 0, out.stdout + out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line["rel_l2"] < 1e-12
+    assert line["rel_l2"] < 1e-12                  # callbacks as lambdas: flux_div(b200) + spb_rk_update + exchange
+    assert line["rel_l2_fused"] < 1e-12            # callbacks as b200::flux_div_rhs / b200::exchange_bc: one kernel per stage
     assert line["umax"] > 300.0
