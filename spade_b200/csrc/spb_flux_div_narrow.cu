@@ -25,30 +25,37 @@ namespace spb
 {
     namespace nrw
     {
-        constexpr int TI = 32, TJ = 8;
-        constexpr int NCOMPUTE = TI*TJ;                 // 8 warps
+        // Tile shapes: 32 x 8 (one warp per row) for blocks wider than 16 cells, 16 x 16 (two rows per warp) for blocks of
+        // up to 16 cells along i, which would leave half of every 32-wide row idle. Everything below is written on TI, TJ.
+        constexpr int NCOMPUTE = 256;                   // 8 compute warps, one cell column per thread
+        constexpr int NCW = NCOMPUTE/32;
         constexpr int NTHREADS = NCOMPUTE + 64;         // + edge warp + ghost warp
-        constexpr int TIp = TI + 2 + 2;                 // halo + 16-byte TMA start alignment slack
-        constexpr int TJp = TJ + 2;
         constexpr int NP = 3;                           // ring slots: planes k, k+1 resident, k+2 in flight
-        constexpr int PLANE_DOUBLES = TIp*TJp*5;
-        constexpr int PLANE_BYTES = PLANE_DOUBLES*8;
-        constexpr int PLANE_STRIDE = ((PLANE_BYTES + 127)/128*128)/8;
-        constexpr int PW = TI + 2;                      // published arrays: [NPUB][TJ+2][PW]
-        constexpr int PSZ = (TJ + 2)*PW;
         constexpr int NPUB = 7;                         // rho, cX, Dy.u, Dz.u, cY, Dz.v, Dx.v
-        constexpr int FX_DOUBLES = TJ*(TI + 1)*5;
-        constexpr int FY_DOUBLES = (TJ + 1)*TI*5;
-        constexpr int STAGE_DOUBLES = TJ*TI*5;          // 10 240 B, a multiple of 128
-        constexpr int OFF_P = NP*PLANE_STRIDE;
-        constexpr int OFF_STAGE_K = (OFF_P + NPUB*PSZ + 15)/16*16;        // 128-byte aligned for the TMA stores
-        constexpr int OFF_STAGE_Q = OFF_STAGE_K + STAGE_DOUBLES;
-        constexpr int OFF_FX = OFF_STAGE_Q + STAGE_DOUBLES;
-        constexpr int OFF_FY = OFF_FX + FX_DOUBLES;
-        constexpr int OFF_BAR = OFF_FY + FY_DOUBLES;
-        // fused ghost exchange: the same-rank neighbour table of this block (27 ints)
-        constexpr int OFF_NBR = (OFF_BAR + NP + 1 + 15)/16*16;
-        constexpr int SMEM_BYTES = (OFF_NBR + 16)*8 + 128;
+        template <int TI_, int TJ_> struct Lay
+        {
+            static_assert(TI_*TJ_ == NCOMPUTE && TI_ <= 32 && 2*TJ_ <= 32, "tile = 256 cells, rows within a warp, 2 TJ edge lanes");
+            static constexpr int TI = TI_, TJ = TJ_;
+            static constexpr int TIp = TI + 2 + 2;                 // halo + 16-byte TMA start alignment slack
+            static constexpr int TJp = TJ + 2;
+            static constexpr int PLANE_DOUBLES = TIp*TJp*5;
+            static constexpr int PLANE_BYTES = PLANE_DOUBLES*8;
+            static constexpr int PLANE_STRIDE = ((PLANE_BYTES + 127)/128*128)/8;
+            static constexpr int PW = TI + 2;                      // published arrays: [NPUB][TJ+2][PW]
+            static constexpr int PSZ = (TJ + 2)*PW;
+            static constexpr int FX_DOUBLES = TJ*(TI + 1)*5;
+            static constexpr int FY_DOUBLES = (TJ + 1)*TI*5;
+            static constexpr int STAGE_DOUBLES = TJ*TI*5;          // 10 240 B, a multiple of 128
+            static constexpr int OFF_P = NP*PLANE_STRIDE;
+            static constexpr int OFF_STAGE_K = (OFF_P + NPUB*PSZ + 15)/16*16;        // 128-byte aligned for the TMA stores
+            static constexpr int OFF_STAGE_Q = OFF_STAGE_K + STAGE_DOUBLES;
+            static constexpr int OFF_FX = OFF_STAGE_Q + STAGE_DOUBLES;
+            static constexpr int OFF_FY = OFF_FX + FX_DOUBLES;
+            static constexpr int OFF_BAR = OFF_FY + FY_DOUBLES;
+            // fused ghost exchange: the same-rank neighbour table of this block (27 ints)
+            static constexpr int OFF_NBR = (OFF_BAR + NP + 1 + 15)/16*16;
+            static constexpr int SMEM_BYTES = (OFF_NBR + 16)*8 + 128;
+        };
 
         enum { P_RHO = 0, P_CX /* Dy.v + Dz.w */, P_DYU, P_DZU, P_CY /* Dz.w + Dx.u */, P_DZV, P_DXV };
 
@@ -161,7 +168,7 @@ namespace spb
             }
         };
 
-        template <int CONV, int VISC, bool UNIF, bool FUSED>
+        template <int CONV, int VISC, bool UNIF, bool FUSED, int TI, int TJ>
         __global__ void __launch_bounds__(NTHREADS, 2)
         flux_div_narrow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_rhs,
                                const __grid_constant__ CUtensorMap tmap_qout, const __grid_constant__ CUtensorMap tmap_in0,
@@ -171,6 +178,10 @@ namespace spb
                                const __grid_constant__ GhostMaps GM, const int* __restrict__ nbr_tab,
                                double* __restrict__ qout_raw)
         {
+            using L = Lay<TI, TJ>;
+            constexpr int TIp = L::TIp, PLANE_BYTES = L::PLANE_BYTES, PLANE_STRIDE = L::PLANE_STRIDE, PW = L::PW, PSZ = L::PSZ;
+            constexpr int STAGE_DOUBLES = L::STAGE_DOUBLES, OFF_P = L::OFF_P, OFF_STAGE_K = L::OFF_STAGE_K, OFF_STAGE_Q = L::OFF_STAGE_Q;
+            constexpr int OFF_FX = L::OFF_FX, OFF_FY = L::OFF_FY, OFF_BAR = L::OFF_BAR, OFF_NBR = L::OFF_NBR;
             extern __shared__ __align__(128) double smem_raw[];
             double*   ring    = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
             double*   pub     = ring + OFF_P;
@@ -183,7 +194,7 @@ namespace spb
 
             const int tid = threadIdx.x;
             const int lane = tid & 31, warp = tid >> 5;
-            const bool is_edge = (warp == TJ), is_ghost = (warp == TJ + 1);
+            const bool is_edge = (warp == NCW), is_ghost = (warp == NCW + 1);
 
             int t = blockIdx.x;
             const int ti = t % G.tiles_i; t /= G.tiles_i;
@@ -236,7 +247,7 @@ namespace spb
             if (!is_edge && !is_ghost)
             {
                 // ======================= compute warps: one cell column per thread =======================
-                const int il = lane, jl = warp;
+                const int il = tid % TI, jl = tid / TI;
                 const bool active = (il < ni_t) && (jl < nj_t);
                 const int co = cell_off(il, jl);
                 const int po = pidx(il, jl);
@@ -443,8 +454,8 @@ namespace spb
                 // row job (lanes 0..31): cell (lane, -1) is published, cell (lane, nj_t) is the R cell of the upper y-face
                 // col job (lanes 0..15): cell (-1, lane) is published, cell (ni_t, lane-8) is the R cell of the upper x-face
                 const bool row_on = lane < ni_t;
-                const int  ccj = lane & 7;
-                const bool col_lo = lane < 8, col_on = (lane < 16) && (ccj < nj_t);
+                const int  ccj = lane % TJ;
+                const bool col_lo = lane < TJ, col_on = (lane < 2*TJ) && (ccj < nj_t);
                 const int  cci = col_lo ? -1 : ni_t;
                 const int co_r0 = cell_off(lane, -1), co_r1 = cell_off(lane, nj_t), co_c = cell_off(cci, ccj);
                 // z-neighbours (k-1, k) of the edge cells roll through registers: v,w for the row cells, u,w for the column cell
@@ -605,10 +616,12 @@ namespace spb
                     gzs = gez > 0 ? nz - G.ng[2] : 0;
                     prefetch_tmap(&GM.m[lane]);
                 }
-                // x pieces: lane = (half h, piece p): piece p = (side, row r) is 10 consecutive doubles = 5 double2; half 0 moves
-                // double2 0, 2, 4 and half 1 moves 1, 3. Everything that does not depend on the plane is computed here.
-                const int xp = lane & 15, xh = lane >> 4;
-                const int xside = xp >> 3, xr = xp & 7;
+                // x pieces: piece p = (side, row r) is 10 consecutive doubles = 5 double2. With TJ = 8 there are 16 pieces and two
+                // lanes share one (half 0 moves double2 0, 2, 4, half 1 moves 1, 3); with TJ = 16 every lane owns a whole piece.
+                // Everything that does not depend on the plane is computed here.
+                constexpr int NPIECE = 2*TJ, HALVES = 32/NPIECE;
+                const int xp = lane % NPIECE, xh = lane / NPIECE;
+                const int xside = xp / TJ, xr = xp % TJ;
                 const bool x_on = on && (xr < nj_t) && (xside ? (xhi0 >= 0 && xhi0 < TI) : (i0 == 0));
                 const int xsm = xr*(5*TI) + (xside ? 5*xhi0 : 0) + 2*xh;                       // first double2 of this lane in stage_q
                 const int xj = j0 + xr;
@@ -633,9 +646,12 @@ namespace spb
                         }
                         if (x_on)
                         {
-                            const double2 a0 = *reinterpret_cast<const double2*>(stage_q + xsm);
-                            const double2 a1 = *reinterpret_cast<const double2*>(stage_q + xsm + 4);
-                            const double2 a2 = xh ? a0 : *reinterpret_cast<const double2*>(stage_q + xsm + 8);
+                            // this lane's double2 of the piece: indices xh, xh + HALVES, ... < 5
+                            constexpr int NM = (5 + HALVES - 1)/HALVES;
+                            double2 a[NM];
+                            #pragma unroll
+                            for (int m = 0; m < NM; ++m)
+                                if (xh + m*HALVES < 5) a[m] = *reinterpret_cast<const double2*>(stage_q + xsm + 2*m*HALVES);
                             #pragma unroll
                             for (int ez = -1; ez <= 1; ++ez)
                             {
@@ -648,9 +664,9 @@ namespace spb
                                     if (dst < 0) continue;
                                     double* o = qout_raw + dst*G.block_stride + 5ll*xip + xrow*(xj - ey*G.nx[1] + G.ng[1])
                                                 + xplane*(kk - ez*nz + G.ng[2]) + 2*xh;
-                                    *reinterpret_cast<double2*>(o) = a0;
-                                    *reinterpret_cast<double2*>(o + 4) = a1;
-                                    if (!xh) *reinterpret_cast<double2*>(o + 8) = a2;
+                                    #pragma unroll
+                                    for (int m = 0; m < NM; ++m)
+                                        if (xh + m*HALVES < 5) *reinterpret_cast<double2*>(o + 2*m*HALVES) = a[m];
                                 }
                             }
                         }
@@ -676,12 +692,14 @@ namespace spb
     }
 
     // stage == nullptr: plain flux_div; otherwise the fused RK stage (q_out, stage description)
-    template <int CONV, int VISC>
-    int launch_fdiv_narrow(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
-                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const nrw::Stage* stage,
-                           spb_exchange* exch)
+    template <int CONV, int VISC, int TI, int TJ>
+    static int launch_fdiv_narrow_tile(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
+                                       int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const nrw::Stage* stage,
+                                       spb_exchange* exch)
     {
         using namespace nrw;
+        using L = Lay<TI, TJ>;
+        constexpr int TIp = L::TIp, TJp = L::TJp, SMEM_BYTES = L::SMEM_BYTES;
         for (int d = 0; d < 3; ++d)
             if (g->ng[d] < 1) { set_error("spb_flux_div: scheme needs 1 exchange cell"); return SPB_ERR_BAD_ARG; }
         if ((5*g->np[0]) % 2 != 0) { set_error("spb_flux_div: n0 + 2*g0 must be even (16-byte TMA row pitch)"); return SPB_ERR_UNSUPPORTED; }
@@ -780,8 +798,18 @@ namespace spb
             SPB_LAUNCH_CHECK();
             return 0;
         };
-        if (stage) return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, true>) : go(flux_div_narrow_kernel<CONV, VISC, false, true>);
-        return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, false>) : go(flux_div_narrow_kernel<CONV, VISC, false, false>);
+        if (stage) return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, true, TI, TJ>) : go(flux_div_narrow_kernel<CONV, VISC, false, true, TI, TJ>);
+        return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, false, TI, TJ>) : go(flux_div_narrow_kernel<CONV, VISC, false, false, TI, TJ>);
+    }
+
+    template <int CONV, int VISC>
+    int launch_fdiv_narrow(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const nrw::Stage* stage,
+                           spb_exchange* exch)
+    {
+        // blocks of up to 16 cells along i (16^3 blocks: BASELINE configs 1 and 5) would fill half of a 32-wide tile row
+        if (g->nx[0] <= 16) return launch_fdiv_narrow_tile<CONV, VISC, 16, 16>(g, q, rhs, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
+        return launch_fdiv_narrow_tile<CONV, VISC, 32, 8>(g, q, rhs, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
     }
 
     template int launch_fdiv_narrow<SPB_CONV_TOTANI, 1>(const spb_grid*, const double*, double*, const FluxParams&, int, int64_t, int64_t, cudaStream_t, double*, const nrw::Stage*, spb_exchange*);
