@@ -426,7 +426,8 @@ namespace spade::time_integration
         constexpr int n = scheme_t::table_type::rows();
         using numeric_type = typename axis_t::value_type;
         const spb_flux_desc fd = b200::flux_desc(rhs.flux_func);
-        const bool narrow = fd.diss == SPB_DISS_NONE && (fd.conv == SPB_CONV_NONE || fd.conv == SPB_CONV_TOTANI) && (fd.conv != SPB_CONV_NONE || fd.visc);
+        const bool narrow = (fd.diss == SPB_DISS_NONE && (fd.conv == SPB_CONV_NONE || fd.conv == SPB_CONV_TOTANI) && (fd.conv != SPB_CONV_NONE || fd.visc))
+                         || (fd.visc && ((fd.conv == SPB_CONV_TOTANI && fd.diss == SPB_DISS_FWENO) || fd.conv == SPB_CONV_CENT_KEEP4));   // fused stage available
 
         // diffs[i][j]: coefficient of k_j in the update that follows stage i (last row: the accumulation row)
         double diffs[n][n];

@@ -766,7 +766,9 @@ class integrator_t:
         self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
         if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
             f = rhs_calc.flux
-            if f.diss == DISS_NONE and f.conv in (CONV_NONE, CONV_TOTANI) and (f.conv != CONV_NONE or f.visc):
+            narrow = f.diss == DISS_NONE and f.conv in (CONV_NONE, CONV_TOTANI) and (f.conv != CONV_NONE or f.visc)
+            wide = bool(f.visc) and ((f.conv == CONV_TOTANI and f.diss == DISS_FWENO) or f.conv == CONV_CENT_KEEP4)
+            if narrow or wide:
                 self._plan = self._fused_plan(scheme)
 
     def solution(self):

@@ -53,10 +53,12 @@ namespace spb
         }
     };
 
-    template <int CONV, int DISS, int VISC>
+    // FUSED: the RK stage update of spb_flux_div_rk_stage rides on the rhs of each finished cell (see spb_flux.cuh:
+    // StageParams); rhs is then the residual register written (or null) and q_out the new state.
+    template <int CONV, int DISS, int VISC, bool FUSED>
     __global__ void __launch_bounds__(NTHREADS, 2)
     flux_div_kernel(const __grid_constant__ CUtensorMap tmap_q, double* __restrict__ rhs, const FluxParams P,
-                    const FdivDims G, const double* __restrict__ inv_dx_tab)
+                    const FdivDims G, const double* __restrict__ inv_dx_tab, double* __restrict__ q_out, const StageParams ST)
     {
         constexpr int H = stencil_halo<CONV, DISS>::value;
         using S = FdivSmem<H>;
@@ -126,8 +128,9 @@ namespace spb
         for (int d = 0; d < 4; ++d) { const int p = H + (d - 2); acc.pl[d] = (p >= 0 ? p : 0)*S::PLANE_STRIDE; }
 
         double rprev[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // partial rhs of cell k-1 (x, y and lower-z parts)
-        double* rhs_col = rhs + lb*G.block_stride
+        const long long col0 = lb*G.block_stride
             + 5ll*((i0 + il + G.ng[0]) + (long long)G.np[0]*((j0 + jl + G.ng[1]) + (long long)G.np[1]*G.ng[2]));
+        double* rhs_col = rhs + col0;
         const long long kstride = 5ll*G.np[0]*G.np[1];
 
         for (int k = 0; k <= nz; ++k)
@@ -146,12 +149,56 @@ namespace spb
             if (k >= 1 && active)
             {
                 double* o = rhs_col + (long long)(k - 1)*kstride;
-                #pragma unroll
-                for (int v = 0; v < 5; ++v)
+                if (!FUSED)
                 {
-                    double r = fma(-Fz[v], invdx[2], rprev[v]);
-                    if (G.increment) r += o[v];
-                    o[v] = r;
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v)
+                    {
+                        double r = fma(-Fz[v], invdx[2], rprev[v]);
+                        if (G.increment) r += o[v];
+                        o[v] = r;
+                    }
+                }
+                else
+                {
+                    const long long c = col0 + (long long)(k - 1)*kstride;
+                    double w[5], ov[5];
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v)
+                    {
+                        const double r = fma(-Fz[v], invdx[2], rprev[v]);
+                        w[v] = ST.cq_self*r; ov[v] = ST.co_self*r;
+                    }
+                    #pragma unroll
+                    for (int a = 0; a < 2; ++a)
+                        if (a < ST.nin)
+                        {
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v)
+                            {
+                                const double x = ST.in[a][c + v];
+                                w[v] = fma(ST.cq[a], x, w[v]); ov[v] = fma(ST.co[a], x, ov[v]);
+                            }
+                        }
+                    if (ST.has_out)
+                    {
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v) o[v] = ov[v];
+                    }
+                    // prim -> cons (fluid_state.h:103-116), add the increment, cons -> prim (fluid_state.h:119-135)
+                    double qc[5];
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) qc[v] = acc(v, 0, 0, -1);
+                    const double rho0 = qc[0]*rcp_nr(P.R*qc[1]);
+                    const double u2 = fma(qc[2], qc[2], fma(qc[3], qc[3], qc[4]*qc[4]));
+                    const double rho  = rho0 + w[0];
+                    const double rhoE = fma(0.5*rho0, u2, qc[0]*ST.inv_gm1) + w[1];
+                    const double mx = fma(rho0, qc[2], w[2]), my = fma(rho0, qc[3], w[3]), mz = fma(rho0, qc[4], w[4]);
+                    const double ir = rcp_nr(rho);
+                    const double un = ir*mx, vn = ir*my, wn = ir*mz;
+                    const double pn = ST.gm1*fma(-0.5*rho, fma(un, un, fma(vn, vn, wn*wn)), rhoE);
+                    double* qo = q_out + c;
+                    qo[0] = pn; qo[1] = pn*ir*ST.inv_R; qo[2] = un; qo[3] = vn; qo[4] = wn;
                 }
             }
 
@@ -215,9 +262,9 @@ namespace spb
         }
     }
 
-    template <int CONV, int DISS, int VISC>
+    template <int CONV, int DISS, int VISC, bool FUSED = false>
     static int launch_fdiv(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
-                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream)
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out = nullptr, const StageParams* stage = nullptr)
     {
         constexpr int H = stencil_halo<CONV, DISS>::value;
         using S = FdivSmem<H>;
@@ -247,9 +294,11 @@ namespace spb
         G.increment = increment;
         const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
         if (nblk <= 0) return 0;
-        auto kern = flux_div_kernel<CONV, DISS, VISC>;
+        auto kern = flux_div_kernel<CONV, DISS, VISC, FUSED>;
+        StageParams SP{};
+        if (stage) SP = *stage;
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-        kern<<<(unsigned)nblk, NTHREADS, S::BYTES, stream>>>(tq, rhs, P, G, g->inv_dx_dev);
+        kern<<<(unsigned)nblk, NTHREADS, S::BYTES, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP);
         SPB_LAUNCH_CHECK();
         return 0;
     }
@@ -329,7 +378,15 @@ extern "C"
         SPB_NARROW(SPB_CONV_TOTANI, 0);
         SPB_NARROW(SPB_CONV_NONE,   1);
 #undef SPB_NARROW
-        set_error("spb_flux_div_rk_stage: the fused stage is implemented for the one-ghost-cell functor set (totani_lr and/or visc_lr)");
+        // wide stencils: the stage update rides on the rhs kernel; no ghost fusion there (the caller runs spb_exchange_local)
+        if (exch) { set_error("spb_flux_div_rk_stage_exchange: ghost fusion is implemented for the one-ghost-cell functor set (use spb_flux_div_rk_stage + spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
+#define SPB_WIDE(C, D) if (f->conv == C && f->diss == D && f->visc != 0) \
+            return launch_fdiv<C, D, 1, true>(g, q_in, sd->out, P, 0, lb_begin, lb_end, st, q_out, &S)
+        SPB_WIDE(SPB_CONV_TOTANI,     SPB_DISS_FWENO);
+        SPB_WIDE(SPB_CONV_CENT_KEEP4, SPB_DISS_NONE);
+        SPB_WIDE(SPB_CONV_CENT_KEEP4, SPB_DISS_FWENO);
+#undef SPB_WIDE
+        set_error("spb_flux_div_rk_stage: the fused stage is implemented for totani_lr and/or visc_lr, and for the hybrid / cent_keep<4> schemes with visc_lr");
         return SPB_ERR_UNSUPPORTED;
     }
 

@@ -457,7 +457,8 @@ namespace spb
                 const int  ccj = lane % TJ;
                 const bool col_lo = lane < TJ, col_on = (lane < 2*TJ) && (ccj < nj_t);
                 const int  cci = col_lo ? -1 : ni_t;
-                const int co_r0 = cell_off(lane, -1), co_r1 = cell_off(lane, nj_t), co_c = cell_off(cci, ccj);
+                const int rl = min(lane, TI - 1);                // 16-wide tiles: the upper half of the warp has no row cell (its loads stay inside the plane)
+                const int co_r0 = cell_off(rl, -1), co_r1 = cell_off(rl, nj_t), co_c = cell_off(cci, ccj);
                 // z-neighbours (k-1, k) of the edge cells roll through registers: v,w for the row cells, u,w for the column cell
                 double r0m[2], r00[2], r1m[2], r10[2], ccm[2], cc0[2];
                 {

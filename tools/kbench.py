@@ -88,9 +88,10 @@ def main():
         sp.check(lib.spb_flux_div_rk_stage_exchange(q.h, C.c_void_p(q.data.data_ptr()), C.c_void_p(q2.data.data_ptr()), C.byref(flux),
                                                     C.byref(sd), ex._h if ghost else None, 0, grid.num_local_blocks, None))
 
-    if a.scheme in ("central", "euler"):
+    if a.scheme in ("central", "euler", "hybrid", "ck4"):
         for nin, out in ((0, 1), (1, 1), (2, 1), (1, 0)):
             timeit(f"fused_stage[nin={nin},out={out}]", lambda nin=nin, out=out: fused(nin, out), 80.0 + 40.0 * nin + 40.0 * out)
+    if a.scheme in ("central", "euler"):
         for nin, out in ((0, 1), (1, 1), (2, 1), (1, 0)):
             timeit(f"fused_stage+ghosts[nin={nin},out={out}]", lambda nin=nin, out=out: fused(nin, out, True),
                    80.0 + 40.0 * nin + 40.0 * out + 40.0 * ghost_frac)
