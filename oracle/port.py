@@ -4,7 +4,7 @@ import ctypes as C
 import os
 import subprocess
 import numpy as np
-from .ref import RefBc, RefCfg, make_bc, make_cfg  # same struct layouts (spo_cfg == ref_cfg, spo_bc == ref_bc)
+from .ref import RefBc, RefCfg, RefCoords, make_bc, make_cfg, make_coords  # same struct layouts (spo_cfg == ref_cfg, spo_bc == ref_bc, spo_coords == RefCoords)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
@@ -28,6 +28,9 @@ def lib():
         _lib.spo_array_size.restype = C.c_int64
         _lib.spo_offset.restype = C.c_int64
         _lib.spo_offset.argtypes = [C.POINTER(RefCfg), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
+        for f in (_lib.spo_coord_map, _lib.spo_coord_deriv):
+            f.restype = C.c_double
+            f.argtypes = [C.POINTER(RefCoords), C.c_int, C.c_double]
     return _lib
 
 
@@ -86,6 +89,24 @@ def advance_channel(cfg, bc, q, dt, nsteps):
     out = np.array(q, dtype=np.float64, copy=True)
     assert lib().spo_advance_channel(C.byref(cfg), C.byref(bc), _ptr(out), C.c_double(dt), int(nsteps)) == 0
     return out
+
+
+_coords_keep = None
+
+
+def set_coords(cd=None):
+    """General coordinates (coords::diagonal_coords) for the following calls; set_coords() returns to coords::identity."""
+    global _coords_keep
+    _coords_keep = cd
+    lib().spo_set_coords(None if cd is None else C.byref(cd))
+
+
+def coord_map(cd, d, x):
+    return float(lib().spo_coord_map(C.byref(cd), int(d), float(x)))
+
+
+def coord_deriv(cd, d, x):
+    return float(lib().spo_coord_deriv(C.byref(cd), int(d), float(x)))
 
 
 class SpoAmr(C.Structure):

@@ -181,3 +181,80 @@ def cons2prim(gamma, R, w):
     p = np.zeros(5)
     lib().ref_cons2prim(C.c_double(gamma), C.c_double(R), _ptr(w), _ptr(p))
     return p
+
+
+# ---- curvilinear (coords::diagonal_coords) convective path: oracle/_ref/libspade_ref_curv.so, see ref_driver_curv.cc ----
+CURV_LIB_PATH = os.path.join(_HERE, "_ref", "libspade_ref_curv.so")
+COORD_IDENTITY, COORD_SCALED, COORD_TANH, COORD_QUAD = 0, 1, 2, 3
+
+
+class RefCoords(C.Structure):
+    """ref_coords (and the head of spo_coords): one 1-D mapping per direction."""
+    _fields_ = [("kind", C.c_int * 3), ("par", (C.c_double * 4) * 3), ("metric_at_physical", C.c_int)]
+
+
+def make_coords(maps, metric_at_physical=True):
+    """maps: three entries, each None / ("scaled", k) / ("tanh", y0, y1, inflation, rate) / ("quad",)."""
+    names = {"identity": COORD_IDENTITY, "scaled": COORD_SCALED, "tanh": COORD_TANH, "quad": COORD_QUAD}
+    cd = RefCoords()
+    for d, m in enumerate(maps):
+        m = ("identity",) if m is None else tuple(m)
+        cd.kind[d] = names[m[0]]
+        for i, x in enumerate(m[1:]):
+            cd.par[d][i] = float(x)
+    cd.metric_at_physical = int(bool(metric_at_physical))
+    return cd
+
+
+def curv_available():
+    return os.path.exists(CURV_LIB_PATH)
+
+
+_clib = None
+
+
+def curv_lib():
+    global _clib
+    if _clib is None:
+        _clib = C.CDLL(CURV_LIB_PATH)
+        _clib.refc_last_error.restype = C.c_char_p
+        _clib.refc_map.restype = C.c_double
+        _clib.refc_deriv.restype = C.c_double
+        _clib.refc_map.argtypes = [C.POINTER(RefCoords), C.c_int, C.c_double]
+        _clib.refc_deriv.argtypes = [C.POINTER(RefCoords), C.c_int, C.c_double]
+    return _clib
+
+
+def _ccheck(rc):
+    if rc != 0:
+        raise RuntimeError("curvilinear reference driver failed: " + curv_lib().refc_last_error().decode())
+
+
+def curv_map(cd, d, x):
+    return float(curv_lib().refc_map(C.byref(cd), int(d), float(x)))
+
+
+def curv_deriv(cd, d, x):
+    return float(curv_lib().refc_deriv(C.byref(cd), int(d), float(x)))
+
+
+def curv_flux_div(cfg, cd, q, rhs=None, increment=False):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.zeros_like(q) if rhs is None else np.array(rhs, dtype=np.float64, copy=True)
+    _ccheck(curv_lib().refc_flux_div(C.byref(cfg), C.byref(cd), _ptr(q), _ptr(out), int(increment)))
+    return out
+
+
+def curv_geometry(cfg, cd, lb):
+    n = [int(x) for x in cfg.ncells]
+    jac = np.zeros((n[2], n[1], n[0]))
+    nrm = np.zeros((n[2], n[1], n[0], 3))
+    xyz = np.zeros((n[2], n[1], n[0], 3))
+    _ccheck(curv_lib().refc_geometry(C.byref(cfg), C.byref(cd), C.c_int64(lb), _ptr(jac), _ptr(nrm), _ptr(xyz)))
+    return jac, nrm, xyz
+
+
+def curv_advance(cfg, cd, q, dt, nsteps):
+    out = np.array(q, dtype=np.float64, copy=True)
+    _ccheck(curv_lib().refc_advance(C.byref(cfg), C.byref(cd), _ptr(out), C.c_double(dt), int(nsteps)))
+    return out
