@@ -77,6 +77,35 @@ void spb_grid_destroy(spb_grid* g);
 int64_t spb_grid_array_size(const spb_grid* g);                    /* doubles in one 5-variable array */
 int64_t spb_grid_offset(const spb_grid* g, int v, int i, int j, int k, int64_t lb);
 
+/* ---- general coordinates: replaces the geometry of coords::diagonal_coords ---------------------
+ * reference src/core/coord_system.h:65-90 (one 1-D mapping x_d(xi_d) per direction), calc_normal_vector :250-267,
+ * calc_jacobian :295-302, used by flux_div_basic.h:49-71 and info::metric (src/omni/infos/info_metric.h:24-32).
+ * A diagonal system is separable, so the whole geometry is three 1-D tables per block and direction of the
+ * coordinate derivative m_d = dx_d/dxi_d (host arrays, copied by the call):
+ *   area[d]  [nlb][n_d + 2 g_d]      m_d at the cell centres AS info::metric EVALUATES IT. The reference passes the
+ *                                    mapped position into coord_deriv (info_metric.h:31: grid.get_coords(idx)); a
+ *                                    caller that wants the reference's numbers fills this table the same way, one
+ *                                    that wants the consistent metric passes the same values as jac[d].
+ *   jac[d]   [nlb][n_d + 2 g_d]      m_d at the computational cell centres (calc_jacobian, flux_div_basic.h:49-50)
+ *   face[d]  [nlb][n_d + 2 g_d + 1]  m_d at the computational face positions (entry i = lower face of padded cell i)
+ * With a metric set, spb_flux_div / spb_flux_div_rk_stage compute
+ *   rhs(c) = J(c) sum_d (F_lower - F_upper)/dxi_d,   J = 1/(m_0 m_1 m_2),   F = flux with metric vector (m_t1 m_t2) e_d,
+ * and the face gradient of visc_lr / ducros_t is transformed as d/dx_d = (1/m_d) d/dxi_d (face[d] for the normal
+ * direction, jac[t] for the tangential ones). That transform is NOT in the reference (info_gradient.h:83
+ * static_asserts coords::identity): the convective functors match the reference on stretched grids, the viscous and
+ * sensor terms are this library's completion. spb_source_term divides by J like source_term.h:38-46.
+ * The one-kernel ghost fusion (spb_flux_div_rk_stage_exchange with a plan) is for identity coordinates; with a metric
+ * it returns SPB_ERR_UNSUPPORTED and the caller runs spb_flux_div_rk_stage + spb_exchange_local.
+ * m == NULL returns the grid to coords::identity. */
+typedef struct spb_metric_desc
+{
+    const double* area[3];
+    const double* jac[3];
+    const double* face[3];
+} spb_metric_desc;
+int spb_grid_set_metric(spb_grid* g, const spb_metric_desc* m);
+int spb_grid_has_metric(const spb_grid* g);
+
 /* ---- RHS: replaces pde_algs::flux_div(q, rhs, flux_func, traits) ------------------------------
  * reference src/pde-algs/flux-div/flux_div.h:23-41, flux_div_basic.h:17-77.
  * rhs(cell) (+)= sum_dir (F_lowerface - F_upperface) / dx_dir on interior cells (identity coords,

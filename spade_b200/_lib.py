@@ -37,6 +37,11 @@ class SourceDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("f", C.c_double * 5)]
 
 
+class MetricDesc(C.Structure):
+    """spb_metric_desc (include/spade_b200.h)."""
+    _fields_ = [("area", C.POINTER(C.c_double) * 3), ("jac", C.POINTER(C.c_double) * 3), ("face", C.POINTER(C.c_double) * 3)]
+
+
 class SpbError(RuntimeError):
     pass
 
@@ -52,6 +57,8 @@ SYMBOLS = {
     "spb_grid_destroy": (None, [C.c_void_p]),
     "spb_grid_array_size": (C.c_int64, [C.c_void_p]),
     "spb_grid_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),
+    "spb_grid_set_metric": (C.c_int, [C.c_void_p, C.POINTER(MetricDesc)]),
+    "spb_grid_has_metric": (C.c_int, [C.c_void_p]),
     "spb_flux_div": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.c_int, C.c_void_p]),
     "spb_flux_div_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FluxDesc), C.c_int,
                                       C.c_int64, C.c_int64, C.c_void_p]),

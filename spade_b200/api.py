@@ -113,12 +113,91 @@ class identity:
     gradient-based fluxes accept (info_gradient.h:83)."""
 
 
+class identity_1D:
+    """coords::identity_1D (core/coord_system.h:54-63)."""
+
+    def map(self, x):
+        return np.asarray(x, dtype=np.float64)
+
+    def coord_deriv(self, x):
+        return np.ones_like(np.asarray(x, dtype=np.float64))
+
+
+class scaled_coord_1D:
+    """coords::scaled_coord_1D(k) (core/coord_system.h:142-158): x = k xi."""
+
+    def __init__(self, k):
+        self.k = float(k)
+
+    def map(self, x):
+        return self.k * np.asarray(x, dtype=np.float64)
+
+    def coord_deriv(self, x):
+        return np.full_like(np.asarray(x, dtype=np.float64), self.k)
+
+
+class quad_1D:
+    """coords::quad_1D (core/coord_system.h:160-173): x = xi^2."""
+
+    def map(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return x * x
+
+    def coord_deriv(self, x):
+        return 2.0 * np.asarray(x, dtype=np.float64)
+
+
+class integrated_tanh_1D:
+    """coords::integrated_tanh_1D(y0, y1, inflation, rate) (core/coord_system.h:103-140): wall-clustered stretching of a
+    channel; the constructor's assignments (eta1 = y0, eta0 = y1) are kept as written there."""
+
+    def __init__(self, y0, y1, inflation, rate):
+        self.eta1, self.eta0 = float(y0), float(y1)
+        self.deta = self.eta1 - self.eta0
+        k, strch = float(rate), float(inflation)
+        self.alpha0, self.alpha1 = k / self.deta, -k / self.deta
+        self.beta0 = self.alpha0 * (strch * self.deta - self.eta0)
+        self.beta1 = self.alpha0 * (self.eta1 + strch * self.deta)
+        self.f0 = float(self._func(self.eta0))
+        self.normInv = 1.0 / (float(self._func(self.eta1)) - self.f0)
+
+    def _func(self, eta):
+        eta = np.asarray(eta, dtype=np.float64)
+        return (np.log(np.abs(np.cosh(self.alpha0 * eta + self.beta0))) / self.alpha0
+                + np.log(np.abs(np.cosh(self.alpha1 * eta + self.beta1))) / self.alpha1 - eta)
+
+    def map(self, x):
+        return self.eta0 + self.deta * (self._func(x) - self.f0) * self.normInv
+
+    def coord_deriv(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return (self.deta * (np.tanh(self.alpha0 * x + self.beta0) + np.tanh(self.alpha1 * x + self.beta1) - 1.0)) * self.normInv
+
+
+class diagonal_coords:
+    """coords::diagonal_coords(xcoord, ycoord, zcoord) (core/coord_system.h:65-90): one 1-D mapping per direction.
+    `metric_at` selects where info::metric evaluates coord_deriv: "physical" = the mapped position, which is what the
+    reference does (omni/infos/info_metric.h:31 passes grid.get_coords(idx)); "computational" = the consistent choice.
+    calc_jacobian always uses the computational position (flux_div_basic.h:49-50)."""
+
+    def __init__(self, xcoord=None, ycoord=None, zcoord=None, metric_at="physical"):
+        self.maps = [m if m is not None else identity_1D() for m in (xcoord, ycoord, zcoord)]
+        if metric_at not in ("physical", "computational"):
+            raise SpbError("diagonal_coords: metric_at is 'physical' (reference) or 'computational'")
+        self.metric_at = metric_at
+
+    def map(self, x):
+        return [self.maps[d].map(x[d]) for d in range(3)]
+
+
 class cartesian_grid_t:
-    """cartesian_grid_t(cells_in_block, blocks, coords, group), cartesian_grid.h:84-89."""
+    """cartesian_grid_t(cells_in_block, blocks, coords, group), cartesian_grid.h:84-89. coords: identity (default) or
+    diagonal_coords; dense coordinate systems (coords::cyl_coords) are not implemented."""
 
     def __init__(self, cells_in_block, blocks, coords=None, group=None):
-        if coords is not None and not isinstance(coords, identity):
-            raise SpbError("cartesian_grid_t: only coords.identity is implemented (as in the reference's flux path)")
+        if coords is not None and not isinstance(coords, (identity, diagonal_coords)):
+            raise SpbError("cartesian_grid_t: coords must be identity or diagonal_coords")
+        self.coords = coords if isinstance(coords, diagonal_coords) else None
         self.num_cell = [int(x) for x in cells_in_block]
         self.blocks = blocks
         self._group = group if group is not None else pool_t()
@@ -143,6 +222,7 @@ class cartesian_grid_t:
         g.num_cell = [int(x) for x in cells_in_block]
         g.blocks = None
         g._group = group if group is not None else pool_t()
+        g.coords = None
         g._boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 6)
         g.num_local_blocks = g._boxes.shape[0]
         g.first_block = int(first_block)
@@ -159,7 +239,33 @@ class cartesian_grid_t:
             check(lib().spb_grid_create(C.byref(h), int3(self.num_cell), int3(key), self.num_local_blocks,
                                         self._bbox.ctypes.data_as(C.POINTER(C.c_double))))
             self._handles[key] = h
+            if self.coords is not None:
+                self._set_metric(h, key)
         return self._handles[key]
+
+    def metric_tables(self, num_exch):
+        """The three 1-D tables per direction of spb_grid_set_metric for this rank's blocks: (area, jac, face), each a
+        list over directions of arrays [nlb, n_d + 2 g_d (+ 1)]; positions as grid_geometry.h:57-70."""
+        area, jac, face = [], [], []
+        box = self._bbox.reshape(-1, 6)
+        for d in range(3):
+            m = self.coords.maps[d]
+            n, g = self.num_cell[d], int(num_exch[d])
+            dx = (box[:, 2 * d + 1] - box[:, 2 * d]) / n
+            xc = box[:, 2 * d, None] + (np.arange(-g, n + g)[None, :] + 0.5) * dx[:, None]
+            xf = box[:, 2 * d, None] + (np.arange(-g, n + g + 1)[None, :] + 0.5 - 0.5) * dx[:, None]
+            jac.append(np.ascontiguousarray(m.coord_deriv(xc)))
+            face.append(np.ascontiguousarray(m.coord_deriv(xf)))
+            area.append(np.ascontiguousarray(m.coord_deriv(m.map(xc)) if self.coords.metric_at == "physical" else jac[-1].copy()))
+        return area, jac, face
+
+    def _set_metric(self, h, num_exch):
+        area, jac, face = self.metric_tables(num_exch)
+        md = _lib.MetricDesc()
+        dp = C.POINTER(C.c_double)
+        for d in range(3):
+            md.area[d], md.jac[d], md.face[d] = area[d].ctypes.data_as(dp), jac[d].ctypes.data_as(dp), face[d].ctypes.data_as(dp)
+        check(lib().spb_grid_set_metric(h, C.byref(md)))
 
     def __del__(self):
         try:

@@ -1,6 +1,7 @@
 // Grid handle, error string, utilities of the C ABI (include/spade_b200.h).
 #include "spb_common.cuh"
 #include <mutex>
+#include <cmath>
 
 namespace spb
 {
@@ -72,9 +73,50 @@ extern "C"
         return 0;
     }
 
+    // reference: src/core/coord_system.h:250-267 (calc_normal_vector), 295-302 (calc_jacobian)
+    int spb_grid_set_metric(spb_grid* g, const spb_metric_desc* m)
+    {
+        if (!g) { spb::set_error("spb_grid_set_metric: null grid"); return SPB_ERR_BAD_ARG; }
+        if (g->metric_dev) { cudaFree(g->metric_dev); g->metric_dev = nullptr; g->metric_lm = 0; }
+        if (!m) return 0;
+        int lm = 0;
+        for (int d = 0; d < 3; ++d)
+        {
+            if (!m->area[d] || !m->jac[d] || !m->face[d]) { spb::set_error("spb_grid_set_metric: null table"); return SPB_ERR_BAD_ARG; }
+            lm = g->np[d] + 1 > lm ? g->np[d] + 1 : lm;
+        }
+        std::vector<double> tab((size_t)g->nlb*9*lm, 1.0);
+        for (int64_t lb = 0; lb < g->nlb; ++lb)
+            for (int d = 0; d < 3; ++d)
+            {
+                double* row = tab.data() + ((size_t)lb*3 + d)*3*lm;
+                for (int i = 0; i < g->np[d]; ++i)
+                {
+                    const double a = m->area[d][lb*g->np[d] + i], j = m->jac[d][lb*g->np[d] + i];
+                    // (a mapping may fold beyond the domain boundary — integrated_tanh_1D does — so ghost entries can be negative)
+                    if (!(a != 0.0) || !(j != 0.0) || !std::isfinite(a) || !std::isfinite(j)) { spb::set_error("spb_grid_set_metric: coordinate derivatives must be finite and nonzero"); return SPB_ERR_BAD_ARG; }
+                    row[i] = a;
+                    row[lm + i] = 1.0/j;
+                }
+                for (int i = 0; i <= g->np[d]; ++i)
+                {
+                    const double f = m->face[d][lb*(g->np[d] + 1) + i];
+                    if (!(f != 0.0) || !std::isfinite(f)) { spb::set_error("spb_grid_set_metric: coordinate derivatives must be finite and nonzero"); return SPB_ERR_BAD_ARG; }
+                    row[2*lm + i] = 1.0/f;
+                }
+            }
+        if (g->nlb == 0) return 0;
+        SPB_CUDA(cudaMalloc(&g->metric_dev, sizeof(double)*tab.size()));
+        SPB_CUDA(cudaMemcpy(g->metric_dev, tab.data(), sizeof(double)*tab.size(), cudaMemcpyHostToDevice));
+        g->metric_lm = lm;
+        return 0;
+    }
+    int spb_grid_has_metric(const spb_grid* g) { return (g && g->metric_dev) ? 1 : 0; }
+
     void spb_grid_destroy(spb_grid* g)
     {
         if (!g) return;
+        if (g->metric_dev) cudaFree(g->metric_dev);
         if (g->inv_dx_dev) cudaFree(g->inv_dx_dev);
         if (g->red_scratch) cudaFree(g->red_scratch);
         for (int i = 0; i < 6; ++i) if (g->bnd_blocks_dev[i]) cudaFree(g->bnd_blocks_dev[i]);

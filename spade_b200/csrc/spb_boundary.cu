@@ -71,7 +71,8 @@ namespace spb
     }
 
     __global__ void __launch_bounds__(256) source_term_kernel(const double* __restrict__ q, double* __restrict__ rhs, const BcDims G,
-                                                              const long long ncells, const spb_source_desc sd)
+                                                              const long long ncells, const spb_source_desc sd,
+                                                              const double* __restrict__ met, const int lm)
     {
         const long long stride = (long long)gridDim.x*blockDim.x;
         for (long long cell = (long long)blockIdx.x*blockDim.x + threadIdx.x; cell < ncells; cell += stride)
@@ -92,6 +93,14 @@ namespace spb
             {
                 #pragma unroll
                 for (int v = 0; v < 5; ++v) S[v] = sd.f[v];
+            }
+            if (met)
+            {
+                // general coordinates: rhs += S/jac, jac = 1/(m0 m1 m2) (source_term.h:38-46); row 1 of the tables holds 1/m
+                const double* mt = met + lb*9*(long long)lm;
+                const double jac = mt[lm + i + G.ng[0]]*mt[4*lm + j + G.ng[1]]*mt[7*lm + k + G.ng[2]];
+                #pragma unroll
+                for (int v = 0; v < 5; ++v) S[v] = __ddiv_rn(S[v], jac);
             }
             #pragma unroll
             for (int v = 0; v < 5; ++v) rhs[o + v] = __dadd_rn(rhs[o + v], S[v]);
@@ -152,7 +161,7 @@ extern "C"
         long long nb = (ncells + 255)/256;
         const long long cap = (long long)g->num_sms*16;
         if (nb > cap) nb = cap;
-        source_term_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(q_dev, rhs_dev, make_dims(g), ncells, *src);
+        source_term_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(q_dev, rhs_dev, make_dims(g), ncells, *src, g->metric_dev, g->metric_lm);
         SPB_LAUNCH_CHECK();
         return 0;
     }

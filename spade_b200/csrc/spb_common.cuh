@@ -53,6 +53,10 @@ struct spb_grid
     std::vector<double> inv_dx_host;  // [nlb][3]
     double* inv_dx_dev;               // [nlb][3]
     int     num_sms;
+    // general coordinates (spb_grid_set_metric): [nlb][3 directions][3 rows][metric_lm] doubles, rows = area metric,
+    // 1/jacobian metric, 1/face metric; null for coords::identity
+    double* metric_dev = nullptr;
+    int     metric_lm = 0;
     // scratch of spb_reduce (partials | result | counter), owned by the handle so a reduction never allocates
     mutable double* red_scratch = nullptr;
     mutable int64_t red_cap = 0;

@@ -77,6 +77,18 @@ namespace spb
         return a(v, o[0], o[1], o[2]);
     }
 
+    // General (diagonal) coordinates, reference src/core/coord_system.h:250-267,295-302: what one face of direction D needs.
+    //   A      face-area factor: the D component of calc_normal_vector = (m0 m1 m2)/m_D = m_T1 m_T2 (the reference forms it
+    //          per stencil cell as 1/(m_D * (1/(m0 m1 m2))); the tangential derivatives are the same for every cell of the
+    //          stencil of a face, so the cells agree to round-off)
+    //   gs[d]  gradient scale of direction d: inv_dx_d / m_d (normal: m_D at the face, tangential: m_t at the cell row)
+    // Identity coordinates: A = 1, gs = inv_dx (the CURV = false instantiations never read A).
+    struct FaceMetric
+    {
+        double A;
+        double gs[3];
+    };
+
     // ---- convective::totani_lr -------------------------------------------------------------
     template <int D>
     __device__ __forceinline__ void flux_totani(const FluxParams& P, const double (&qL)[5], const double (&qR)[5], double (&F)[5])
@@ -150,9 +162,11 @@ namespace spb
         return fma(w0, r0 - r1, r1) + fma(w3, r3 - r2, r2);
     }
 
-    template <int D>
+    // general coordinates: the metric scales the flux part (u.n, p n) but not the Rusanov dissipation, exactly like the
+    // reference (convective.h:363-378 forms hlf_sig_rho without the metric)
+    template <int D, bool CURV = false>
     __device__ __forceinline__ void flux_fweno(const FluxParams& P, const double (&c0)[5], const double (&c1)[5],
-                                               const double (&c2)[5], const double (&c3)[5], double (&F)[5])
+                                               const double (&c2)[5], const double (&c3)[5], double (&F)[5], const double A = 1.0)
     {
         const double* q[4] = {c0, c1, c2, c3};
         double rho[4], hsr[4], a[4], ke[4], fm[4], fl[4], ds[4];
@@ -165,7 +179,9 @@ namespace spb
             rho[i] = q[i][0]*rcp_nr(a[i]);
             hsr[i] = 0.5*rho[i]*(sqrt_nr(fmax(u2, 1e-300)) + sqrt_nr(a[i]*P.gamma));      // |u| = 0 becomes 1e-150
             fm[i]  = 0.5*rho[i]*q[i][2+D];
+            if (CURV) fm[i] *= A;
         }
+        const double hA = CURV ? 0.5*A : 0.5;
         // continuity
         F[0] = fweno_apply(fm, hsr);
         // energy
@@ -185,7 +201,7 @@ namespace spb
             for (int i = 0; i < 4; ++i)
             {
                 fl[i] = fm[i]*q[i][2+dr];
-                if (dr == D) fl[i] = fma(0.5, q[i][0], fl[i]);
+                if (dr == D) fl[i] = fma(hA, q[i][0], fl[i]);
                 ds[i] = hsr[i]*q[i][2+dr];
             }
             F[2+dr] = fweno_apply(fl, ds);
@@ -193,8 +209,9 @@ namespace spb
     }
 
     // ---- the composed functor on the lower face (direction D) of the cell the accessor is centred on
-    template <int CONV, int DISS, int VISC, int D, class A>
-    __device__ __forceinline__ void face_flux(const A& a, const FluxParams& P, const double (&invdx)[3], double (&F)[5])
+    template <int CONV, int DISS, int VISC, int D, bool CURV = false, class A>
+    __device__ __forceinline__ void face_flux(const A& a, const FluxParams& P, const double (&invdx)[3], double (&F)[5],
+                                              const double area = 1.0)
     {
         constexpr int T1 = (D + 1) % 3, T2 = (D + 2) % 3;
         constexpr bool WIDE = (CONV == SPB_CONV_CENT_KEEP4) || (CONV == SPB_CONV_FWENO) || (DISS != SPB_DISS_NONE);
@@ -211,7 +228,13 @@ namespace spb
 
         if (CONV == SPB_CONV_TOTANI)     flux_totani<D>(P, qL, qR, F);
         if (CONV == SPB_CONV_CENT_KEEP4) flux_cent_keep4<D>(P, qLL, qL, qR, qRR, F);
-        if (CONV == SPB_CONV_FWENO)      flux_fweno<D>(P, qLL, qL, qR, qRR, F);
+        if (CONV == SPB_CONV_FWENO)      flux_fweno<D, CURV>(P, qLL, qL, qR, qRR, F, area);
+        if (CURV && (CONV == SPB_CONV_TOTANI || CONV == SPB_CONV_CENT_KEEP4))
+        {
+            // both are linear in the metric vector (convective.h:76-91, 128-182)
+            #pragma unroll
+            for (int v = 0; v < 5; ++v) F[v] *= area;
+        }
 
         if (VISC || DISS)
         {
@@ -244,20 +267,21 @@ namespace spb
                 const double vort = fma(w0, w0, fma(w1, w1, w2*w2));
                 const double alpha = th2*rcp_nr(th2 + vort + P.eps);
                 double F1[5];
-                flux_fweno<D>(P, qLL, qL, qR, qRR, F1);
+                flux_fweno<D, CURV>(P, qLL, qL, qR, qRR, F1, area);
                 const double coeff0 = (P.blend == SPB_BLEND_FULL_FLUX) ? (1.0 - alpha) : 1.0;
                 #pragma unroll
                 for (int v = 0; v < 5; ++v) F[v] = fma(alpha, F1[v], coeff0*F[v]);
             }
             if (VISC)
             {
-                const double tDD = fma(P.two_mu, g[D][D], P.beta*div);
-                const double tD1 = P.mu*(g[D][T1] + g[T1][D]);
-                const double tD2 = P.mu*(g[D][T2] + g[T2][D]);
+                double tDD = fma(P.two_mu, g[D][D], P.beta*div);
+                double tD1 = P.mu*(g[D][T1] + g[T1][D]);
+                double tD2 = P.mu*(g[D][T2] + g[T2][D]);
                 const double ufD = 0.5*(qL[2+D]  + qR[2+D]);
                 const double uf1 = 0.5*(qL[2+T1] + qR[2+T1]);
                 const double uf2 = 0.5*(qL[2+T2] + qR[2+T2]);
-                const double h = fma(ufD, tDD, fma(uf1, tD1, fma(uf2, tD2, P.kappa*gT)));
+                double h = fma(ufD, tDD, fma(uf1, tD1, fma(uf2, tD2, P.kappa*gT)));
+                if (CURV) { h *= area; tDD *= area; tD1 *= area; tD2 *= area; }      // -(n . tau), n = area e_D (viscous.h:70-74)
                 F[1]    -= h;
                 F[2+D]  -= tDD;
                 F[2+T1] -= tD1;

@@ -1,0 +1,366 @@
+// (template; instantiated by spb_flux_div.cu for coords::identity and by spb_flux_div_curv.cu for general coordinates)
+// Fused RHS kernel: replaces pde_algs::flux_div (reference src/pde-algs/flux-div/flux_div_basic.h:17-77
+// and its shared-memory variants flux_div_fldbc.h / flux_div_ldbal.h) on sm_100a.
+//
+// One CTA owns a TI x TJ column of cells of one block and marches through k. Planes of the
+// primitive array (reference AoS order, 5 doubles per cell) are staged into a shared-memory ring by
+// TMA (cp.async.bulk.tensor.4d over the tensor [5*(n0+2g), n1+2g, n2+2g, nlb]) and signalled on
+// mbarriers; the next plane is in flight while the current one is computed. Every face flux is
+// evaluated once: a thread computes the lower x-, y- and z-face of its cell, x/y fluxes are
+// shared through shared memory, the z flux is carried in registers to the next plane.
+#pragma once
+#include "spb_common.cuh"
+#include "spb_tma.cuh"
+#include "spb_flux.cuh"
+#include <type_traits>
+
+namespace spb
+{
+    constexpr int TI = 32;
+    constexpr int TJ = 8;
+    constexpr int NTHREADS = TI*TJ;
+
+    struct FdivDims
+    {
+        int nx[3], ng[3], np[3];
+        int tiles_i, tiles_j;
+        long long block_stride;
+        long long lb0;
+        int increment;
+        int lm;                     // general coordinates: length of one metric table row (spb_grid::metric_lm)
+    };
+
+    template <int H> struct FdivSmem
+    {
+        // +2: fp64 TMA boxes must start on a 16-byte boundary (measured on B200: an odd first coordinate raises
+        // an illegal-instruction fault), so the box starts one cell early when the halo start is an odd cell
+        static constexpr int TIp = TI + 2*H + 2, TJp = TJ + 2*H;
+        static constexpr int NP = H + 3;                                  // ring slots
+        static constexpr int PLANE_DOUBLES = TIp*TJp*5;
+        static constexpr int PLANE_BYTES = PLANE_DOUBLES*8;
+        static constexpr int PLANE_STRIDE_BYTES = (PLANE_BYTES + 127)/128*128;
+        static constexpr int PLANE_STRIDE = PLANE_STRIDE_BYTES/8;
+        static constexpr int FX_DOUBLES = TJ*(TI + 1)*5;
+        static constexpr int FY_DOUBLES = (TJ + 1)*TI*5;
+        static constexpr int BYTES = NP*PLANE_STRIDE_BYTES + (FX_DOUBLES + FY_DOUBLES)*8 + NP*8 + 128;
+    };
+
+    // accessor of the staged planes, centred on tile-local cell (il, jl) of the current plane
+    template <int H> struct TileAcc
+    {
+        const double* ring;
+        int cell;          // ((jl+H)*TIp + (il+H))*5
+        int pl[4];         // plane offsets (doubles) for dk = -2, -1, 0, +1
+        __device__ __forceinline__ double operator()(int v, int di, int dj, int dk) const
+        {
+            return ring[pl[dk + 2] + cell + (dj*FdivSmem<H>::TIp + di)*5 + v];
+        }
+    };
+
+    // FUSED: the RK stage update of spb_flux_div_rk_stage rides on the rhs of each finished cell (see spb_flux.cuh:
+    // StageParams); rhs is then the residual register written (or null) and q_out the new state.
+    // CURV: general (diagonal) coordinates, reference src/core/coord_system.h:250-267,295-302 with flux_div_basic.h:49-71:
+    //   rhs(c) = J(c) sum_d (F_lower - F_upper)/dxi_d,  F = flux with the metric vector area*e_d,  J = 1/(m0 m1 m2).
+    // `met` holds, per block and direction, three rows of length G.lm (spb_grid_set_metric): row 0 = m as info::metric
+    // evaluates it at the cell centres, row 1 = 1/m at the computational cell centres (Jacobian, tangential gradient
+    // transform), row 2 = 1/m at the faces (normal gradient transform); index = padded cell / face index.
+    template <int CONV, int DISS, int VISC, bool FUSED, bool CURV = false>
+    __global__ void __launch_bounds__(NTHREADS, 2)
+    flux_div_kernel(const __grid_constant__ CUtensorMap tmap_q, double* __restrict__ rhs, const FluxParams P,
+                    const FdivDims G, const double* __restrict__ inv_dx_tab, double* __restrict__ q_out, const StageParams ST,
+                    const double* __restrict__ met)
+    {
+        constexpr int H = stencil_halo<CONV, DISS>::value;
+        using S = FdivSmem<H>;
+        extern __shared__ __align__(128) double smem_raw[];
+        // pointer arithmetic on the __shared__ symbol (no integer round trip) keeps the address space known
+        // to the compiler: LDS/STS instead of generic LD/ST
+        double*   ring = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
+        double*   Fx   = ring + S::NP*S::PLANE_STRIDE;
+        double*   Fy   = Fx + S::FX_DOUBLES;
+        uint64_t* bars = (uint64_t*)(Fy + S::FY_DOUBLES);
+
+        const int tid = threadIdx.x;
+        const int il = tid & 31, jl = tid >> 5;
+
+        int t = blockIdx.x;
+        const int ti = t % G.tiles_i; t /= G.tiles_i;
+        const int tj = t % G.tiles_j; t /= G.tiles_j;
+        const long long lb = G.lb0 + t;
+        const int i0 = ti*TI, j0 = tj*TJ;
+        const int nz = G.nx[2];
+        const int ni_t = min(TI, G.nx[0] - i0);     // interior cells of this tile along i / j
+        const int nj_t = min(TJ, G.nx[1] - j0);
+        const bool active = (il < ni_t) && (jl < nj_t);
+
+        const double invdx[3] = {inv_dx_tab[3*lb + 0], inv_dx_tab[3*lb + 1], inv_dx_tab[3*lb + 2]};
+        // metric rows of this block: M(d, row, idx)
+        const double* mt = CURV ? met + lb*9*(long long)G.lm : nullptr;
+        auto M = [&](const int d, const int row, const int idx) { return __ldg(mt + (d*3 + row)*G.lm + idx); };
+        // gradient scales and area factor of the lower face of direction D of the padded cell (ip, jp, kp)
+        auto face_metric = [&](auto Dc, const int ip, const int jp, const int kp, double (&gs)[3], double& area)
+        {
+            constexpr int D = decltype(Dc)::value, T1 = (D + 1) % 3, T2 = (D + 2) % 3;
+            const int idx[3] = {ip, jp, kp};
+            area   = M(T1, 0, idx[T1])*M(T2, 0, idx[T2]);
+            gs[D]  = invdx[D]*M(D, 2, idx[D]);
+            gs[T1] = invdx[T1]*M(T1, 1, idx[T1]);
+            gs[T2] = invdx[T2]*M(T2, 1, idx[T2]);
+        };
+        constexpr std::integral_constant<int, 0> DX{};
+        constexpr std::integral_constant<int, 1> DY{};
+        constexpr std::integral_constant<int, 2> DZ{};
+        const int ipc = i0 + il + G.ng[0], jpc = j0 + jl + G.ng[1];       // padded indices of this thread's cell column
+
+        // TMA coordinates of the tile (fused (v,i) dimension first)
+        const int ash = (i0 + G.ng[0] - H) & 1;          // alignment shift (cells)
+        const int c0 = 5*(i0 + G.ng[0] - H - ash);
+        const int c1 = j0 + G.ng[1] - H;
+        const int c2base = G.ng[2] - H;               // plane p -> k = p - H -> coordinate p + ng - H
+        const int nplanes = nz + 2*H;
+
+        if (tid == 0)
+        {
+            prefetch_tmap(&tmap_q);
+            #pragma unroll
+            for (int s = 0; s < S::NP; ++s) mbar_init(&bars[s], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            #pragma unroll
+            for (int p = 0; p < S::NP; ++p)
+            {
+                if (p < nplanes)
+                {
+                    mbar_arrive_expect_tx(&bars[p], S::PLANE_BYTES);
+                    tma_load_4d(ring + p*S::PLANE_STRIDE, &tmap_q, &bars[p], c0, c1, c2base + p, (int)lb);
+                }
+            }
+        }
+
+        TileAcc<H> acc;
+        acc.ring = ring;
+        acc.cell = ((jl + H)*S::TIp + (il + H + ash))*5;
+
+        // planes p = 0 .. H are needed by step 0 besides plane H+1
+        uint32_t parity_bits = 0;                      // bit s = parity to wait for on slot s
+        #pragma unroll
+        for (int p = 0; p <= H; ++p) { mbar_wait(&bars[p], 0); }
+        parity_bits = (1u << (H + 1)) - 1;             // slots 0..H consumed once
+        int slot_next = H + 1;                         // slot of plane k+1 at step k
+        // plane offsets for dk = -2..+1 at step k=0: plane p = k + H + dk
+        #pragma unroll
+        for (int d = 0; d < 4; ++d) { const int p = H + (d - 2); acc.pl[d] = (p >= 0 ? p : 0)*S::PLANE_STRIDE; }
+
+        double rprev[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // partial rhs of cell k-1 (x, y and lower-z parts)
+        const long long col0 = lb*G.block_stride
+            + 5ll*((i0 + il + G.ng[0]) + (long long)G.np[0]*((j0 + jl + G.ng[1]) + (long long)G.np[1]*G.ng[2]));
+        double* rhs_col = rhs + col0;
+        const long long kstride = 5ll*G.np[0]*G.np[1];
+
+        for (int k = 0; k <= nz; ++k)
+        {
+            // plane k+1
+            if (k + 1 + H < nplanes)
+            {
+                mbar_wait(&bars[slot_next], (parity_bits >> slot_next) & 1u);
+                parity_bits ^= (1u << slot_next);
+            }
+            acc.pl[3] = slot_next*S::PLANE_STRIDE;
+
+            double Fz[5];
+            double jac_prev = 1.0;                   // Jacobian of cell k-1
+            if (active)
+            {
+                if (CURV)
+                {
+                    double gs[3], area;
+                    face_metric(DZ, ipc, jpc, k + G.ng[2], gs, area);
+                    face_flux<CONV, DISS, VISC, 2, true>(acc, P, gs, Fz, area);
+                    if (k >= 1) jac_prev = M(0, 1, ipc)*M(1, 1, jpc)*M(2, 1, k - 1 + G.ng[2]);
+                }
+                else face_flux<CONV, DISS, VISC, 2>(acc, P, invdx, Fz);
+            }
+
+            if (k >= 1 && active)
+            {
+                double* o = rhs_col + (long long)(k - 1)*kstride;
+                if (!FUSED)
+                {
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v)
+                    {
+                        double r = fma(-Fz[v], invdx[2], rprev[v]);
+                        if (CURV) r *= jac_prev;
+                        if (G.increment) r += o[v];
+                        o[v] = r;
+                    }
+                }
+                else
+                {
+                    const long long c = col0 + (long long)(k - 1)*kstride;
+                    double w[5], ov[5];
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v)
+                    {
+                        double r = fma(-Fz[v], invdx[2], rprev[v]);
+                        if (CURV) r *= jac_prev;
+                        w[v] = ST.cq_self*r; ov[v] = ST.co_self*r;
+                    }
+                    #pragma unroll
+                    for (int a = 0; a < 2; ++a)
+                        if (a < ST.nin)
+                        {
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v)
+                            {
+                                const double x = ST.in[a][c + v];
+                                w[v] = fma(ST.cq[a], x, w[v]); ov[v] = fma(ST.co[a], x, ov[v]);
+                            }
+                        }
+                    if (ST.has_out)
+                    {
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v) o[v] = ov[v];
+                    }
+                    // prim -> cons (fluid_state.h:103-116), add the increment, cons -> prim (fluid_state.h:119-135)
+                    double qc[5];
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) qc[v] = acc(v, 0, 0, -1);
+                    const double rho0 = qc[0]*rcp_nr(P.R*qc[1]);
+                    const double u2 = fma(qc[2], qc[2], fma(qc[3], qc[3], qc[4]*qc[4]));
+                    const double rho  = rho0 + w[0];
+                    const double rhoE = fma(0.5*rho0, u2, qc[0]*ST.inv_gm1) + w[1];
+                    const double mx = fma(rho0, qc[2], w[2]), my = fma(rho0, qc[3], w[3]), mz = fma(rho0, qc[4], w[4]);
+                    const double ir = rcp_nr(rho);
+                    const double un = ir*mx, vn = ir*my, wn = ir*mz;
+                    const double pn = ST.gm1*fma(-0.5*rho, fma(un, un, fma(vn, vn, wn*wn)), rhoE);
+                    double* qo = q_out + c;
+                    qo[0] = pn; qo[1] = pn*ir*ST.inv_R; qo[2] = un; qo[3] = vn; qo[4] = wn;
+                }
+            }
+
+            if (k < nz)
+            {
+                if (active)
+                {
+                    double F[5], gs[3], area;
+                    if (CURV) { face_metric(DX, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true>(acc, P, gs, F, area); }
+                    else face_flux<CONV, DISS, VISC, 0>(acc, P, invdx, F);
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) Fx[(jl*(TI + 1) + il)*5 + v] = F[v];
+                    if (CURV) { face_metric(DY, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true>(acc, P, gs, F, area); }
+                    else face_flux<CONV, DISS, VISC, 1>(acc, P, invdx, F);
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) Fy[(jl*TI + il)*5 + v] = F[v];
+                }
+                // faces on the upper edge of the tile
+                if (tid < nj_t)                      // warp 0: x-face i = ni_t of row tid
+                {
+                    TileAcc<H> e = acc;
+                    e.cell = ((tid + H)*S::TIp + (ni_t + H + ash))*5;
+                    double F[5], gs[3], area;
+                    if (CURV) { face_metric(DX, i0 + ni_t + G.ng[0], j0 + tid + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true>(e, P, gs, F, area); }
+                    else face_flux<CONV, DISS, VISC, 0>(e, P, invdx, F);
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) Fx[(tid*(TI + 1) + ni_t)*5 + v] = F[v];
+                }
+                if (tid >= 32 && tid < 32 + ni_t)    // warp 1: y-face j = nj_t of column tid-32
+                {
+                    TileAcc<H> e = acc;
+                    e.cell = ((nj_t + H)*S::TIp + (tid - 32 + H + ash))*5;
+                    double F[5], gs[3], area;
+                    if (CURV) { face_metric(DY, i0 + tid - 32 + G.ng[0], j0 + nj_t + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true>(e, P, gs, F, area); }
+                    else face_flux<CONV, DISS, VISC, 1>(e, P, invdx, F);
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) Fy[(nj_t*TI + (tid - 32))*5 + v] = F[v];
+                }
+            }
+            __syncthreads();
+            if (k < nz && active)
+            {
+                #pragma unroll
+                for (int v = 0; v < 5; ++v)
+                {
+                    const double dFx = Fx[(jl*(TI + 1) + il)*5 + v] - Fx[(jl*(TI + 1) + il + 1)*5 + v];
+                    const double dFy = Fy[(jl*TI + il)*5 + v] - Fy[((jl + 1)*TI + il)*5 + v];
+                    rprev[v] = fma(dFx, invdx[0], fma(dFy, invdx[1], Fz[v]*invdx[2]));
+                }
+            }
+            __syncthreads();
+            // slot of plane p = k (dk = -H) is free now: refill it with plane k + H + 3 = p + NP
+            if (tid == 0)
+            {
+                const int pnew = k + S::NP;
+                if (pnew < nplanes)
+                {
+                    const int s = k % S::NP;
+                    mbar_arrive_expect_tx(&bars[s], S::PLANE_BYTES);
+                    tma_load_4d(ring + s*S::PLANE_STRIDE, &tmap_q, &bars[s], c0, c1, c2base + pnew, (int)lb);
+                }
+            }
+            acc.pl[0] = acc.pl[1]; acc.pl[1] = acc.pl[2]; acc.pl[2] = acc.pl[3];
+            slot_next = (slot_next + 1 == S::NP) ? 0 : slot_next + 1;
+        }
+    }
+
+    template <int CONV, int DISS, int VISC, bool FUSED = false, bool CURV = false>
+    static int launch_fdiv(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out = nullptr, const StageParams* stage = nullptr)
+    {
+        constexpr int H = stencil_halo<CONV, DISS>::value;
+        using S = FdivSmem<H>;
+        for (int d = 0; d < 3; ++d)
+            if (g->ng[d] < H) { set_error("spb_flux_div: scheme needs " + std::to_string(H) + " exchange cells"); return SPB_ERR_BAD_ARG; }
+        if (g->ng[2] < 2 && H == 2) { set_error("spb_flux_div: need 2 exchange cells"); return SPB_ERR_BAD_ARG; }
+        if ((5*g->np[0]) % 2 != 0) { set_error("spb_flux_div: n0 + 2*g0 must be even (16-byte TMA row pitch)"); return SPB_ERR_UNSUPPORTED; }
+        encode_tiled_fn enc = get_encode_tiled();
+        if (!enc) { set_error("spb_flux_div: cuTensorMapEncodeTiled not available from the driver"); return SPB_ERR_DRIVER; }
+
+        CUtensorMap tq;
+        const cuuint64_t dims[4]    = {(cuuint64_t)5*g->np[0], (cuuint64_t)g->np[1], (cuuint64_t)g->np[2], (cuuint64_t)g->nlb};
+        const cuuint64_t strides[3] = {(cuuint64_t)40*g->np[0], (cuuint64_t)40*g->np[0]*g->np[1], (cuuint64_t)8*g->block_stride};
+        const cuuint32_t box[4]     = {(cuuint32_t)(5*S::TIp), (cuuint32_t)S::TJp, 1, 1};
+        const cuuint32_t estr[4]    = {1, 1, 1, 1};
+        CUresult cr = enc(&tq, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)q, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { set_error("spb_flux_div: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)cr)); return SPB_ERR_DRIVER; }
+
+        FdivDims G;
+        for (int d = 0; d < 3; ++d) { G.nx[d] = g->nx[d]; G.ng[d] = g->ng[d]; G.np[d] = g->np[d]; }
+        G.tiles_i = (g->nx[0] + TI - 1)/TI;
+        G.tiles_j = (g->nx[1] + TJ - 1)/TJ;
+        G.block_stride = g->block_stride;
+        G.lb0 = lb_begin;
+        G.increment = increment;
+        G.lm = g->metric_lm;
+        if (CURV && !g->metric_dev) { set_error("spb_flux_div: general-coordinate kernel without a metric (spb_grid_set_metric)"); return SPB_ERR_BAD_ARG; }
+        const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
+        if (nblk <= 0) return 0;
+        auto kern = flux_div_kernel<CONV, DISS, VISC, FUSED, CURV>;
+        StageParams SP{};
+        if (stage) SP = *stage;
+        SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+        kern<<<(unsigned)nblk, NTHREADS, S::BYTES, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP, g->metric_dev);
+        SPB_LAUNCH_CHECK();
+        return 0;
+    }
+
+    static inline FluxParams make_params(const spb_flux_desc* f)
+    {
+        FluxParams P;
+        P.gamma = f->gamma; P.R = f->R; P.gm1 = f->gamma - 1.0; P.cv = f->R/(f->gamma - 1.0); P.inv_gm1 = 1.0/(f->gamma - 1.0);
+        P.mu = f->mu; P.beta = f->beta; P.two_mu = 2.0*f->mu;
+        // reference viscous.h:64-68: cond = (gamma R/(gamma-1)) * (mu * prandtl_inv)
+        P.kappa = (f->gamma*f->R/(f->gamma - 1.0))*(f->mu*f->prandtl_inv);
+        P.eps = f->sensor_eps; P.blend = f->blend;
+        return P;
+    }
+
+    // general coordinates (spb_flux_div_curv.cu): every functor combination through the wide kernel with CURV = true
+    int flux_div_curv(const spb_grid* g, const double* q, double* rhs, const spb_flux_desc* f, const FluxParams& P, int increment,
+                      int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage);
+}

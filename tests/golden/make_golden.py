@@ -115,8 +115,40 @@ def main():
         ref.set_amr([])
         print("amr case", case, nblk, "blocks")
     np.savez_compressed(os.path.join(HERE, "amr_small.npz"), **amr)
-    for f in ("hotpath_small.npz", "exchange_tables.npz", "channel_small.npz", "amr_small.npz"):
+    make_curvilinear()
+    for f in ("hotpath_small.npz", "exchange_tables.npz", "channel_small.npz", "amr_small.npz", "curvilinear_small.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+CURV_BOUNDS = [0.0, 2 * np.pi, -1.0, 1.0, 0.5, 2.0]
+CURV_MAPS = {"channel": (("scaled", 2.0), ("tanh", -1.0, 1.0, 0.1, 1.3), None),
+             "tanh_quad": (None, ("tanh", -1.0, 1.0, 0.1, 1.3), ("quad",))}
+
+
+def make_curvilinear():
+    """(vii) stretched grids (coords::diagonal_coords): the reference's own flux_div(basic) for the convective functors,
+    from oracle/_ref/libspade_ref_curv.so (the reference compiled with the two-declaration repair of
+    core/coord_system.h:255,274 described in oracle/ref_driver_curv.cc); its Jacobian / metric tables; an RK4 trajectory."""
+    assert ref.curv_available(), "build oracle/_ref first (make -C oracle ref)"
+    nb, n = (2, 2, 1), (8, 4, 4)
+    cv = {}
+    for name, maps in CURV_MAPS.items():
+        cd = ref.make_coords(maps)
+        for scheme in (3, 5, 7):
+            q = make_state(nb, n, NG, seed=200 + scheme, bounds=CURV_BOUNDS)
+            cfg = oracle_cfg(nb, n, NG, scheme=scheme, bounds=CURV_BOUNDS)
+            # the input is regenerated by the tests from the seed (make_state(nb, n, NG, seed=200 + scheme, bounds=CURV_BOUNDS))
+            cv[f"{name}_rhs_{scheme}"] = ref.curv_flux_div(cfg, cd, q.ravel()).reshape(q.shape)
+        jac, nrm, xyz = ref.curv_geometry(oracle_cfg(nb, n, NG, scheme=3, bounds=CURV_BOUNDS), cd, 3)
+        cv[f"{name}_jac"], cv[f"{name}_nrm"], cv[f"{name}_xyz"] = jac, nrm, xyz
+    cd = ref.make_coords(CURV_MAPS["channel"])
+    cfg = oracle_cfg(nb, n, NG, scheme=3, integrator=0, bounds=CURV_BOUNDS)
+    q0 = ref.exchange(cfg, make_state(nb, n, NG, seed=77, bounds=CURV_BOUNDS).ravel())
+    dt = 2e-5
+    q2 = ref.curv_advance(cfg, cd, q0, dt, 2)
+    shape = cv["channel_rhs_3"].shape
+    cv["adv_q2"], cv["adv_dt"] = q2.reshape(shape), np.array([dt])      # q0 = exchange(make_state(seed=77)), regenerated
+    np.savez_compressed(os.path.join(HERE, "curvilinear_small.npz"), **cv)
 
 
 if __name__ == "__main__":
