@@ -96,8 +96,10 @@ namespace spade::b200
         const key_t key{(const void*)&grid, ng[0], ng[1], ng[2], nlb};
         auto it = cache.find(key);
         if (it != cache.end()) return it->second;
-        static_assert(std::same_as<typename array_t::grid_type::coord_sys_type, coords::identity<typename array_t::grid_type::coord_type>>,
-            "spade_b200: coords::identity only, like the reference's gradient-based fluxes (omni/infos/info_gradient.h:83)");
+        using coord_sys_t = typename array_t::grid_type::coord_sys_type;
+        constexpr bool is_identity = std::same_as<coord_sys_t, coords::identity<typename array_t::grid_type::coord_type>>;
+        static_assert(is_identity || coords::diagonal_coordinate_system<coord_sys_t>,
+            "spade_b200: coords::identity or coords::diagonal_coords (dense coordinate systems are not implemented)");
         std::vector<double> bbox(6*nlb);
         for (std::size_t lb = 0; lb < nlb; ++lb)
         {
@@ -108,6 +110,37 @@ namespace spade::b200
         const int g[3]  = {ng[0], ng[1], ng[2]};
         spb_grid* h = nullptr;
         check(spb_grid_create(&h, nx, g, (int64_t)nlb, bbox.data()), "spb_grid_create");
+        if constexpr (!is_identity)
+        {
+            // coords::diagonal_coords: the separable geometry as three 1-D tables per block and direction, evaluated with the
+            // reference's own mapping objects. `area` follows info::metric to the letter: coord_deriv at the MAPPED cell
+            // centre (omni/infos/info_metric.h:31 passes grid.get_coords(idx)); `jac` follows calc_jacobian: coord_deriv
+            // at the computational centre (flux_div_basic.h:49-50); positions as grid_geometry.h:57-70.
+            const auto& cs = grid.get_coord_sys();
+            std::vector<double> area[3], jac[3], face[3];
+            auto fill_dir = [&](const int d, const auto& map1d)
+            {
+                const int np = nx[d] + 2*g[d];
+                area[d].resize(nlb*np); jac[d].resize(nlb*np); face[d].resize(nlb*(np + 1));
+                for (std::size_t lb = 0; lb < nlb; ++lb)
+                {
+                    const double lo = bbox[6*lb + 2*d], dx = (bbox[6*lb + 2*d + 1] - bbox[6*lb + 2*d])/nx[d];
+                    for (int i = 0; i <= np; ++i)
+                    {
+                        double rf = double(i - g[d]) + 0.5; rf -= 0.5;
+                        face[d][lb*(np + 1) + i] = map1d.coord_deriv(lo + rf*dx);
+                        if (i == np) break;
+                        const double xc = lo + (double(i - g[d]) + 0.5)*dx;
+                        jac[d][lb*np + i]  = map1d.coord_deriv(xc);
+                        area[d][lb*np + i] = map1d.coord_deriv(map1d.map(xc));
+                    }
+                }
+            };
+            fill_dir(0, cs.xcoord); fill_dir(1, cs.ycoord); fill_dir(2, cs.zcoord);
+            spb_metric_desc md;
+            for (int d = 0; d < 3; ++d) { md.area[d] = area[d].data(); md.jac[d] = jac[d].data(); md.face[d] = face[d].data(); }
+            check(spb_grid_set_metric(h, &md), "spb_grid_set_metric");
+        }
         cache[key] = h;
         return h;
     }

@@ -1,0 +1,132 @@
+// Stretched-grid solver written against SPADE's own API (reference headers #included at build time only), BASELINE config 3
+// style: coords::diagonal_coords(scaled x, integrated_tanh_1D y, identity z), 2 exchange cells, rk4_t.
+//   A. the reference's generic CUDA path (flux_div tag `basic`) for the convective functor totani_lr — the only kind of
+//      functor the reference can evaluate on general coordinates (omni/infos/info_gradient.h:83), and only once the two
+//      parameter declarations of core/coord_system.h:255,274 are repaired (integration/Makefile does that on a temporary
+//      copy of that one header, as oracle/Makefile does);
+//   B. the drop-in (tag `b200`, b200::make_exchange) on the same grid object: the shim reads the mapping objects of the
+//      grid and hands the library its separable metric tables (spb_grid_set_metric);
+//   C. the drop-in running the config-3 functor (hybrid totani/fweno + ducros + visc_lr) on the same stretched grid with
+//      lambdas (flux_div + update + exchange) and with named callbacks (one fused kernel per stage): no reference
+//      counterpart exists for the viscous / sensor terms, so C checks the two drop-in paths against each other.
+// Prints one JSON line. Usage: channel_curv_demo [blocks_per_dim=2] [cells_per_block=16] [steps=2]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "spade.h"
+#include "spade_b200_shim.hpp"
+
+using real_t = double;
+using prim_t = spade::fluid_state::prim_t<real_t>;
+using cons_t = spade::fluid_state::cons_t<real_t>;
+using flux_t = spade::fluid_state::flux_t<real_t>;
+
+int main(int argc, char** argv)
+{
+    const int nb = argc > 1 ? std::atoi(argv[1]) : 2;
+    const int nc = argc > 2 ? std::atoi(argv[2]) : 16;
+    const int nsteps = argc > 3 ? std::atoi(argv[3]) : 2;
+    std::vector<int> devices{0};
+    spade::parallel::compute_env_t env(&argc, &argv, devices);
+    env.exec([&](spade::parallel::pool_t& pool)
+    {
+        const real_t gamma = 1.4, rgas = 287.15, p0 = 101325.0, t0 = 300.0, u0 = 34.7, pi = 3.14159265358979323846;
+        const real_t mu = (p0/(rgas*t0))*u0/1600.0;
+        spade::ctrs::array<int, 3> num_blocks(nb, nb, nb), cells(nc, nc, nc), exch(2, 2, 2);
+        spade::bound_box_t<real_t, 3> bounds;
+        bounds.min(0) = 0.0;  bounds.max(0) = pi;
+        bounds.min(1) = -1.0; bounds.max(1) = 1.0;
+        bounds.min(2) = 0.0;  bounds.max(2) = 2.0*pi;
+        spade::coords::scaled_coord_1D<real_t>    xc(2.0);
+        spade::coords::integrated_tanh_1D<real_t> yc(-1.0, 1.0, 0.1, 4.0);
+        spade::coords::identity_1D<real_t>        zc;
+        spade::coords::diagonal_coords coords(xc, yc, zc);
+        spade::grid::cartesian_blocks_t blocks(num_blocks, bounds);
+        spade::grid::cartesian_grid_t grid(cells, blocks, coords, pool);
+        spade::ctrs::array<bool, 3> periodic(true, true, true);
+        spade::fluid_state::ideal_gas_t<real_t> air(gamma, rgas);
+        spade::viscous_laws::constant_viscosity_t<real_t> vlaw(mu, 0.72);
+        spade::convective::totani_lr tscheme(air);
+        spade::convective::fweno_t<decltype(air)> wscheme(air);
+        spade::state_sensor::ducros_t<real_t> ducr(1e-2);
+        spade::viscous::visc_lr vscheme(vlaw, air);
+
+        // a smooth field of the COMPUTATIONAL coordinates' periodic images (the y map is not periodic: the state is what matters)
+        const auto ic = [=] _sp_hybrid (const spade::coords::point_t<real_t>& x)
+        {
+            prim_t q;
+            const real_t yy = pi*(x[1] + 1.0);
+            q.p() = p0 + (p0/(rgas*t0))*u0*u0/16.0*(cos(x[0]) + cos(2.0*yy))*(cos(2.0*x[2]) + 2.0);
+            q.T() = t0*(1.0 + 0.02*sin(0.5*x[0] + 2.0*yy - x[2]));
+            q.u() = u0*sin(0.5*x[0])*cos(yy)*cos(x[2]);
+            q.v() = -u0*cos(0.5*x[0])*sin(yy)*cos(x[2]);
+            q.w() = 0.3*u0*sin(x[2])*cos(0.5*x[0] + yy);
+            return q;
+        };
+        const real_t dxmin = 0.3*2.0/(nb*nc);
+        const real_t dt = 0.2*dxmin/(std::sqrt(gamma*rgas*t0*1.02) + 1.5*u0);
+
+        // mode 0: reference `basic`; 1: b200 with lambdas; 2: b200 with named callbacks (fused stage kernel)
+        auto run = [&](const auto& flux_func, const auto mode_c, std::vector<real_t>& out, double& seconds)
+        {
+            constexpr int mode = decltype(mode_c)::value;
+            prim_t fill1 = 0.0; flux_t fill2 = 0.0;
+            spade::grid::grid_array prim(grid, fill1, exch, spade::device::gpu);
+            spade::grid::grid_array rhs (grid, fill2, exch, spade::device::gpu);
+            spade::algs::fill_array(prim, ic);
+            cons_t cstate;
+            spade::fluid_state::state_transform_t trans(cstate, air);
+            spade::time_integration::time_axis_t axis(real_t(0.0), dt);
+            spade::time_integration::rk4_t alg;
+            auto ref_handle = spade::grid::make_exchange(prim, periodic);
+            auto new_handle = spade::b200::make_exchange(prim, periodic);
+            auto go = [&](const auto& calc_rhs, const auto& bc)
+            {
+                bc(prim, real_t(0.0));
+                spade::time_integration::integrator_data_t qd(std::move(prim), std::move(rhs), alg);
+                spade::time_integration::integrator_t ti(axis, alg, qd, calc_rhs, bc, trans);
+                ti.advance();
+                cudaDeviceSynchronize();
+                const auto t0w = std::chrono::steady_clock::now();
+                for (int n = 0; n < nsteps; ++n) ti.advance();
+                cudaDeviceSynchronize();
+                seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0w).count();
+                auto& sol = ti.solution();
+                out.resize(sol.data.size());
+                cudaMemcpy(out.data(), &sol.data[0], sizeof(real_t)*out.size(), cudaMemcpyDeviceToHost);
+            };
+            if constexpr (mode == 2)
+                go(spade::b200::flux_div_rhs(flux_func), spade::b200::exchange_bc(new_handle, pool));
+            else if constexpr (mode == 1)
+                go([&](auto& rr, const auto& qq, const auto&) { spade::pde_algs::flux_div(qq, rr, flux_func, spade::algs::make_traits(spade::pde_algs::b200, spade::pde_algs::overwrite)); },
+                   [&](auto& qq, const auto&) { new_handle.exchange(qq, pool); });
+            else
+                go([&](auto& rr, const auto& qq, const auto&) { spade::pde_algs::flux_div(qq, rr, flux_func, spade::algs::make_traits(spade::pde_algs::basic, spade::pde_algs::overwrite)); },
+                   [&](auto& qq, const auto&) { ref_handle.exchange(qq, pool); });
+        };
+        auto rel = [](const std::vector<real_t>& a, const std::vector<real_t>& b)
+        {
+            double num = 0.0, den = 0.0;
+            for (std::size_t i = 0; i < a.size(); ++i) { const double d = a[i] - b[i]; num += d*d; den += a[i]*a[i]; }
+            return std::sqrt(num/den);
+        };
+        const double work = double(nb)*nb*nb*double(nc)*nc*nc*4*nsteps;
+        std::vector<real_t> qa, qb, qc, qd;
+        double ta = 0.0, tb = 0.0, tc = 0.0, td = 0.0;
+        run(tscheme, std::integral_constant<int, 0>(), qa, ta);
+        run(tscheme, std::integral_constant<int, 1>(), qb, tb);
+        spade::convective::hybrid_scheme_t hyb(tscheme, wscheme, ducr, spade::convective::full_flux);
+        const auto c3 = spade::omni::compose(hyb, vscheme);
+        run(c3, std::integral_constant<int, 1>(), qc, tc);
+        run(c3, std::integral_constant<int, 2>(), qd, td);
+        std::printf("{\"solver\": \"channel_curv_demo\", \"blocks\": %d, \"cells_per_block\": %d, \"steps\": %d, "
+                    "\"reference_gpu_basic_convective_cell_stage_updates_per_s\": %.6e, \"b200_convective_cell_stage_updates_per_s\": %.6e, "
+                    "\"speedup_convective\": %.2f, \"rel_l2_convective\": %.3e, "
+                    "\"b200_hybrid_visc_cell_stage_updates_per_s\": %.6e, \"b200_hybrid_visc_fused_cell_stage_updates_per_s\": %.6e, "
+                    "\"rel_l2_hybrid_fused_vs_unfused\": %.3e}\n",
+                    nb, nc, nsteps, work/ta, work/tb, ta/tb, rel(qa, qb), work/tc, work/td, rel(qc, qd));
+    });
+    return 0;
+}

@@ -22,3 +22,20 @@ def test_spade_api_solver_through_the_shim(scheme):
     assert line["rel_l2"] < 1e-12                  # callbacks as lambdas: flux_div(b200) + spb_rk_update + exchange
     assert line["rel_l2_fused"] < 1e-12            # callbacks as b200::flux_div_rhs / b200::exchange_bc: one kernel per stage
     assert line["umax"] > 300.0
+
+
+BIN_CURV = os.path.join(ROOT, "integration", "_build", "channel_curv_demo")
+
+
+@pytest.mark.gpu
+def test_spade_api_solver_on_a_stretched_grid_through_the_shim():
+    """coords::diagonal_coords(scaled, integrated_tanh_1D, identity): the reference's own CUDA flux_div(basic) for totani_lr
+    (compiled with the header repair of oracle/ref_driver_curv.cc) against the drop-in reading the same grid object; and the
+    config-3 functor (hybrid + ducros + visc_lr) on that grid through both drop-in paths."""
+    if not os.path.exists(BIN_CURV):
+        pytest.skip("integration/_build/channel_curv_demo not built (needs /root/reference at build time)")
+    out = subprocess.run([BIN_CURV, "2", "16", "2"], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(BIN_CURV))
+    assert out.returncode == 0, out.stdout + out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["rel_l2_convective"] < 1e-12
+    assert line["rel_l2_hybrid_fused_vs_unfused"] < 1e-12

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--scheme", default="central")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--coords", default="identity", help="identity | channel (diagonal_coords: scaled x, integrated tanh y)")
     a = ap.parse_args()
     import torch
     import bench
@@ -27,7 +28,8 @@ def main():
     lat = tuple(a.lattice)
     L = 2 * 3.141592653589793
     blocks = sp.cartesian_blocks_t(lat, [0.0, L] * 3)
-    grid = sp.cartesian_grid_t((a.block,) * 3, blocks, sp.identity(), sp.pool_t())
+    coords = sp.identity() if a.coords == "identity" else sp.diagonal_coords(sp.scaled_coord_1D(2.0), sp.integrated_tanh_1D(0.0, L, 0.1, 4.0), None)
+    grid = sp.cartesian_grid_t((a.block,) * 3, blocks, coords, sp.pool_t())
     gas = sp.ideal_gas_t(bench.GAMMA, bench.RGAS)
     mu = (bench.P0 / (bench.RGAS * bench.T0)) * bench.U0 / bench.REYNOLDS
     visc = sp.visc_lr(sp.constant_viscosity_t(mu, bench.PRANDTL), gas)
@@ -91,7 +93,7 @@ def main():
     if a.scheme in ("central", "euler", "hybrid", "ck4"):
         for nin, out in ((0, 1), (1, 1), (2, 1), (1, 0)):
             timeit(f"fused_stage[nin={nin},out={out}]", lambda nin=nin, out=out: fused(nin, out), 80.0 + 40.0 * nin + 40.0 * out)
-    if a.scheme in ("central", "euler"):
+    if a.scheme in ("central", "euler") and a.coords == "identity":
         for nin, out in ((0, 1), (1, 1), (2, 1), (1, 0)):
             timeit(f"fused_stage+ghosts[nin={nin},out={out}]", lambda nin=nin, out=out: fused(nin, out, True),
                    80.0 + 40.0 * nin + 40.0 * out + 40.0 * ghost_frac)
