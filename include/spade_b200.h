@@ -164,6 +164,13 @@ int spb_rk_update(const spb_grid* g, double* q_dev, const double* const* k_dev, 
 int spb_ssprk3_stage(const spb_grid* g, int stage, double* q_dev, double* r0_dev, const double* r1_dev,
                      double dt, double gamma, double R, void* stream);
 
+/* Generic integrate_advance (reference src/time-integration/advance.h:109-230, the path taken when `trans` is not a
+ * state_transform_t, e.g. time_integration::identity_transform): its building block
+ *     resid *= c;  sol += resid  (sol -= resid if subtract);  resid *= 1.0/c
+ * (advance.h:149-153, 190-194, 216-221; the scalar passes touch every element incl. exchange cells, the array pass the
+ * interior, grid_array.h:289-321,359-369) as ONE pass instead of three, bit-identical including the round trip of resid. */
+int spb_axpy_roundtrip(const spb_grid* g, double* sol_dev, double* resid_dev, double c, int subtract, void* stream);
+
 /* ---- reduction: replaces algs::transform_reduce(array, make_reduction(array, f, op)) ----------
  * reference src/algs/transform_reduce.h:43-191. Closed set of element kernels `f`. */
 enum { SPB_RED_MAX = 0, SPB_RED_SUM = 1 };

@@ -46,7 +46,7 @@ namespace spade::b200
     template <typename F> inline void fill(spb_flux_desc&, const F&)
     {
         static_assert(always_false<F>::value, "spade_b200: this flux functor type is not in the implemented set "
-            "(totani_lr, cent_keep<2|4>, fweno_t, hybrid_scheme_t<central, fweno_t, ducros_t>, visc_lr<constant_viscosity_t>, omni::compose of those); "
+            "(totani_lr, cent_keep<2|4>, fweno_t, weno_t<rusanov_t>, hybrid_scheme_t<central, fweno_t | weno_t<rusanov_t>, ducros_t>, visc_lr<constant_viscosity_t>, omni::compose of those); "
             "there is no CPU fallback");
     }
     template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::totani_lr<gas_t>& f)
@@ -58,6 +58,18 @@ namespace spade::b200
     }
     template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::fweno_t<gas_t, convective::enable_smooth>& f)
     { d.conv = SPB_CONV_FWENO; fill_gas(d, f.gas); }
+    // weno_t<rusanov_t> (convective.h:256-333, flux_funcs.h:9-53): the same reconstruction as fweno_t on precomputed split
+    // fluxes (the nonlinear weights are algebraically identical); runs on the fweno_t kernel, agrees to round-off
+    template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::weno_t<convective::rusanov_t<gas_t>, convective::enable_smooth>& f)
+    { d.conv = SPB_CONV_FWENO; fill_gas(d, f.flux_func.gas); }
+    template <typename s0_t, typename gas_t, typename float_t, typename tag_t>
+    inline void fill(spb_flux_desc& d, const convective::hybrid_scheme_t<s0_t, convective::weno_t<convective::rusanov_t<gas_t>, convective::enable_smooth>, state_sensor::ducros_t<float_t>, tag_t>& f)
+    {
+        fill(d, f.scheme0);
+        d.diss = SPB_DISS_FWENO;
+        d.blend = tag_t::value ? SPB_BLEND_FULL_FLUX : SPB_BLEND_DISS_FLUX;
+        d.sensor_eps = f.blender.epsilon;
+    }
     template <typename s0_t, typename gas_t, typename float_t, typename tag_t>
     inline void fill(spb_flux_desc& d, const convective::hybrid_scheme_t<s0_t, convective::fweno_t<gas_t, convective::enable_smooth>, state_sensor::ducros_t<float_t>, tag_t>& f)
     {

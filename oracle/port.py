@@ -72,6 +72,12 @@ def advance(cfg, q, dt, nsteps):
     return out
 
 
+def advance_generic(cfg, q, dt, nsteps, high_storage=False):
+    out = np.array(q, dtype=np.float64, copy=True)
+    assert lib().spo_advance_generic(C.byref(cfg), _ptr(out), C.c_double(dt), int(nsteps), int(bool(high_storage))) == 0
+    return out
+
+
 def boundary_fill(cfg, bc, q):
     out = np.array(q, dtype=np.float64, copy=True)
     assert lib().spo_boundary_fill(C.byref(cfg), C.byref(bc), _ptr(out)) == 0

@@ -107,6 +107,12 @@ def advance(cfg, q, dt, nsteps):
     return out, sec.value
 
 
+def advance_generic(cfg, q, dt, nsteps, high_storage=False):
+    out = np.array(q, dtype=np.float64, copy=True)
+    _check(lib().ref_advance_generic(C.byref(cfg), _ptr(out), C.c_double(dt), int(nsteps), int(bool(high_storage))))
+    return out
+
+
 def boundary_fill(cfg, bc, q):
     out = np.array(q, dtype=np.float64, copy=True)
     _check(lib().ref_boundary_fill(C.byref(cfg), C.byref(bc), _ptr(out)))

@@ -159,6 +159,20 @@ namespace
                 func(spade::omni::compose(hyb, vscheme));
                 break;
             }
+            case 9:
+            {
+                spade::convective::rusanov_t rus(air);
+                func(spade::convective::weno_t(rus));
+                break;
+            }
+            case 10:
+            {
+                spade::convective::rusanov_t rus(air);
+                spade::convective::weno_t wrus(rus);
+                spade::convective::hybrid_scheme_t hyb(tscheme, wrus, ducr, spade::convective::full_flux);
+                func(spade::omni::compose(hyb, vscheme));
+                break;
+            }
             default: throw std::runtime_error("ref_driver: unknown scheme id");
         }
     }
@@ -426,6 +440,48 @@ extern "C"
                 });
             });
             if (seconds) *seconds = tmax;
+        });
+    }
+
+    // the same through the GENERIC integrate_advance (advance.h:109-230): no state transform (identity_transform), the array
+    // itself is integrated; integrator: 0 rk4_t, 2 ssprk3_t, 3 rk2_t; high_storage: rk2hs_t / ssprk3hs_t
+    int ref_advance_generic(const ref_cfg* c, double* q, double dt, int nsteps, int high_storage)
+    {
+        return guarded([&]
+        {
+            with_setup(*c, [&](auto& pool, auto& grid, auto& prim, auto& rhs, auto& handle, std::size_t off, std::size_t cnt)
+            {
+                std::copy(q + off, q + off + cnt, prim.data.begin());
+                with_scheme(*c, [&](const auto& flux_func)
+                {
+                    auto bc = [&](auto& qq, const auto& t) { handle.exchange(qq, pool); };
+                    auto calc_rhs = [&](auto& rr, const auto& qq, const auto& t)
+                    {
+                        spade::pde_algs::flux_div(qq, rr, flux_func, spade::algs::make_traits(spade::pde_algs::basic, spade::pde_algs::overwrite));
+                    };
+                    spade::time_integration::time_axis_t axis(real_t(0.0), real_t(dt));
+                    auto run = [&](const auto& alg)
+                    {
+                        spade::time_integration::integrator_data_t qd(std::move(prim), std::move(rhs), alg);
+                        spade::time_integration::integrator_t ti(axis, alg, qd, calc_rhs, bc);
+                        pool.sync();
+                        for (int n = 0; n < nsteps; ++n) ti.advance();
+                        pool.sync();
+                        const auto& sol = ti.solution();
+                        std::copy(sol.data.begin(), sol.data.end(), q + off);
+                    };
+                    const int id = c->integrator + 10*(high_storage ? 1 : 0);
+                    switch (id)
+                    {
+                        case 0:  { run(spade::time_integration::rk4_t());      break; }
+                        case 2:  { run(spade::time_integration::ssprk3_t());   break; }
+                        case 3:  { run(spade::time_integration::rk2_t());      break; }
+                        case 12: { run(spade::time_integration::ssprk3hs_t()); break; }
+                        case 13: { run(spade::time_integration::rk2hs_t());    break; }
+                        default: throw std::runtime_error("ref_driver: generic advance: integrator 0, 2, 3 (high storage: 2, 3)");
+                    }
+                });
+            });
         });
     }
 

@@ -416,6 +416,24 @@ class fweno_t(_functor):
         d.gamma, d.R = self.gas.gamma, self.gas.R
 
 
+class rusanov_t:
+    """convective::rusanov_t(gas), flux_funcs.h:9-53: the local Lax-Friedrichs split fluxes consumed by weno_t."""
+
+    def __init__(self, gas):
+        self.gas = gas
+
+
+class weno_t(fweno_t):
+    """convective::weno_t(rusanov_t(gas)) with enable_smooth, convective.h:256-333: the same reconstruction as fweno_t
+    (the nonlinear weights a0/(a0+a1) and be1^2/(2 be0^2 + be1^2) are the same number), applied to precomputed split
+    fluxes; it runs on the fweno_t kernel and agrees with the reference's weno_t to round-off."""
+
+    def __init__(self, flux_func):
+        if not isinstance(flux_func, rusanov_t):
+            raise SpbError("weno_t: implemented for the rusanov_t flux function")
+        super().__init__(flux_func.gas)
+
+
 class ducros_t:
     """state_sensor::ducros_t(epsilon), state_sensor.h:21-43"""
 
@@ -782,11 +800,17 @@ def transform_reduce(array, fn=FN_WAVESPEED, op=RED_MAX, gas=None, ivar=0):
 class rk_t:
     """Butcher table as exact ratios, explicit.h:27-116."""
 
-    def __init__(self, table, accum, dt, name):
+    def __init__(self, table, accum, dt, name, high_storage=False):
         self.table = [[Fraction(x) for x in row] for row in table]
         self.accum = [Fraction(x) for x in accum]
         self.dt = [Fraction(x) for x in dt]
         self.name = name
+        self.high_storage = bool(high_storage)
+
+    def var_size(self):
+        """explicit.h:33: the high-storage variants keep a second copy of the solution (same arithmetic in the fused
+        prim/cons path, advance.h:236-280, which never touches the second copy)."""
+        return 2 if self.high_storage else 1
 
     def rhs_size(self):
         return len(self.table[0])
@@ -797,9 +821,12 @@ class rk_t:
 
 F = Fraction
 rk2_t = rk_t([[0, 0], [F(1, 2), 0]], [0, 1], [0, F(1, 2)], "rk2")
+rk2hs_t = rk_t([[0, 0], [F(1, 2), 0]], [0, 1], [0, F(1, 2)], "rk2hs", high_storage=True)
 rk4_t = rk_t([[0, 0, 0, 0], [F(1, 2), 0, 0, 0], [0, F(1, 2), 0, 0], [0, 0, 1, 0]],
              [F(1, 6), F(1, 3), F(1, 3), F(1, 6)], [0, F(1, 2), F(1, 2), 1], "rk4")
 ssprk3_t = rk_t([[0, 0, 0], [1, 0, 0], [F(1, 4), F(1, 4), 0]], [F(1, 6), F(1, 6), F(2, 3)], [0, 1, F(1, 2)], "ssprk3")
+ssprk3hs_t = rk_t([[0, 0, 0], [1, 0, 0], [F(1, 4), F(1, 4), 0]], [F(1, 6), F(1, 6), F(2, 3)], [0, 1, F(1, 2)], "ssprk3hs",
+                  high_storage=True)
 ssprk34_t = rk_t([[0, 0, 0, 0], [F(1, 2), 0, 0, 0], [F(1, 2), F(1, 2), 0, 0], [F(1, 6), F(1, 6), F(1, 6), 0]],
                  [F(1, 6), F(1, 6), F(1, 6), F(1, 2)], [0, F(1, 2), 1, F(1, 2)], "ssprk34")
 rk38r_t = rk_t([[0, 0, 0, 0], [F(1, 3), 0, 0, 0], [F(-1, 3), 1, 0, 0], [1, -1, 1, 0]],
@@ -839,7 +866,8 @@ class integrator_data_t:
     """integrator_data_t(q, rhs, scheme): one solution array and rhs_size() residual registers."""
 
     def __init__(self, q, rhs, scheme):
-        self.solution_data = [q]
+        nvar = scheme.var_size() if hasattr(scheme, "var_size") else 1
+        self.solution_data = [q] + [q.clone() for _ in range(nvar - 1)]          # high-storage tables: a second copy (explicit.h:33)
         self.residual_data = [rhs] + [rhs.clone() for _ in range(scheme.rhs_size() - 1)]
 
     def solution(self, i=0):
@@ -856,6 +884,14 @@ class state_transform_t:
         self.gas = gas
 
 
+class identity_transform_t:
+    """time_integration::identity_transform (integrator.h:8-14): the array itself is integrated — integrator_t then takes
+    the generic integrate_advance path (advance.h:109-230)."""
+
+
+identity_transform = identity_transform_t()
+
+
 class integrator_t:
     """integrator_t(axis, scheme, data, rhs_calc, boundary_cond, trans).advance()
     — the fused prim/cons path of advance.h:236-280 and the ssprk3_opt path of advance.h:359-402.
@@ -863,7 +899,13 @@ class integrator_t:
     (flux_div + stage update, spb_flux_div_rk_stage) writing into a second solution buffer; `fused=False` forces the
     two-kernel path."""
 
-    def __init__(self, axis, scheme, data, rhs_calc, boundary_cond, trans, fused=True, fuse_exchange=True):
+    def __init__(self, axis, scheme, data, rhs_calc, boundary_cond, trans=identity_transform, fused=True, fuse_exchange=True):
+        if not isinstance(trans, (state_transform_t, identity_transform_t)):
+            raise SpbError("integrator_t: trans is a state_transform_t or identity_transform")
+        if isinstance(trans, identity_transform_t):
+            if not isinstance(scheme, rk_t):
+                raise SpbError("integrator_t: ssprk3_opt needs a state_transform_t (advance.h:359)")
+            fused = False
         self.axis, self.scheme, self.data = axis, scheme, data
         self.rhs_calc, self.boundary_cond, self.trans = rhs_calc, boundary_cond, trans
         self._plan = None
@@ -987,7 +1029,40 @@ class integrator_t:
         ks = (C.c_void_p * nk)(*[r.data.data_ptr() for r in self.data.residual_data[:nk]])
         check(lib().spb_rk_update(q.h, _dptr(q.data), ks, nk, coeff, self.trans.gas.gamma, self.trans.gas.R, _stream_ptr()))
 
+    def _advance_generic(self):
+        """integrate_advance for a trans that is not a state_transform_t (advance.h:109-230) with identity_transform: per
+        stage the solution is augmented with dt a_ij k_j, the residual evaluated, and (without a second copy of the
+        solution) the augmentation taken out again; each `resid *= c; sol += resid; resid *= 1/c` triple is one kernel."""
+        ax, dt, d, s = self.axis, self.axis.dt, self.data, self.scheme
+        second = len(d.solution_data) > 1
+
+        def axpy(sol, resid, c, subtract):
+            check(lib().spb_axpy_roundtrip(sol.h, _dptr(sol.data), _dptr(resid.data), float(c), int(subtract), _stream_ptr()))
+
+        for i in range(s.rows()):
+            sol = d.solution(1 if second else 0)
+            if second:
+                sol.data.copy_(d.solution(0).data)
+            used = [j for j in range(i) if s.table[i][j] != 0]
+            for j in used:
+                axpy(sol, d.residual(j), dt * (s.table[i][j].numerator / s.table[i][j].denominator), 0)
+            t = ax.t + float(s.dt[i]) * dt
+            if i > 0:
+                self.boundary_cond(sol, t)
+            self.rhs_calc(d.residual(i), sol, t)
+            if not second:
+                for j in used:
+                    axpy(sol, d.residual(j), dt * (s.table[i][j].numerator / s.table[i][j].denominator), 1)
+        q = d.solution(0)
+        for i in range(s.rows()):
+            if s.accum[i] != 0:
+                axpy(q, d.residual(i), (s.accum[i].numerator / s.accum[i].denominator) * dt, 0)
+        ax.t += dt
+        self.boundary_cond(q, ax.t)
+
     def advance(self):
+        if isinstance(self.trans, identity_transform_t):
+            return self._advance_generic()
         if self._plan is not None:
             return self._advance_fused()
         ax, q, dt = self.axis, self.data.solution(0), self.axis.dt

@@ -123,8 +123,49 @@ namespace spb
     }
 }
 
+namespace spb
+{
+    // generic integrate_advance (advance.h:149-153, 190-194, 216-221): the reference's three passes
+    //   resid *= c (every element incl. exchange cells, grid_array.h:359-369);  sol +-= resid (interior, grid_array.h:289-321);
+    //   resid *= 1.0/c
+    // as one pass with the same per-element operations in the same order (no FMA contraction: the rounding of resid*c is
+    // part of the reference's result, and resid comes back perturbed by the round trip exactly like there)
+    __global__ void __launch_bounds__(256) axpy_roundtrip_kernel(double* __restrict__ sol, double* __restrict__ resid, const double c,
+                                                                 const double inv_c, const int subtract, const CellDims G, const long long ncell_all)
+    {
+        const long long stride = (long long)gridDim.x*blockDim.x;
+        for (long long cell = (long long)blockIdx.x*blockDim.x + threadIdx.x; cell < ncell_all; cell += stride)
+        {
+            const int ip = (int)(cell % G.np[0]); long long t = cell / G.np[0];
+            const int jp = (int)(t % G.np[1]); t /= G.np[1];
+            const int kp = (int)(t % G.np[2]);
+            const bool interior = ip >= G.ng[0] && ip < G.ng[0] + G.nx[0] && jp >= G.ng[1] && jp < G.ng[1] + G.nx[1]
+                               && kp >= G.ng[2] && kp < G.ng[2] + G.nx[2];
+            #pragma unroll
+            for (int v = 0; v < 5; ++v)
+            {
+                const double r = __dmul_rn(resid[5*cell + v], c);
+                if (interior) sol[5*cell + v] = subtract ? __dsub_rn(sol[5*cell + v], r) : __dadd_rn(sol[5*cell + v], r);
+                resid[5*cell + v] = __dmul_rn(r, inv_c);
+            }
+        }
+    }
+}
+
 extern "C"
 {
+    int spb_axpy_roundtrip(const spb_grid* g, double* sol_dev, double* resid_dev, double c, int subtract, void* stream)
+    {
+        using namespace spb;
+        if (!g || !sol_dev || !resid_dev) { set_error("spb_axpy_roundtrip: null argument"); return SPB_ERR_BAD_ARG; }
+        const CellDims G = make_dims(g);
+        const long long nall = (long long)g->np[0]*g->np[1]*g->np[2]*g->nlb;
+        if (nall == 0) return 0;
+        axpy_roundtrip_kernel<<<grid_for(g, nall, 256, 8), 256, 0, (cudaStream_t)stream>>>(sol_dev, resid_dev, c, 1.0/c, subtract, G, nall);
+        SPB_LAUNCH_CHECK();
+        return 0;
+    }
+
     int spb_rk_update(const spb_grid* g, double* q_dev, const double* const* k_dev, int nk, const double* coeff,
                       double gamma, double R, void* stream)
     {

@@ -13,11 +13,11 @@ import pytest
 from util import GAMMA, RGAS, make_state, oracle_cfg, rel_l2, zero_ghosts
 
 
-@pytest.mark.parametrize("scheme", range(9))
+@pytest.mark.parametrize("scheme", range(11))
 def test_flux_div_all_schemes(ref_lib, scheme):
     from oracle import port
     nb, n, ng = (2, 1, 2), (8, 6, 4), 2
-    q = make_state(nb, n, ng, seed=scheme, jump=scheme in (1, 6, 8))
+    q = make_state(nb, n, ng, seed=scheme, jump=scheme in (1, 6, 8, 10))
     cfg = oracle_cfg(nb, n, ng, scheme=scheme)
     want = ref_lib.flux_div(cfg, q.ravel())
     got = port.flux_div(cfg, q.ravel())
@@ -184,3 +184,16 @@ def test_channel_trajectory(ref_lib, integ):
     want, _ = ref_lib.advance_channel(cfg, bc, q0, dt, 3)
     got = port.advance_channel(cfg, bc, q0, dt, 3)
     assert rel_l2(got, want) < 1e-14
+
+
+@pytest.mark.parametrize("integ,hs", [(0, False), (2, False), (3, False), (2, True), (3, True)])
+def test_generic_integrate_advance_bit_exact(ref_lib, integ, hs):
+    """integrator_t without a state transform (identity_transform): the generic integrate_advance of advance.h:109-230,
+    including the rounding of its scale / add / unscale passes and the high-storage tables rk2hs_t / ssprk3hs_t."""
+    from oracle import port
+    nb, n, ng = (2, 1, 2), (8, 4, 4), 2
+    cfg = oracle_cfg(nb, n, ng, scheme=0, integrator=integ)
+    q0 = port.exchange(cfg, make_state(nb, n, ng, seed=3).ravel())
+    want = ref_lib.advance_generic(cfg, q0, 1e-5, 2, hs)
+    assert np.array_equal(port.advance_generic(cfg, q0, 1e-5, 2, hs), want)
+    assert rel_l2(want, q0) > 1e-5

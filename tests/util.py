@@ -87,7 +87,9 @@ def product_flux(scheme, gamma=GAMMA, R=RGAS, mu=1e-2, prandtl=0.72, eps=1e-2):
             5: lambda: w,
             6: lambda: sp.compose(sp.hybrid_scheme_t(ck4, w, du, sp.full_flux), v),
             7: lambda: ck4,
-            8: lambda: sp.compose(sp.hybrid_scheme_t(t, w, du, sp.diss_flux), v)}[scheme]()
+            8: lambda: sp.compose(sp.hybrid_scheme_t(t, w, du, sp.diss_flux), v),
+            9: lambda: sp.weno_t(sp.rusanov_t(gas)),
+            10: lambda: sp.compose(sp.hybrid_scheme_t(t, sp.weno_t(sp.rusanov_t(gas)), du, sp.full_flux), v)}[scheme]()
 
 
 def oracle_cfg(nb, n, ng=2, scheme=0, mu=1e-2, prandtl=0.72, eps=1e-2, periodic=(1, 1, 1), nranks=1, integrator=0,
