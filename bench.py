@@ -70,7 +70,28 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thr = None
 
+    def _run_nvml(self):
+        """NVML directly (nvidia_ml_py): a query takes well under a millisecond, so even a 0.2 s timed region gets
+        tens of samples; same quantities as the nvidia-smi line of the recipe."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for n, b in bits.items():
+                if r & b:
+                    self.reasons.add(n)
+            self._stop.wait(0.005)
+
     def _run(self):
+        try:
+            return self._run_nvml()
+        except Exception:
+            pass                      # no NVML binding: the nvidia-smi line of the recipe
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]

@@ -14,6 +14,7 @@ the same thing for Python drivers, the tests and bench.py. torch supplies device
 torch.distributed — every kernel is in libspade_b200.so.
 """
 import ctypes as C
+import os
 from fractions import Fraction
 
 import numpy as np
@@ -656,11 +657,18 @@ class exchange_bc_t:
     rank-boundary blocks are advanced first, their ghost messages leave over NVLink, and the rank-interior blocks are
     advanced while the messages are in flight."""
 
-    def __init__(self, handle):
-        self.handle = handle
+    def __init__(self, handle, boundaries=None, kern=None):
+        """boundaries / kern: the other half of a wall-bounded solver's callback, algs::boundary_fill(q, boundaries, kern)
+        after the exchange (bc = exchange + boundary_fill)."""
+        self.handle, self.boundaries, self.kern = handle, boundaries, kern
+
+    def after(self, q):
+        if self.boundaries is not None:
+            boundary_fill(q, self.boundaries, self.kern)
 
     def __call__(self, q, t):
         self.handle.exchange(q)
+        self.after(q)
 
 
 def make_exchange(array, periodic, tables=None):
@@ -1016,6 +1024,7 @@ class integrator_t:
                 tnext = ax.t
             if ex is not None:
                 ex.finish(cur, local=not self._fuse_exchange)
+                self.boundary_cond.after(cur)
             else:
                 self.boundary_cond(cur, tnext)
         if cur is not d.solution(0):                       # odd number of stages: the result sits in the scratch buffer
@@ -1089,6 +1098,48 @@ class integrator_t:
         self._update(s.table[s.rows() - 1], s.accum)
         ax.t += dt
         self.boundary_cond(q, ax.t)
+
+
+# ---- checkpoint files in the reference's byte order (reference src/io/io_native.h:18-56) --------------------------
+class io:
+    """io::binary_write / io::binary_read: a headerless file in which global block lb_glob occupies the bytes
+    [lb_glob * B, (lb_glob + 1) * B), B = bytes of one padded block (exchange cells included) in the array's own memory
+    order. The device layout here IS that order, so a rank's share is one contiguous slab at offset first_block * B:
+    checkpoints written by a SPADE solver restart here and the other way round."""
+
+    @staticmethod
+    def _slab(array):
+        per_block = int(np.prod(array.shape[1:])) * 8
+        return per_block, array.grid.first_block * per_block
+
+    @staticmethod
+    def binary_write(filename, array):
+        per_block, off = io._slab(array)
+        host = array.data.cpu().numpy()
+        pool = array.grid.group()
+        if pool.isroot():
+            total = (array.grid.get_num_global_blocks() if array.grid.blocks is not None else array.shape[0]) * per_block
+            with open(filename, "ab"):
+                pass
+            os.truncate(filename, total)
+        pool.sync()
+        with open(filename, "r+b") as f:
+            f.seek(off)
+            f.write(host.tobytes())
+        pool.sync()
+
+    @staticmethod
+    def binary_read(filename, array):
+        per_block, off = io._slab(array)
+        nbytes = per_block * array.shape[0]
+        with open(filename, "rb") as f:
+            f.seek(off)
+            raw = f.read(nbytes)
+        if len(raw) != nbytes:
+            raise SpbError(f"binary_read: {filename} holds {len(raw)} of the {nbytes} bytes of this rank's blocks")
+        host = torch.from_numpy(np.frombuffer(raw, dtype=np.float64).reshape(array.shape).copy())
+        array.data.copy_(host.pin_memory(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
 
 def launch_count():

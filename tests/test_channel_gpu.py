@@ -83,3 +83,32 @@ def test_channel_trajectory_matches_oracle(integ):
     got = ti.solution().to_host()
     assert rel_l2(got, want) < 1e-12
     assert rel_l2(got - q0, want - q0) < 1e-9
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_wall_bounded_fused_stage_path_matches_oracle(scheme):
+    """exchange_bc_t(handle, boundaries, wall): the boundary callback of a channel solver as an object, so that integrator_t
+    keeps its one-kernel-per-stage path (narrow kernel + fused same-rank ghosts for scheme 0, wide kernel for the hybrid
+    scheme) and fills the walls after the exchange like `handle.exchange(q); boundary_fill(q, ymin || ymax, wall)`."""
+    from oracle import port, ref
+    nb, n, ng = (2, 2, 2), (16, 8, 8), 2
+    periodic = (1, 0, 1)
+    sp, blocks, grid = product_setup(nb, n, ng)
+    cfg = oracle_cfg(nb, n, ng, scheme=scheme, integrator=0, periodic=periodic)
+    bc = ref.make_bc(mask=(0, 0, 1, 1, 0, 0), a=(1, -1, -1, -1, -1), b=(0, 2 * WALL_T, 0, 0, 0), force=(0.0, 0.0, 0.0))
+    q0 = make_state(nb, n, ng, seed=47, jump=scheme == 1)
+    q0 = port.boundary_fill(cfg, bc, port.exchange(cfg, q0.ravel())).reshape(q0.shape)
+    dt = 0.2 * (2 * np.pi / 32) / port.reduce_umax(cfg, q0.ravel())
+    want = port.advance_channel(cfg, bc, q0.ravel(), dt, 3).reshape(q0.shape)
+    gas = sp.ideal_gas_t(GAMMA, RGAS)
+    qa, ra = sp.grid_array.from_host(grid, q0), sp.grid_array(grid, 0.0)
+    ex = sp.make_exchange(qa, periodic)
+    bcs = sp.exchange_bc_t(ex, sp.boundary.ymin | sp.boundary.ymax, sp.noslip_isothermal_wall(WALL_T))
+    ti = sp.integrator_t(sp.time_axis_t(0.0, dt), sp.rk4_t, sp.integrator_data_t(qa, ra, sp.rk4_t),
+                         sp.flux_div_rhs_t(product_flux(scheme), sp.overwrite), bcs, sp.state_transform_t(gas))
+    assert ti._plan is not None
+    for _ in range(3):
+        ti.advance()
+    got = ti.solution().to_host()
+    assert rel_l2(got, want) < 1e-12
+    assert rel_l2(got - q0, want - q0) < 1e-9

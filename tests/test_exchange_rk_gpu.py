@@ -196,3 +196,23 @@ def test_generic_integrate_advance_matches_oracle(integ, hs):
     got = ti.solution().to_host().ravel()
     assert rel_l2(got, want) < 1e-12
     assert rel_l2(got - q0, want - q0) < 1e-9
+
+
+def test_checkpoint_file_is_the_reference_byte_order(tmp_path):
+    """io::binary_write / binary_read (reference src/io/io_native.h:18-56): block lb_glob at byte offset lb_glob * block_bytes,
+    padded block in the array's memory order, no header — i.e. the file is the global array as the reference stores it."""
+    nb, n, ng = (2, 2, 1), (8, 4, 4), 2
+    sp, blocks, grid = product_setup(nb, n, ng)
+    q = make_state(nb, n, ng, seed=9)
+    qa = sp.grid_array.from_host(grid, q)
+    f = str(tmp_path / "q.bin")
+    sp.io.binary_write(f, qa)
+    assert open(f, "rb").read() == q.tobytes()
+    back = sp.grid_array(grid, 0.0)
+    sp.io.binary_read(f, back)
+    assert np.array_equal(back.to_host(), q)
+    # a rank owning blocks 2..3 of the same file reads its own slab
+    sp2, _, grid2 = product_setup(nb, n, ng, rank=1, size=2)
+    part = sp2.grid_array(grid2, 0.0)
+    sp2.io.binary_read(f, part)
+    assert np.array_equal(part.to_host(), q[grid2.first_block:grid2.first_block + grid2.num_local_blocks])
