@@ -52,6 +52,10 @@ enum { SPB_CONV_NONE = 0, SPB_CONV_TOTANI = 1 /* totani_lr, convective.h:54-94 *
        SPB_CONV_FWENO = 3 /* fweno_t alone, convective.h:336-497 */ };
 enum { SPB_DISS_NONE = 0, SPB_DISS_FWENO = 1 /* hybrid_scheme_t(conv, fweno_t, ducros_t, tag) */ };
 enum { SPB_BLEND_FULL_FLUX = 0 /* (1-a)F0 + a F1 */, SPB_BLEND_DISS_FLUX = 1 /* F0 + a F1 */ };
+/* LES closure of visc_lr: viscous_laws::sgs_visc_t(constant_viscosity_t, subgrid_scale::wale_t(gas, cw, delta, prt)),
+ * reference src/navier-stokes/viscous_laws.h:175-216, subgrid_scale.h:25-91: mu += mu_t, beta -= 0.66666666667 mu_t,
+ * alpha += mu_t/prt with mu_t from the face gradient and the face density. */
+enum { SPB_SGS_NONE = 0, SPB_SGS_WALE = 1 };
 
 typedef struct spb_flux_desc
 {
@@ -64,6 +68,8 @@ typedef struct spb_flux_desc
     double beta;        /* constant_viscosity_t::beta   (= -2 mu/3 as stored by the reference) */
     double prandtl_inv; /* constant_viscosity_t::prandtl_inv */
     double sensor_eps;  /* state_sensor::ducros_t::epsilon, reference state_sensor.h:21-43 */
+    int    sgs;         /* SPB_SGS_* (needs visc) */
+    double sgs_cw, sgs_delta, sgs_prt;   /* wale_t::cw, delta, prt */
 } spb_flux_desc;
 
 /* ---- grid ------------------------------------------------------------------------------------

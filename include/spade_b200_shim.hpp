@@ -46,7 +46,7 @@ namespace spade::b200
     template <typename F> inline void fill(spb_flux_desc&, const F&)
     {
         static_assert(always_false<F>::value, "spade_b200: this flux functor type is not in the implemented set "
-            "(totani_lr, cent_keep<2|4>, fweno_t, weno_t<rusanov_t>, hybrid_scheme_t<central, fweno_t | weno_t<rusanov_t>, ducros_t>, visc_lr<constant_viscosity_t>, omni::compose of those); "
+            "(totani_lr, cent_keep<2|4>, fweno_t, weno_t<rusanov_t>, hybrid_scheme_t<central, fweno_t | weno_t<rusanov_t>, ducros_t>, visc_lr<constant_viscosity_t | sgs_visc_t<constant_viscosity_t, wale_t>>, omni::compose of those); "
             "there is no CPU fallback");
     }
     template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::totani_lr<gas_t>& f)
@@ -83,6 +83,13 @@ namespace spade::b200
     {
         d.visc = 1; d.mu = f.vlaw.visc; d.beta = f.vlaw.beta; d.prandtl_inv = f.vlaw.prandtl_inv; fill_gas(d, f.gas);
     }
+    // LES closure: visc_lr<sgs_visc_t<constant_viscosity_t, wale_t>> (viscous_laws.h:175-216, subgrid_scale.h:25-91)
+    template <typename float_t, typename wgas_t, typename gas_t>
+    inline void fill(spb_flux_desc& d, const viscous::visc_lr<viscous_laws::sgs_visc_t<viscous_laws::constant_viscosity_t<float_t>, subgrid_scale::wale_t<float_t, wgas_t>>, gas_t>& f)
+    {
+        d.visc = 1; d.mu = f.vlaw.lam.visc; d.beta = f.vlaw.lam.beta; d.prandtl_inv = f.vlaw.lam.prandtl_inv; fill_gas(d, f.gas);
+        d.sgs = SPB_SGS_WALE; d.sgs_cw = f.vlaw.turb.cw; d.sgs_delta = f.vlaw.turb.delta; d.sgs_prt = f.vlaw.turb.prt;
+    }
     template <typename k0_t> inline void fill(spb_flux_desc& d, const omni::composite_kernel_t<k0_t>& f) { fill(d, f.kern); }
     template <typename k0_t, typename k1_t, typename... ks_t>
     inline void fill(spb_flux_desc& d, const omni::composite_kernel_t<k0_t, k1_t, ks_t...>& f) { fill(d, f.kern); fill(d, f.next); }
@@ -92,6 +99,7 @@ namespace spade::b200
         spb_flux_desc d{};
         d.conv = SPB_CONV_NONE; d.diss = SPB_DISS_NONE; d.blend = SPB_BLEND_FULL_FLUX; d.visc = 0;
         d.gamma = 1.4; d.R = 287.15; d.prandtl_inv = 1.0;
+        d.sgs = SPB_SGS_NONE; d.sgs_prt = 1.0;
         fill(d, f);
         return d;
     }

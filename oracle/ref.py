@@ -13,7 +13,7 @@ class RefCfg(C.Structure):
                 ("bounds", C.c_double * 6), ("periodic", C.c_int * 3), ("scheme", C.c_int),
                 ("gamma", C.c_double), ("R", C.c_double), ("mu", C.c_double),
                 ("prandtl", C.c_double), ("sensor_eps", C.c_double), ("nranks", C.c_int),
-                ("integrator", C.c_int)]
+                ("integrator", C.c_int), ("sgs_cw", C.c_double), ("sgs_delta", C.c_double), ("sgs_prt", C.c_double)]
 
 
 class RefBc(C.Structure):
@@ -51,7 +51,7 @@ def lib():
 
 
 def make_cfg(nblocks, ncells, ng=2, bounds=None, periodic=(1, 1, 1), scheme=0, gamma=1.4, R=287.15,
-             mu=1.0e-3, prandtl=0.72, sensor_eps=1e-2, nranks=1, integrator=0):
+             mu=1.0e-3, prandtl=0.72, sensor_eps=1e-2, nranks=1, integrator=0, sgs=(0.55, 0.1, 0.9)):
     c = RefCfg()
     c.nblocks[:] = list(nblocks)
     c.ncells[:] = list(ncells)
@@ -64,6 +64,7 @@ def make_cfg(nblocks, ncells, ng=2, bounds=None, periodic=(1, 1, 1), scheme=0, g
     c.gamma, c.R, c.mu, c.prandtl, c.sensor_eps = gamma, R, mu, prandtl, sensor_eps
     c.nranks = nranks
     c.integrator = integrator
+    c.sgs_cw, c.sgs_delta, c.sgs_prt = [float(x) for x in sgs]
     return c
 
 

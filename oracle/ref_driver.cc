@@ -59,6 +59,7 @@ extern "C"
         double gamma, R, mu, prandtl, sensor_eps;
         int    nranks;        // number of thread-ranks
         int    integrator;    // 0 = rk4_t fused prim/cons, 1 = ssprk3_opt, 2 = ssprk3_t fused, 3 = rk2_t fused
+        double sgs_cw, sgs_delta, sgs_prt;   // subgrid_scale::wale_t(gas, cw, delta, prt) of schemes 11, 12
     };
 }
 
@@ -157,6 +158,24 @@ namespace
             {
                 spade::convective::hybrid_scheme_t hyb(tscheme, wscheme, ducr, spade::convective::diss_flux);
                 func(spade::omni::compose(hyb, vscheme));
+                break;
+            }
+            case 11:
+            {
+                // LES closure: visc_lr over sgs_visc_t(constant_viscosity_t, wale_t) (viscous_laws.h:175-216, subgrid_scale.h:25-91)
+                spade::subgrid_scale::wale_t eddy(air, real_t(c.sgs_cw), real_t(c.sgs_delta), real_t(c.sgs_prt));
+                spade::viscous_laws::sgs_visc_t slaw(vlaw, eddy);
+                spade::viscous::visc_lr svisc(slaw, air);
+                func(spade::omni::compose(tscheme, svisc));
+                break;
+            }
+            case 12:
+            {
+                spade::subgrid_scale::wale_t eddy(air, real_t(c.sgs_cw), real_t(c.sgs_delta), real_t(c.sgs_prt));
+                spade::viscous_laws::sgs_visc_t slaw(vlaw, eddy);
+                spade::viscous::visc_lr svisc(slaw, air);
+                spade::convective::hybrid_scheme_t hyb(tscheme, wscheme, ducr, spade::convective::full_flux);
+                func(spade::omni::compose(hyb, svisc));
                 break;
             }
             case 9:

@@ -53,6 +53,7 @@ extern "C"
         double gamma, R, mu, prandtl, sensor_eps;
         int    nranks;
         int    integrator;    // 0 rk4_t, 1 ssprk3_opt, 2 ssprk3_t, 3 rk2_t
+        double sgs_cw, sgs_delta, sgs_prt;   // (unused here)
     };
     // one 1-D mapping per direction (reference src/core/coord_system.h:54-177)
     //   kind 0 identity_1D; 1 scaled_coord_1D(par[0]); 2 integrated_tanh_1D(par[0..3] = y0, y1, inflation, rate); 3 quad_1D

@@ -460,18 +460,38 @@ class hybrid_scheme_t(_functor):
         d.sensor_eps = self.blender.epsilon
 
 
+class wale_t:
+    """subgrid_scale::wale_t(gas, cw, delta, prt), subgrid_scale.h:25-91 (Nicoud & Ducros eddy viscosity)."""
+
+    def __init__(self, gas, cw, delta, prt):
+        self.gas, self.cw, self.delta, self.prt = gas, float(cw), float(delta), float(prt)
+
+
+class sgs_visc_t:
+    """viscous_laws::sgs_visc_t(laminar, turb), viscous_laws.h:175-216: mu + mu_t, beta - 0.66666666667 mu_t, alpha + mu_t/Pr_t."""
+
+    def __init__(self, lam, turb):
+        if not isinstance(lam, constant_viscosity_t) or not isinstance(turb, wale_t):
+            raise SpbError("sgs_visc_t: implemented for (constant_viscosity_t, wale_t)")
+        self.lam, self.turb = lam, turb
+
+
 class visc_lr(_functor):
-    """viscous::visc_lr(vlaw, gas), viscous.h:14-113"""
+    """viscous::visc_lr(vlaw, gas), viscous.h:14-113; vlaw = constant_viscosity_t or sgs_visc_t(constant_viscosity_t, wale_t)"""
 
     def __init__(self, vlaw, gas):
-        if not isinstance(vlaw, constant_viscosity_t):
-            raise SpbError("visc_lr: only constant_viscosity_t has get_all() in the reference (viscous_laws.h:102-135)")
+        if not isinstance(vlaw, (constant_viscosity_t, sgs_visc_t)):
+            raise SpbError("visc_lr: constant_viscosity_t or sgs_visc_t (power_law_t has no get_all() in the reference, viscous_laws.h:102-135)")
         self.vlaw, self.gas = vlaw, gas
 
     def _fill(self, d):
+        lam = self.vlaw.lam if isinstance(self.vlaw, sgs_visc_t) else self.vlaw
         d.visc = 1
-        d.mu, d.beta, d.prandtl_inv = self.vlaw.visc, self.vlaw.beta, self.vlaw.prandtl_inv
+        d.mu, d.beta, d.prandtl_inv = lam.visc, lam.beta, lam.prandtl_inv
         d.gamma, d.R = self.gas.gamma, self.gas.R
+        if isinstance(self.vlaw, sgs_visc_t):
+            t = self.vlaw.turb
+            d.sgs, d.sgs_cw, d.sgs_delta, d.sgs_prt = 1, t.cw, t.delta, t.prt
 
 
 class composite_kernel_t(_functor):
@@ -497,6 +517,7 @@ def flux_desc(flux_func):
     d = FluxDesc()
     d.conv, d.diss, d.blend, d.visc = CONV_NONE, DISS_NONE, BLEND_FULL_FLUX, 0
     d.gamma, d.R, d.mu, d.beta, d.prandtl_inv, d.sensor_eps = 1.4, 287.15, 0.0, 0.0, 1.0, 0.0
+    d.sgs, d.sgs_cw, d.sgs_delta, d.sgs_prt = 0, 0.0, 0.0, 1.0
     flux_func._fill(d)
     return d
 
@@ -924,6 +945,8 @@ class integrator_t:
             f = rhs_calc.flux
             narrow = f.diss == DISS_NONE and f.conv in (CONV_NONE, CONV_TOTANI) and (f.conv != CONV_NONE or f.visc)
             wide = bool(f.visc) and ((f.conv == CONV_TOTANI and f.diss == DISS_FWENO) or f.conv == CONV_CENT_KEEP4)
+            if f.sgs:                      # the WALE closure rides on the wide kernel for every functor set it supports
+                narrow, wide = False, bool(f.visc) and f.conv in (CONV_NONE, CONV_TOTANI, CONV_CENT_KEEP4)
             if narrow or wide:
                 self._plan = self._fused_plan(scheme)
 

@@ -23,6 +23,7 @@ namespace spb
         double mu, beta, two_mu, kappa;
         double eps;
         int    blend;                 // SPB_BLEND_*
+        double sgs_c, sgs_cp_prt;     // wale_t: cw^2 delta^2; (gamma R/(gamma-1))/Pr_t
     };
 
     // Fused RK stage (spb_flux_div_rk_stage): with r = rhs(q_in) of a cell,
@@ -209,7 +210,35 @@ namespace spb
     }
 
     // ---- the composed functor on the lower face (direction D) of the cell the accessor is centred on
-    template <int CONV, int DISS, int VISC, int D, bool CURV = false, class A>
+    // ---- subgrid_scale::wale_t::get_mu_t (subgrid_scale.h:45-90) from the face gradient g[dir][comp] and the face density
+    __device__ __forceinline__ double wale_mu_t(const FluxParams& P, const double rho, const double (&g)[3][3])
+    {
+        // gij(i,j) = grad[j].u(i) = g[j][i];  gij2 = gij gij;  sd = sym(gij2) - tr(gij2)/3 I;  s = sym(gij)
+        double g2[3][3];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i)
+            #pragma unroll
+            for (int j = 0; j < 3; ++j) g2[i][j] = fma(g[0][i], g[j][0], fma(g[1][i], g[j][1], g[2][i]*g[j][2]));
+        const double tr3 = 0.33333333333333333*(g2[0][0] + g2[1][1] + g2[2][2]);
+        double ssd = 0.0, ss = 0.0;
+        #pragma unroll
+        for (int i = 0; i < 3; ++i)
+            #pragma unroll
+            for (int j = 0; j < 3; ++j)
+            {
+                double sd = 0.5*(g2[i][j] + g2[j][i]);
+                if (i == j) sd -= tr3;
+                ssd = fma(sd, sd, ssd);
+                const double sij = 0.5*(g[j][i] + g[i][j]);
+                ss = fma(sij, sij, ss);
+            }
+        const double sqrt0 = sqrt_nr(fmax(ssd, 1e-300));
+        const double sqrt1 = sqrt_nr(sqrt0);
+        const double sqrt2 = sqrt_nr(fmax(ss, 1e-300));
+        return rho*P.sgs_c*ssd*sqrt0*rcp_nr(1e-8 + fma(ss*ss, sqrt2, ssd*sqrt1));
+    }
+
+    template <int CONV, int DISS, int VISC, int D, bool CURV = false, bool SGS = false, class A>
     __device__ __forceinline__ void face_flux(const A& a, const FluxParams& P, const double (&invdx)[3], double (&F)[5],
                                               const double area = 1.0)
     {
@@ -247,8 +276,8 @@ namespace spb
             #pragma unroll
             for (int c = 0; c < 3; ++c)
             {
-                const bool need1 = DISS || (c == T1) || (c == D);
-                const bool need2 = DISS || (c == T2) || (c == D);
+                const bool need1 = DISS || SGS || (c == T1) || (c == D);
+                const bool need2 = DISS || SGS || (c == T2) || (c == D);
                 g[T1][c] = 0.0; g[T2][c] = 0.0;
                 if (need1)
                     g[T1][c] = c1*((qrel<D>(a, 2+c, -1,  1, 0) - qrel<D>(a, 2+c, -1, -1, 0))
@@ -274,13 +303,23 @@ namespace spb
             }
             if (VISC)
             {
-                double tDD = fma(P.two_mu, g[D][D], P.beta*div);
-                double tD1 = P.mu*(g[D][T1] + g[T1][D]);
-                double tD2 = P.mu*(g[D][T2] + g[T2][D]);
+                double mu = P.mu, two_mu = P.two_mu, beta = P.beta, kappa = P.kappa;
+                if (SGS)
+                {
+                    // viscous_laws::sgs_visc_t::get_all (viscous_laws.h:185-196) with the face value of the density
+                    const double rho_f = 0.5*(qL[0] + qR[0])*rcp_nr(P.R*(0.5*(qL[1] + qR[1])));
+                    const double mu_t = wale_mu_t(P, rho_f, g);
+                    mu += mu_t; two_mu = 2.0*mu;
+                    beta = fma(-0.66666666667, mu_t, beta);
+                    kappa = fma(P.sgs_cp_prt, mu_t, kappa);
+                }
+                double tDD = fma(two_mu, g[D][D], beta*div);
+                double tD1 = mu*(g[D][T1] + g[T1][D]);
+                double tD2 = mu*(g[D][T2] + g[T2][D]);
                 const double ufD = 0.5*(qL[2+D]  + qR[2+D]);
                 const double uf1 = 0.5*(qL[2+T1] + qR[2+T1]);
                 const double uf2 = 0.5*(qL[2+T2] + qR[2+T2]);
-                double h = fma(ufD, tDD, fma(uf1, tD1, fma(uf2, tD2, P.kappa*gT)));
+                double h = fma(ufD, tDD, fma(uf1, tD1, fma(uf2, tD2, kappa*gT)));
                 if (CURV) { h *= area; tDD *= area; tD1 *= area; tD2 *= area; }      // -(n . tau), n = area e_D (viscous.h:70-74)
                 F[1]    -= h;
                 F[2+D]  -= tDD;

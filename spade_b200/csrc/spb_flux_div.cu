@@ -22,6 +22,8 @@ extern "C"
         if (lb_begin < 0 || lb_end > g->nlb || lb_begin > lb_end) { set_error("spb_flux_div: bad block range"); return SPB_ERR_BAD_ARG; }
         const FluxParams P = make_params(f);
         cudaStream_t st = (cudaStream_t)stream;
+        if (f->sgs == SPB_SGS_WALE) return flux_div_sgs(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr);
+        if (f->sgs != SPB_SGS_NONE) { set_error("spb_flux_div: unknown SGS model"); return SPB_ERR_BAD_ARG; }
         if (g->metric_dev) return flux_div_curv(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr);
 #define SPB_CASE(C, D, V) if (f->conv == C && f->diss == D && (f->visc != 0) == (V != 0)) \
             return launch_fdiv<C, D, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st)
@@ -62,9 +64,11 @@ extern "C"
         S.cq_self = sd->cq_self; S.co_self = sd->co_self;
         S.gm1 = f->gamma - 1.0; S.inv_gm1 = 1.0/(f->gamma - 1.0); S.inv_R = 1.0/f->R;
         cudaStream_t st = (cudaStream_t)stream;
-        if (g->metric_dev)
+        if (f->sgs != SPB_SGS_NONE && f->sgs != SPB_SGS_WALE) { set_error("spb_flux_div_rk_stage: unknown SGS model"); return SPB_ERR_BAD_ARG; }
+        if (g->metric_dev || f->sgs == SPB_SGS_WALE)
         {
-            if (exch) { set_error("spb_flux_div_rk_stage_exchange: ghost fusion is implemented for identity coordinates (use spb_flux_div_rk_stage + spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
+            if (exch) { set_error("spb_flux_div_rk_stage_exchange: ghost fusion is implemented for identity coordinates without an SGS model (use spb_flux_div_rk_stage + spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
+            if (f->sgs == SPB_SGS_WALE) return flux_div_sgs(g, q_in, sd->out, f, P, 0, lb_begin, lb_end, st, q_out, &S);
             return flux_div_curv(g, q_in, sd->out, f, P, 0, lb_begin, lb_end, st, q_out, &S);
         }
 #define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \

@@ -64,7 +64,7 @@ namespace spb
     // `met` holds, per block and direction, three rows of length G.lm (spb_grid_set_metric): row 0 = m as info::metric
     // evaluates it at the cell centres, row 1 = 1/m at the computational cell centres (Jacobian, tangential gradient
     // transform), row 2 = 1/m at the faces (normal gradient transform); index = padded cell / face index.
-    template <int CONV, int DISS, int VISC, bool FUSED, bool CURV = false>
+    template <int CONV, int DISS, int VISC, bool FUSED, bool CURV = false, bool SGS = false>
     __global__ void __launch_bounds__(NTHREADS, 2)
     flux_div_kernel(const __grid_constant__ CUtensorMap tmap_q, double* __restrict__ rhs, const FluxParams P,
                     const FdivDims G, const double* __restrict__ inv_dx_tab, double* __restrict__ q_out, const StageParams ST,
@@ -178,10 +178,10 @@ namespace spb
                 {
                     double gs[3], area;
                     face_metric(DZ, ipc, jpc, k + G.ng[2], gs, area);
-                    face_flux<CONV, DISS, VISC, 2, true>(acc, P, gs, Fz, area);
+                    face_flux<CONV, DISS, VISC, 2, true, SGS>(acc, P, gs, Fz, area);
                     if (k >= 1) jac_prev = M(0, 1, ipc)*M(1, 1, jpc)*M(2, 1, k - 1 + G.ng[2]);
                 }
-                else face_flux<CONV, DISS, VISC, 2>(acc, P, invdx, Fz);
+                else face_flux<CONV, DISS, VISC, 2, false, SGS>(acc, P, invdx, Fz);
             }
 
             if (k >= 1 && active)
@@ -247,12 +247,12 @@ namespace spb
                 if (active)
                 {
                     double F[5], gs[3], area;
-                    if (CURV) { face_metric(DX, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true>(acc, P, gs, F, area); }
-                    else face_flux<CONV, DISS, VISC, 0>(acc, P, invdx, F);
+                    if (CURV) { face_metric(DX, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true, SGS>(acc, P, gs, F, area); }
+                    else face_flux<CONV, DISS, VISC, 0, false, SGS>(acc, P, invdx, F);
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) Fx[(jl*(TI + 1) + il)*5 + v] = F[v];
-                    if (CURV) { face_metric(DY, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true>(acc, P, gs, F, area); }
-                    else face_flux<CONV, DISS, VISC, 1>(acc, P, invdx, F);
+                    if (CURV) { face_metric(DY, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true, SGS>(acc, P, gs, F, area); }
+                    else face_flux<CONV, DISS, VISC, 1, false, SGS>(acc, P, invdx, F);
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) Fy[(jl*TI + il)*5 + v] = F[v];
                 }
@@ -262,8 +262,8 @@ namespace spb
                     TileAcc<H> e = acc;
                     e.cell = ((tid + H)*S::TIp + (ni_t + H + ash))*5;
                     double F[5], gs[3], area;
-                    if (CURV) { face_metric(DX, i0 + ni_t + G.ng[0], j0 + tid + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true>(e, P, gs, F, area); }
-                    else face_flux<CONV, DISS, VISC, 0>(e, P, invdx, F);
+                    if (CURV) { face_metric(DX, i0 + ni_t + G.ng[0], j0 + tid + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true, SGS>(e, P, gs, F, area); }
+                    else face_flux<CONV, DISS, VISC, 0, false, SGS>(e, P, invdx, F);
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) Fx[(tid*(TI + 1) + ni_t)*5 + v] = F[v];
                 }
@@ -272,8 +272,8 @@ namespace spb
                     TileAcc<H> e = acc;
                     e.cell = ((nj_t + H)*S::TIp + (tid - 32 + H + ash))*5;
                     double F[5], gs[3], area;
-                    if (CURV) { face_metric(DY, i0 + tid - 32 + G.ng[0], j0 + nj_t + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true>(e, P, gs, F, area); }
-                    else face_flux<CONV, DISS, VISC, 1>(e, P, invdx, F);
+                    if (CURV) { face_metric(DY, i0 + tid - 32 + G.ng[0], j0 + nj_t + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true, SGS>(e, P, gs, F, area); }
+                    else face_flux<CONV, DISS, VISC, 1, false, SGS>(e, P, invdx, F);
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) Fy[(nj_t*TI + (tid - 32))*5 + v] = F[v];
                 }
@@ -306,7 +306,7 @@ namespace spb
         }
     }
 
-    template <int CONV, int DISS, int VISC, bool FUSED = false, bool CURV = false>
+    template <int CONV, int DISS, int VISC, bool FUSED = false, bool CURV = false, bool SGS = false>
     static int launch_fdiv(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
                            int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out = nullptr, const StageParams* stage = nullptr)
     {
@@ -340,7 +340,7 @@ namespace spb
         if (CURV && !g->metric_dev) { set_error("spb_flux_div: general-coordinate kernel without a metric (spb_grid_set_metric)"); return SPB_ERR_BAD_ARG; }
         const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
         if (nblk <= 0) return 0;
-        auto kern = flux_div_kernel<CONV, DISS, VISC, FUSED, CURV>;
+        auto kern = flux_div_kernel<CONV, DISS, VISC, FUSED, CURV, SGS>;
         StageParams SP{};
         if (stage) SP = *stage;
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
@@ -357,9 +357,15 @@ namespace spb
         // reference viscous.h:64-68: cond = (gamma R/(gamma-1)) * (mu * prandtl_inv)
         P.kappa = (f->gamma*f->R/(f->gamma - 1.0))*(f->mu*f->prandtl_inv);
         P.eps = f->sensor_eps; P.blend = f->blend;
+        // wale_t (subgrid_scale.h:86-89): mu_t = rho cw cw delta delta (...); sgs_visc_t: alpha += mu_t/Pr_t (viscous_laws.h:192-195)
+        P.sgs_c = f->sgs_cw*f->sgs_cw*f->sgs_delta*f->sgs_delta;
+        P.sgs_cp_prt = f->sgs ? (f->gamma*f->R/(f->gamma - 1.0))/f->sgs_prt : 0.0;
         return P;
     }
 
+    // LES closure visc_lr<sgs_visc_t<constant_viscosity_t, wale_t>> (spb_flux_div_sgs.cu): identity and general coordinates
+    int flux_div_sgs(const spb_grid* g, const double* q, double* rhs, const spb_flux_desc* f, const FluxParams& P, int increment,
+                     int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage);
     // general coordinates (spb_flux_div_curv.cu): every functor combination through the wide kernel with CURV = true
     int flux_div_curv(const spb_grid* g, const double* q, double* rhs, const spb_flux_desc* f, const FluxParams& P, int increment,
                       int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage);

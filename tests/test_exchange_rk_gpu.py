@@ -115,13 +115,13 @@ def test_rk_trajectory_matches_oracle(integ):
 
 
 @pytest.mark.parametrize("integ", [0, 2, 3])
-@pytest.mark.parametrize("scheme", [0, 3, 4, 1, 2, 6])
+@pytest.mark.parametrize("scheme", [0, 3, 4, 1, 2, 6, 11, 12])
 def test_fused_stage_kernel_trajectory_matches_oracle(integ, scheme):
     """flux_div + RK stage update in one kernel (spb_flux_div_rk_stage), rk4 (with the pre-combined final update),
     ssprk3 (odd number of stages: result ends in the second buffer) and rk2; blocks that are not multiples of the tile."""
     from oracle import port
     nb, n, ng = (2, 1, 2), (40, 12, 8), 2
-    q0 = make_state(nb, n, ng, seed=23, jump=scheme in (1, 6))
+    q0 = make_state(nb, n, ng, seed=23, jump=scheme in (1, 6, 12))
     cfg = oracle_cfg(nb, n, ng, scheme=scheme, integrator=integ)
     q0 = port.exchange(cfg, q0.ravel()).reshape(q0.shape)
     dt = 0.2 * (2 * np.pi / 80) / port.reduce_umax(cfg, q0.ravel())

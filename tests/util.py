@@ -73,6 +73,9 @@ def rel_l2(a, b):
 
 
 # scheme id of oracle (spo_cfg.scheme) -> constructor of the product-side functor
+SGS = (0.55, 0.4, 0.9)      # wale_t(gas, cw, delta, prt) of schemes 11, 12
+
+
 def product_flux(scheme, gamma=GAMMA, R=RGAS, mu=1e-2, prandtl=0.72, eps=1e-2):
     import spade_b200.api as sp
     gas = sp.ideal_gas_t(gamma, R)
@@ -88,6 +91,8 @@ def product_flux(scheme, gamma=GAMMA, R=RGAS, mu=1e-2, prandtl=0.72, eps=1e-2):
             6: lambda: sp.compose(sp.hybrid_scheme_t(ck4, w, du, sp.full_flux), v),
             7: lambda: ck4,
             8: lambda: sp.compose(sp.hybrid_scheme_t(t, w, du, sp.diss_flux), v),
+            11: lambda: sp.compose(t, sp.visc_lr(sp.sgs_visc_t(vl, sp.wale_t(gas, *SGS)), gas)),
+            12: lambda: sp.compose(sp.hybrid_scheme_t(t, w, du, sp.full_flux), sp.visc_lr(sp.sgs_visc_t(vl, sp.wale_t(gas, *SGS)), gas)),
             9: lambda: sp.weno_t(sp.rusanov_t(gas)),
             10: lambda: sp.compose(sp.hybrid_scheme_t(t, sp.weno_t(sp.rusanov_t(gas)), du, sp.full_flux), v)}[scheme]()
 
@@ -96,7 +101,7 @@ def oracle_cfg(nb, n, ng=2, scheme=0, mu=1e-2, prandtl=0.72, eps=1e-2, periodic=
                bounds=None):
     from oracle import ref
     return ref.make_cfg(nb, n, ng, bounds=bounds, periodic=periodic, scheme=scheme, gamma=GAMMA, R=RGAS, mu=mu,
-                        prandtl=prandtl, sensor_eps=eps, nranks=nranks, integrator=integrator)
+                        prandtl=prandtl, sensor_eps=eps, nranks=nranks, integrator=integrator, sgs=SGS)
 
 
 def product_setup(nb, n, ng=2, bounds=None, rank=0, size=1):
