@@ -49,7 +49,8 @@ enum {
  *   visc: viscous::visc_lr with viscous_laws::constant_viscosity_t, reference viscous.h:14-113 */
 enum { SPB_CONV_NONE = 0, SPB_CONV_TOTANI = 1 /* totani_lr, convective.h:54-94 */,
        SPB_CONV_CENT_KEEP4 = 2 /* cent_keep<4>, convective.h:97-192 */,
-       SPB_CONV_FWENO = 3 /* fweno_t alone, convective.h:336-497 */ };
+       SPB_CONV_FWENO = 3 /* fweno_t alone, convective.h:336-497 */,
+       SPB_CONV_CENT_KEEP6 = 4, SPB_CONV_CENT_KEEP8 = 5 /* cent_keep<6>, cent_keep<8>: 3 / 4 exchange cells, no hybrid */ };
 enum { SPB_DISS_NONE = 0, SPB_DISS_FWENO = 1 /* hybrid_scheme_t(conv, fweno_t, ducros_t, tag) */ };
 enum { SPB_BLEND_FULL_FLUX = 0 /* (1-a)F0 + a F1 */, SPB_BLEND_DISS_FLUX = 1 /* F0 + a F1 */ };
 /* LES closure of visc_lr: viscous_laws::sgs_visc_t(constant_viscosity_t, subgrid_scale::wale_t(gas, cw, delta, prt)),

@@ -46,15 +46,16 @@ namespace spade::b200
     template <typename F> inline void fill(spb_flux_desc&, const F&)
     {
         static_assert(always_false<F>::value, "spade_b200: this flux functor type is not in the implemented set "
-            "(totani_lr, cent_keep<2|4>, fweno_t, weno_t<rusanov_t>, hybrid_scheme_t<central, fweno_t | weno_t<rusanov_t>, ducros_t>, visc_lr<constant_viscosity_t | sgs_visc_t<constant_viscosity_t, wale_t>>, omni::compose of those); "
+            "(totani_lr, cent_keep<2|4|6|8>, fweno_t, weno_t<rusanov_t>, hybrid_scheme_t<central, fweno_t | weno_t<rusanov_t>, ducros_t>, visc_lr<constant_viscosity_t | sgs_visc_t<constant_viscosity_t, wale_t>>, omni::compose of those); "
             "there is no CPU fallback");
     }
     template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::totani_lr<gas_t>& f)
     { d.conv = SPB_CONV_TOTANI; fill_gas(d, f.gas); }
     template <typename gas_t, int order> inline void fill(spb_flux_desc& d, const convective::cent_keep_scheme_t<gas_t, order>& f)
     {
-        static_assert(order == 2 || order == 4, "spade_b200: cent_keep orders 2 and 4 (two exchange cells)");
-        d.conv = (order == 2) ? SPB_CONV_TOTANI : SPB_CONV_CENT_KEEP4; fill_gas(d, f.gas);
+        static_assert(order == 2 || order == 4 || order == 6 || order == 8, "spade_b200: cent_keep orders 2, 4, 6, 8");
+        d.conv = (order == 2) ? SPB_CONV_TOTANI : (order == 4) ? SPB_CONV_CENT_KEEP4 : (order == 6) ? SPB_CONV_CENT_KEEP6 : SPB_CONV_CENT_KEEP8;
+        fill_gas(d, f.gas);
     }
     template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::fweno_t<gas_t, convective::enable_smooth>& f)
     { d.conv = SPB_CONV_FWENO; fill_gas(d, f.gas); }

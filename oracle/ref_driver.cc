@@ -160,6 +160,10 @@ namespace
                 func(spade::omni::compose(hyb, vscheme));
                 break;
             }
+            case 13: { func(spade::omni::compose(spade::convective::cent_keep<6>(air), vscheme)); break; }
+            case 14: { func(spade::omni::compose(spade::convective::cent_keep<8>(air), vscheme)); break; }
+            case 15: { func(spade::convective::cent_keep<6>(air)); break; }
+            case 16: { func(spade::convective::cent_keep<8>(air)); break; }
             case 11:
             {
                 // LES closure: visc_lr over sgs_visc_t(constant_viscosity_t, wale_t) (viscous_laws.h:175-216, subgrid_scale.h:25-91)

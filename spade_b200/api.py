@@ -26,7 +26,7 @@ from ._lib import BcDesc, FluxDesc, SourceDesc, SpbError, StageDesc, check, int3
 NVAR = 5
 
 # ---- enums of include/spade_b200.h ---------------------------------------------------------------
-CONV_NONE, CONV_TOTANI, CONV_CENT_KEEP4, CONV_FWENO = 0, 1, 2, 3
+CONV_NONE, CONV_TOTANI, CONV_CENT_KEEP4, CONV_FWENO, CONV_CENT_KEEP6, CONV_CENT_KEEP8 = 0, 1, 2, 3, 4, 5
 DISS_NONE, DISS_FWENO = 0, 1
 BLEND_FULL_FLUX, BLEND_DISS_FLUX = 0, 1
 RED_MAX, RED_SUM = 0, 1
@@ -394,15 +394,16 @@ class totani_lr(_functor):
 
 
 class cent_keep(_functor):
-    """convective::cent_keep<order>(gas), convective.h:97-192; order 2 == totani_lr arithmetic."""
+    """convective::cent_keep<order>(gas), convective.h:97-192; order 2 == totani_lr arithmetic; orders 6 and 8 need 3 and 4
+    exchange cells."""
 
     def __init__(self, order, gas):
-        if order not in (2, 4):
-            raise SpbError("cent_keep: only orders 2 and 4 fit two exchange cells")
+        if order not in (2, 4, 6, 8):
+            raise SpbError("cent_keep: orders 2, 4, 6, 8 (convective.h:100)")
         self.order, self.gas = order, gas
 
     def _fill(self, d):
-        d.conv = CONV_TOTANI if self.order == 2 else CONV_CENT_KEEP4
+        d.conv = {2: CONV_TOTANI, 4: CONV_CENT_KEEP4, 6: CONV_CENT_KEEP6, 8: CONV_CENT_KEEP8}[self.order]
         d.gamma, d.R = self.gas.gamma, self.gas.R
 
 
@@ -449,7 +450,8 @@ class hybrid_scheme_t(_functor):
     """convective::hybrid_scheme_t(scheme0, scheme1, blender, tag), hybrid_scheme.h:15-47"""
 
     def __init__(self, scheme0, scheme1, blender, tag=full_flux):
-        if not isinstance(scheme1, fweno_t) or not isinstance(blender, ducros_t) or isinstance(scheme0, fweno_t):
+        if (not isinstance(scheme1, fweno_t) or not isinstance(blender, ducros_t) or isinstance(scheme0, fweno_t)
+                or (isinstance(scheme0, cent_keep) and scheme0.order > 4)):
             raise SpbError("hybrid_scheme_t: implemented for (totani_lr|cent_keep, fweno_t, ducros_t)")
         self.scheme0, self.scheme1, self.blender, self.tag = scheme0, scheme1, blender, tag
 
@@ -944,7 +946,7 @@ class integrator_t:
         if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
             f = rhs_calc.flux
             narrow = f.diss == DISS_NONE and f.conv in (CONV_NONE, CONV_TOTANI) and (f.conv != CONV_NONE or f.visc)
-            wide = bool(f.visc) and ((f.conv == CONV_TOTANI and f.diss == DISS_FWENO) or f.conv == CONV_CENT_KEEP4)
+            wide = bool(f.visc) and ((f.conv == CONV_TOTANI and f.diss == DISS_FWENO) or f.conv in (CONV_CENT_KEEP4, CONV_CENT_KEEP6, CONV_CENT_KEEP8))
             if f.sgs:                      # the WALE closure rides on the wide kernel for every functor set it supports
                 narrow, wide = False, bool(f.visc) and f.conv in (CONV_NONE, CONV_TOTANI, CONV_CENT_KEEP4)
             if narrow or wide:

@@ -140,6 +140,46 @@ namespace spb
         F[2+D] = fma(2.0, g, F[2+D]);
     }
 
+    // ---- convective::cent_keep<ORDER>, ORDER = 6, 8 (convective.h:118-184): cells c[0 .. ORDER-1] at half-offsets
+    // -(ORDER-1), ..., +(ORDER-1); coefficients core/finite_diff.h:26-34
+    template <int IDX, int ORDER> struct cfd_coeff
+    {
+        static constexpr double fact(int n) { double f = 1.0; for (int i = 2; i <= n; ++i) f *= i; return f; }
+        static constexpr int h = ORDER/2;
+        static constexpr double value = (fact(h)/fact(h + IDX))*(fact(h)/fact(h - IDX))*(((1 + IDX) % 2 == 0) ? 1.0 : -1.0)/double(IDX);
+    };
+    template <int D, int ORDER>
+    __device__ __forceinline__ void flux_cent_keep_wide(const FluxParams& P, const double (&q)[ORDER][5], double (&F)[5])
+    {
+        constexpr int HW = ORDER/2;
+        double rho[ORDER], eng[ORDER];
+        #pragma unroll
+        for (int i = 0; i < ORDER; ++i) { rho[i] = q[i][0]*rcp_nr(P.R*q[i][1]); eng[i] = P.cv*q[i][1]; }
+        double cc = 0.0, m[3] = {0.0, 0.0, 0.0}, g = 0.0, k = 0.0, ie = 0.0, pd = 0.0;
+        auto pair = [&](const double a, const int i0, const int i1)
+        {
+            const double c_loc = a*0.25*(rho[i0] + rho[i1])*(q[i0][2+D] + q[i1][2+D]);
+            cc += c_loc;
+            #pragma unroll
+            for (int d = 0; d < 3; ++d) m[d] = fma(c_loc, 0.5*(q[i0][2+d] + q[i1][2+d]), m[d]);
+            g  = fma(a, 0.5*(q[i0][0] + q[i1][0]), g);
+            k  = fma(0.5*c_loc, fma(q[i0][2], q[i1][2], fma(q[i0][3], q[i1][3], q[i0][4]*q[i1][4])), k);
+            ie = fma(c_loc, 0.5*(eng[i0] + eng[i1]), ie);
+            pd = fma(a, 0.5*fma(q[i0][2+D], q[i1][0], q[i1][2+D]*q[i0][0]), pd);
+        };
+        // the reference's order: ii = 1 .. HW, jj = 0 .. ii-1, i0 = HW-1-jj, i1 = i0 + ii
+        const double coef[5] = {0.0, cfd_coeff<1, ORDER>::value, cfd_coeff<2, ORDER>::value, cfd_coeff<3, ORDER>::value,
+                                ORDER >= 8 ? cfd_coeff<(ORDER >= 8 ? 4 : 1), ORDER>::value : 0.0};
+        #pragma unroll
+        for (int ii = 1; ii <= HW; ++ii)
+            #pragma unroll
+            for (int jj = 0; jj < ii; ++jj) pair(coef[ii], HW - 1 - jj, HW - 1 - jj + ii);
+        F[0] = 2.0*cc;
+        F[1] = 2.0*(k + ie + pd);
+        F[2] = 2.0*m[0]; F[3] = 2.0*m[1]; F[4] = 2.0*m[2];
+        F[2+D] = fma(2.0, g, F[2+D]);
+    }
+
     // ---- convective::fweno_t ---------------------------------------------------------------------
     __device__ __forceinline__ double fweno_apply(const double (&f)[4], const double (&d)[4])
     {
@@ -258,7 +298,17 @@ namespace spb
         if (CONV == SPB_CONV_TOTANI)     flux_totani<D>(P, qL, qR, F);
         if (CONV == SPB_CONV_CENT_KEEP4) flux_cent_keep4<D>(P, qLL, qL, qR, qRR, F);
         if (CONV == SPB_CONV_FWENO)      flux_fweno<D, CURV>(P, qLL, qL, qR, qRR, F, area);
-        if (CURV && (CONV == SPB_CONV_TOTANI || CONV == SPB_CONV_CENT_KEEP4))
+        if (CONV == SPB_CONV_CENT_KEEP6 || CONV == SPB_CONV_CENT_KEEP8)
+        {
+            constexpr int ORDER = (CONV == SPB_CONV_CENT_KEEP6) ? 6 : 8;
+            double qw[ORDER][5];
+            #pragma unroll
+            for (int s = 0; s < ORDER; ++s)
+                #pragma unroll
+                for (int v = 0; v < 5; ++v) qw[s][v] = qrel<D>(a, v, s - ORDER/2, 0, 0);
+            flux_cent_keep_wide<D, ORDER>(P, qw, F);
+        }
+        if (CURV && (CONV == SPB_CONV_TOTANI || CONV == SPB_CONV_CENT_KEEP4 || CONV == SPB_CONV_CENT_KEEP6 || CONV == SPB_CONV_CENT_KEEP8))
         {
             // both are linear in the metric vector (convective.h:76-91, 128-182)
             #pragma unroll
@@ -331,6 +381,7 @@ namespace spb
 
     template <int CONV, int DISS> struct stencil_halo
     {
-        static constexpr int value = ((CONV == SPB_CONV_CENT_KEEP4) || (CONV == SPB_CONV_FWENO) || (DISS != SPB_DISS_NONE)) ? 2 : 1;
+        static constexpr int value = (CONV == SPB_CONV_CENT_KEEP8) ? 4 : (CONV == SPB_CONV_CENT_KEEP6) ? 3
+            : ((CONV == SPB_CONV_CENT_KEEP4) || (CONV == SPB_CONV_FWENO) || (DISS != SPB_DISS_NONE)) ? 2 : 1;
     };
 }

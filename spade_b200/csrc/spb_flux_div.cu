@@ -39,6 +39,10 @@ extern "C"
         SPB_CASE(SPB_CONV_CENT_KEEP4, SPB_DISS_NONE,  0);
         SPB_CASE(SPB_CONV_FWENO,      SPB_DISS_NONE,  0);
         SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_FWENO, 0);
+        SPB_CASE(SPB_CONV_CENT_KEEP6, SPB_DISS_NONE,  1);
+        SPB_CASE(SPB_CONV_CENT_KEEP6, SPB_DISS_NONE,  0);
+        SPB_CASE(SPB_CONV_CENT_KEEP8, SPB_DISS_NONE,  1);
+        SPB_CASE(SPB_CONV_CENT_KEEP8, SPB_DISS_NONE,  0);
 #undef SPB_CASE
         set_error("spb_flux_div: this combination of flux functors is not in the implemented set");
         return SPB_ERR_UNSUPPORTED;
@@ -84,6 +88,8 @@ extern "C"
         SPB_WIDE(SPB_CONV_TOTANI,     SPB_DISS_FWENO);
         SPB_WIDE(SPB_CONV_CENT_KEEP4, SPB_DISS_NONE);
         SPB_WIDE(SPB_CONV_CENT_KEEP4, SPB_DISS_FWENO);
+        SPB_WIDE(SPB_CONV_CENT_KEEP6, SPB_DISS_NONE);
+        SPB_WIDE(SPB_CONV_CENT_KEEP8, SPB_DISS_NONE);
 #undef SPB_WIDE
         set_error("spb_flux_div_rk_stage: the fused stage is implemented for totani_lr and/or visc_lr, and for the hybrid / cent_keep<4> schemes with visc_lr");
         return SPB_ERR_UNSUPPORTED;

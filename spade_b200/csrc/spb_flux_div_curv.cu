@@ -21,6 +21,8 @@ namespace spb
         SPB_CASE(SPB_CONV_CENT_KEEP4, SPB_DISS_NONE,  0);
         SPB_CASE(SPB_CONV_FWENO,      SPB_DISS_NONE,  0);
         SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_FWENO, 0);
+        SPB_CASE(SPB_CONV_CENT_KEEP6, SPB_DISS_NONE,  1);
+        SPB_CASE(SPB_CONV_CENT_KEEP8, SPB_DISS_NONE,  1);
 #undef SPB_CASE
         set_error("spb_flux_div: this combination of flux functors is not in the implemented set");
         return SPB_ERR_UNSUPPORTED;

@@ -17,8 +17,6 @@
 namespace spb
 {
     constexpr int TI = 32;
-    constexpr int TJ = 8;
-    constexpr int NTHREADS = TI*TJ;
 
     struct FdivDims
     {
@@ -34,8 +32,13 @@ namespace spb
     {
         // +2: fp64 TMA boxes must start on a 16-byte boundary (measured on B200: an odd first coordinate raises
         // an illegal-instruction fault), so the box starts one cell early when the halo start is an odd cell
+        static constexpr int TJ = (H >= 4) ? 4 : 8;                      // tile rows: 9 ring planes of an 8-row tile with 4 halo cells exceed 227 KB
+        static constexpr int NT = TI*TJ;                                  // threads per CTA
         static constexpr int TIp = TI + 2*H + 2, TJp = TJ + 2*H;
-        static constexpr int NP = H + 3;                                  // ring slots
+        // Step k reads planes k-H .. k+AH-H: the z-face of a 2H-cell stencil reaches H-1 planes up (AH = 2H-1), the tangential
+        // differences of the x/y faces one plane up (AH = H+1). One more plane is in flight: NP = AH + 2 ring slots.
+        static constexpr int AH = (H + 1 > 2*H - 1) ? H + 1 : 2*H - 1;
+        static constexpr int NP = AH + 2;
         static constexpr int PLANE_DOUBLES = TIp*TJp*5;
         static constexpr int PLANE_BYTES = PLANE_DOUBLES*8;
         static constexpr int PLANE_STRIDE_BYTES = (PLANE_BYTES + 127)/128*128;
@@ -50,10 +53,10 @@ namespace spb
     {
         const double* ring;
         int cell;          // ((jl+H)*TIp + (il+H))*5
-        int pl[4];         // plane offsets (doubles) for dk = -2, -1, 0, +1
+        int pl[FdivSmem<H>::AH + 1];      // plane offsets (doubles) for dk = -H .. AH-H
         __device__ __forceinline__ double operator()(int v, int di, int dj, int dk) const
         {
-            return ring[pl[dk + 2] + cell + (dj*FdivSmem<H>::TIp + di)*5 + v];
+            return ring[pl[dk + H] + cell + (dj*FdivSmem<H>::TIp + di)*5 + v];
         }
     };
 
@@ -65,13 +68,14 @@ namespace spb
     // evaluates it at the cell centres, row 1 = 1/m at the computational cell centres (Jacobian, tangential gradient
     // transform), row 2 = 1/m at the faces (normal gradient transform); index = padded cell / face index.
     template <int CONV, int DISS, int VISC, bool FUSED, bool CURV = false, bool SGS = false>
-    __global__ void __launch_bounds__(NTHREADS, 2)
+    __global__ void __launch_bounds__(FdivSmem<stencil_halo<CONV, DISS>::value>::NT, 2)
     flux_div_kernel(const __grid_constant__ CUtensorMap tmap_q, double* __restrict__ rhs, const FluxParams P,
                     const FdivDims G, const double* __restrict__ inv_dx_tab, double* __restrict__ q_out, const StageParams ST,
                     const double* __restrict__ met)
     {
         constexpr int H = stencil_halo<CONV, DISS>::value;
         using S = FdivSmem<H>;
+        constexpr int TJ = S::TJ, AH = S::AH;
         extern __shared__ __align__(128) double smem_raw[];
         // pointer arithmetic on the __shared__ symbol (no integer round trip) keeps the address space known
         // to the compiler: LDS/STS instead of generic LD/ST
@@ -144,15 +148,15 @@ namespace spb
         acc.ring = ring;
         acc.cell = ((jl + H)*S::TIp + (il + H + ash))*5;
 
-        // planes p = 0 .. H are needed by step 0 besides plane H+1
+        // planes p = 0 .. AH-1 are needed by step 0 besides plane AH
         uint32_t parity_bits = 0;                      // bit s = parity to wait for on slot s
         #pragma unroll
-        for (int p = 0; p <= H; ++p) { mbar_wait(&bars[p], 0); }
-        parity_bits = (1u << (H + 1)) - 1;             // slots 0..H consumed once
-        int slot_next = H + 1;                         // slot of plane k+1 at step k
-        // plane offsets for dk = -2..+1 at step k=0: plane p = k + H + dk
+        for (int p = 0; p < AH; ++p) { mbar_wait(&bars[p], 0); }
+        parity_bits = (1u << AH) - 1;                  // slots 0..AH-1 consumed once
+        int slot_next = AH;                            // slot of plane k+AH at step k
+        // plane offsets for dk = -H .. AH-H at step k=0: plane p = k + H + dk
         #pragma unroll
-        for (int d = 0; d < 4; ++d) { const int p = H + (d - 2); acc.pl[d] = (p >= 0 ? p : 0)*S::PLANE_STRIDE; }
+        for (int d = 0; d < AH; ++d) acc.pl[d] = d*S::PLANE_STRIDE;
 
         double rprev[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // partial rhs of cell k-1 (x, y and lower-z parts)
         const long long col0 = lb*G.block_stride
@@ -162,13 +166,13 @@ namespace spb
 
         for (int k = 0; k <= nz; ++k)
         {
-            // plane k+1
-            if (k + 1 + H < nplanes)
+            // plane k + AH
+            if (k + AH < nplanes)
             {
                 mbar_wait(&bars[slot_next], (parity_bits >> slot_next) & 1u);
                 parity_bits ^= (1u << slot_next);
             }
-            acc.pl[3] = slot_next*S::PLANE_STRIDE;
+            acc.pl[AH] = slot_next*S::PLANE_STRIDE;
 
             double Fz[5];
             double jac_prev = 1.0;                   // Jacobian of cell k-1
@@ -290,7 +294,7 @@ namespace spb
                 }
             }
             __syncthreads();
-            // slot of plane p = k (dk = -H) is free now: refill it with plane k + H + 3 = p + NP
+            // slot of plane p = k (dk = -H) is free now: refill it with plane p + NP
             if (tid == 0)
             {
                 const int pnew = k + S::NP;
@@ -301,7 +305,8 @@ namespace spb
                     tma_load_4d(ring + s*S::PLANE_STRIDE, &tmap_q, &bars[s], c0, c1, c2base + pnew, (int)lb);
                 }
             }
-            acc.pl[0] = acc.pl[1]; acc.pl[1] = acc.pl[2]; acc.pl[2] = acc.pl[3];
+            #pragma unroll
+            for (int d = 0; d < AH; ++d) acc.pl[d] = acc.pl[d + 1];
             slot_next = (slot_next + 1 == S::NP) ? 0 : slot_next + 1;
         }
     }
@@ -314,7 +319,6 @@ namespace spb
         using S = FdivSmem<H>;
         for (int d = 0; d < 3; ++d)
             if (g->ng[d] < H) { set_error("spb_flux_div: scheme needs " + std::to_string(H) + " exchange cells"); return SPB_ERR_BAD_ARG; }
-        if (g->ng[2] < 2 && H == 2) { set_error("spb_flux_div: need 2 exchange cells"); return SPB_ERR_BAD_ARG; }
         if ((5*g->np[0]) % 2 != 0) { set_error("spb_flux_div: n0 + 2*g0 must be even (16-byte TMA row pitch)"); return SPB_ERR_UNSUPPORTED; }
         encode_tiled_fn enc = get_encode_tiled();
         if (!enc) { set_error("spb_flux_div: cuTensorMapEncodeTiled not available from the driver"); return SPB_ERR_DRIVER; }
@@ -332,7 +336,7 @@ namespace spb
         FdivDims G;
         for (int d = 0; d < 3; ++d) { G.nx[d] = g->nx[d]; G.ng[d] = g->ng[d]; G.np[d] = g->np[d]; }
         G.tiles_i = (g->nx[0] + TI - 1)/TI;
-        G.tiles_j = (g->nx[1] + TJ - 1)/TJ;
+        G.tiles_j = (g->nx[1] + S::TJ - 1)/S::TJ;
         G.block_stride = g->block_stride;
         G.lb0 = lb_begin;
         G.increment = increment;
@@ -344,7 +348,7 @@ namespace spb
         StageParams SP{};
         if (stage) SP = *stage;
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-        kern<<<(unsigned)nblk, NTHREADS, S::BYTES, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP, g->metric_dev);
+        kern<<<(unsigned)nblk, S::NT, S::BYTES, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP, g->metric_dev);
         SPB_LAUNCH_CHECK();
         return 0;
     }

@@ -94,3 +94,41 @@ def test_matches_reference_library_if_present(ref_lib):
         want = ref_lib.flux_div(cfg, q.ravel()).reshape(q.shape)
         got = run_product(nb, n, ng, q, scheme)
         assert rel_l2(got, want) < TOL
+
+
+@pytest.mark.parametrize("scheme,ng", [(13, 3), (14, 4), (15, 3), (16, 4), (13, 4), (0, 3), (1, 4)])
+@pytest.mark.parametrize("n", [(32, 16, 8), (40, 12, 6)])
+def test_cent_keep_6_8_and_deeper_exchange_layers(scheme, ng, n):
+    """cent_keep<6> / cent_keep<8> (convective.h:97-192; 3 / 4 exchange cells, 6- / 8-cell stencils, 7 / 9 staged planes), and the
+    two-cell schemes on arrays that carry more exchange cells than they need."""
+    from oracle import port
+    nb = (2, 1, 2)
+    q = make_state(nb, n, ng, seed=scheme, jump=scheme == 1)
+    cfg = oracle_cfg(nb, n, ng, scheme=scheme)
+    want = port.flux_div(cfg, q.ravel()).reshape(q.shape)
+    got = run_product(nb, n, ng, q, scheme)
+    assert rel_l2(got, want) < TOL
+
+
+@pytest.mark.parametrize("scheme,ng", [(13, 3), (14, 4)])
+def test_cent_keep_6_8_rk4_trajectory(scheme, ng):
+    from oracle import port
+    from util import GAMMA, RGAS
+    nb, n = (2, 2, 1), (16, 8, 8)
+    cfg = oracle_cfg(nb, n, ng, scheme=scheme, integrator=0)
+    q0 = port.exchange(cfg, make_state(nb, n, ng, seed=5).ravel())
+    dt = 0.2 * (2 * np.pi / 32) / port.reduce_umax(cfg, q0)
+    want = port.advance(cfg, q0, dt, 2)
+    sp, blocks, grid = product_setup(nb, n, ng)
+    shape = (-1, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng, 5)
+    for fused in (True, False):
+        qa = sp.grid_array.from_host(grid, q0.reshape(shape), (ng,) * 3)
+        ra = sp.grid_array(grid, 0.0, (ng,) * 3)
+        ex = sp.make_exchange(qa, (1, 1, 1))
+        ti = sp.integrator_t(sp.time_axis_t(0.0, dt), sp.rk4_t, sp.integrator_data_t(qa, ra, sp.rk4_t),
+                             sp.flux_div_rhs_t(product_flux(scheme), sp.overwrite), sp.exchange_bc_t(ex),
+                             sp.state_transform_t(sp.ideal_gas_t(GAMMA, RGAS)), fused=fused)
+        assert (ti._plan is not None) == fused
+        ti.advance()
+        ti.advance()
+        assert rel_l2(ti.solution().to_host().ravel(), want) < TOL

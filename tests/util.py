@@ -93,6 +93,10 @@ def product_flux(scheme, gamma=GAMMA, R=RGAS, mu=1e-2, prandtl=0.72, eps=1e-2):
             8: lambda: sp.compose(sp.hybrid_scheme_t(t, w, du, sp.diss_flux), v),
             11: lambda: sp.compose(t, sp.visc_lr(sp.sgs_visc_t(vl, sp.wale_t(gas, *SGS)), gas)),
             12: lambda: sp.compose(sp.hybrid_scheme_t(t, w, du, sp.full_flux), sp.visc_lr(sp.sgs_visc_t(vl, sp.wale_t(gas, *SGS)), gas)),
+            13: lambda: sp.compose(sp.cent_keep(6, gas), v),
+            14: lambda: sp.compose(sp.cent_keep(8, gas), v),
+            15: lambda: sp.cent_keep(6, gas),
+            16: lambda: sp.cent_keep(8, gas),
             9: lambda: sp.weno_t(sp.rusanov_t(gas)),
             10: lambda: sp.compose(sp.hybrid_scheme_t(t, sp.weno_t(sp.rusanov_t(gas)), du, sp.full_flux), v)}[scheme]()
 
