@@ -19,6 +19,8 @@
 // (dispatch/execute.h:86-96).
 #pragma once
 #include <map>
+#include <mutex>
+#include <tuple>
 #include <tuple>
 #include <vector>
 #include <string>
@@ -177,20 +179,87 @@ namespace spade::b200
     }
 
     // ---------------------------------------------------------------- exchange
+    // In-process multi-GPU (the reference's own model: one host thread per GPU inside one process, compute_pool.h:497-514):
+    // every rank publishes the device pointers of its per-peer receive buffers in this process-wide table; a rank then packs
+    // its message for peer p STRAIGHT INTO p's receive buffer over NVLink (spb_exchange_pack_peer, peer access enabled once per
+    // thread) instead of the reference's pack -> cudaMemcpyPeer -> unpack (exchange_message.h:14-56, compute_pool.h:93-99).
+    struct peer_table_t
+    {
+        std::mutex mut;
+        std::map<std::tuple<int, int, int>, double*> recvbuf;      // (exchange id, owner rank, sending peer) -> buffer on the owner's GPU
+    };
+    inline peer_table_t& peer_table() { static peer_table_t t; return t; }
+
     template <typename array_t> struct arr_exchange_t
     {
         using grid_type = typename array_t::grid_type;
         spb_exchange* plan = nullptr;
-        int rank = 0, size = 1;
-        std::vector<double*> sendbuf, recvbuf;      // device buffers per peer (ranks of this process share an address space)
+        int rank = 0, size = 1, id = 0;
+        std::vector<double*> recvbuf;       // [peer]: messages from `peer` land here (this rank's GPU)
+        std::vector<double*> peerbuf;       // [peer]: where this rank's message for `peer` goes (peer's GPU), or a local staging buffer
+        std::vector<char>    direct;        // [peer]: peerbuf is peer memory (P2P) / a local send buffer the peer pulls from
+        std::vector<double*> stagebuf;      // [peer]: the sender-side staging buffer of `peer` when P2P is not available (pulled by us)
+        bool wired = false;
+
+        template <typename group_t> void wire(group_t& group)
+        {
+            recvbuf.assign(size, nullptr); peerbuf.assign(size, nullptr); direct.assign(size, 1); stagebuf.assign(size, nullptr);
+            auto& tab = peer_table();
+            const int mydev = group.device_id();
+            for (int p = 0; p < size; ++p)
+            {
+                if (p == rank) continue;
+                const int64_t nr = spb_exchange_recv_cells(plan, p), ns = spb_exchange_send_cells(plan, p);
+                if (nr > 0 && cudaMalloc((void**)&recvbuf[p], sizeof(double)*5*nr) != cudaSuccess) throw except::sp_exception("spade_b200: cudaMalloc of a receive buffer failed");
+                const int pdev = group.pid(p).device_id;
+                int can = 0;
+                if (pdev != mydev) cudaDeviceCanAccessPeer(&can, mydev, pdev); else can = 1;
+                if (pdev != mydev && can) { const cudaError_t e = cudaDeviceEnablePeerAccess(pdev, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0; cudaGetLastError(); }
+                direct[p] = char(can);
+                if (!can && ns > 0 && cudaMalloc((void**)&peerbuf[p], sizeof(double)*5*ns) != cudaSuccess) throw except::sp_exception("spade_b200: cudaMalloc of a send buffer failed");
+                std::lock_guard<std::mutex> lk(tab.mut);
+                tab.recvbuf[{id, rank, p}] = recvbuf[p];
+                if (!can) tab.recvbuf[{-1 - id, rank, p}] = peerbuf[p];          // staging buffers under the negated id
+            }
+            group.sync();
+            for (int p = 0; p < size; ++p)
+            {
+                if (p == rank) continue;
+                std::lock_guard<std::mutex> lk(tab.mut);
+                if (direct[p]) peerbuf[p] = tab.recvbuf[{id, p, rank}];
+                auto it = tab.recvbuf.find({-1 - id, p, rank});
+                if (it != tab.recvbuf.end()) stagebuf[p] = it->second;          // peer p cannot reach us: we pull from its staging buffer
+            }
+            group.sync();
+            wired = true;
+        }
+
+        // off-rank half of exchange() on a raw device buffer in the array's layout
+        template <typename group_t> void exchange_messages(double* q, group_t& group)
+        {
+            if (size == 1) return;
+            if (!wired) wire(group);
+            for (int p = 0; p < size; ++p)
+                if (p != rank && spb_exchange_send_cells(plan, p) > 0)
+                    check(direct[p] ? spb_exchange_pack_peer(plan, q, p, peerbuf[p], nullptr) : spb_exchange_pack(plan, q, p, peerbuf[p], nullptr), "spb_exchange_pack");
+            check(spb_sync(nullptr), "spb_sync");
+            group.sync();                                               // every message for this rank has been written
+            for (int p = 0; p < size; ++p)
+            {
+                if (p == rank || spb_exchange_recv_cells(plan, p) == 0) continue;
+                if (stagebuf[p])
+                    cudaMemcpyPeerAsync(recvbuf[p], group.device_id(), stagebuf[p], group.pid(p).device_id, sizeof(double)*5*spb_exchange_recv_cells(plan, p), nullptr);
+                check(spb_exchange_unpack(plan, q, p, recvbuf[p], nullptr), "spb_exchange_unpack");
+            }
+            check(spb_sync(nullptr), "spb_sync");
+            group.sync();                                               // buffers may be overwritten by the next exchange
+        }
 
         void exchange(array_t& array, typename grid_type::group_type& group)
         {
             require_supported_array<array_t>();
-            if (group.size() != 1)
-                throw except::sp_exception("spade_b200: the in-process multi-GPU pool path is not wired in this shim yet; "
-                                           "multi-GPU runs one process per GPU (INTEGRATION.md)");
             check(spb_exchange_local(plan, dev_ptr(array), nullptr), "spb_exchange_local");
+            if (group.size() != 1) exchange_messages(dev_ptr(array), group);
             check(spb_sync(nullptr), "spb_sync");                       // reference semantics: visible on return (execute.h:85)
         }
     };
@@ -245,6 +314,8 @@ namespace spade::b200
         const int ng[3] = {ngv[0], ngv[1], ngv[2]};
         arr_exchange_t<array_t> out;
         out.rank = grid.group().rank(); out.size = grid.group().size();
+        thread_local int next_id = 0;                                   // every rank builds its handles in the same order
+        out.id = next_id++;
         check(spb_exchange_create_from_tables(&out.plan, nx, ng, out.rank, out.size, send.data(), (int64_t)send.size()/16,
                                               recv.data(), (int64_t)recv.size()/16), "spb_exchange_create_from_tables");
         if (!isend.empty() || !irecv.empty())
@@ -562,7 +633,7 @@ namespace spade::time_integration
         const double dt = double(axis.timestep());
         const int64_t nlb = (int64_t)q.get_grid().get_num_local_blocks();
         spb_exchange* fuse = nullptr;
-        if constexpr (b200::is_exchange_bc<boundary_t>::value) { if (boundary.group->size() == 1) fuse = boundary.handle->plan; }
+        if constexpr (b200::is_exchange_bc<boundary_t>::value) fuse = boundary.handle->plan;       // same-rank ghosts; messages below
         thread_local bool fuse_refused = false;
         int cur = 0;
         for (int i = 0; i < n; ++i)
@@ -583,6 +654,11 @@ namespace spade::time_integration
             if (!ghosts_done) b200::check(spb_flux_div_rk_stage(gh, bufs[cur], bufs[1 - cur], &fd, &sd, 0, nlb, nullptr), "spb_flux_div_rk_stage");
             cur = 1 - cur;
             axis.time() = t_start + tfrac[i]*dt;
+            if constexpr (b200::is_exchange_bc<boundary_t>::value)
+            {
+                // the ghost cells fed by other ranks (other GPUs of this process): packed straight into the peers' buffers
+                if (ghosts_done && boundary.group->size() > 1) boundary.handle->exchange_messages(bufs[cur], *boundary.group);
+            }
             if (cur == 0)
             {
                 if (!ghosts_done) boundary(q, axis.time());
@@ -595,7 +671,10 @@ namespace spade::time_integration
                 if (!ghosts_done)
                 {
                     if constexpr (b200::is_exchange_bc<boundary_t>::value)
+                    {
                         b200::check(spb_exchange_local(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local");
+                        boundary.handle->exchange_messages(bufs[cur], *boundary.group);
+                    }
                     else
                     {
                         // opaque boundary callback: bring the state back into q so that the callback sees a SPADE array

@@ -5,7 +5,10 @@
 //   C. the drop-in with the two callbacks passed as named objects (b200::flux_div_rhs, b200::exchange_bc) instead of
 //      lambdas, which lets the same integrator_t call run ONE kernel per stage (RHS + stage update + ghost exchange)
 // and prints one JSON line with the timings and the relative L2 differences of the final states.
-// Usage: tgv_shim_demo [blocks_per_dim=4] [cells_per_block=32] [steps=2] [scheme: 0 central+visc | 1 hybrid+visc]
+// With gpus > 1 the solver runs the reference's own multi-GPU model — one host thread per GPU inside this process
+// (compute_env_t::exec, compute_pool.h:497-514) — and the drop-in exchanges ghost cells by packing straight into the peer GPU's
+// receive buffer over NVLink (b200::arr_exchange_t::exchange_messages).
+// Usage: tgv_shim_demo [blocks_per_dim=4] [cells_per_block=32] [steps=2] [scheme: 0 central+visc | 1 hybrid+visc] [gpus=1]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -25,7 +28,9 @@ int main(int argc, char** argv)
     const int nc = argc > 2 ? std::atoi(argv[2]) : 32;
     const int nsteps = argc > 3 ? std::atoi(argv[3]) : 2;
     const int scheme = argc > 4 ? std::atoi(argv[4]) : 0;
-    std::vector<int> devices{0};
+    const int ngpu = argc > 5 ? std::atoi(argv[5]) : 1;
+    std::vector<int> devices;
+    for (int d = 0; d < ngpu; ++d) devices.push_back(d);
     spade::parallel::compute_env_t env(&argc, &argv, devices);
     env.exec([&](spade::parallel::pool_t& pool)
     {
@@ -109,13 +114,18 @@ int main(int argc, char** argv)
                 const double d = qa[i] - qb[i], dc = qa[i] - qc[i];
                 num += d*d; numc += dc*dc; den += qa[i]*qa[i];
             }
+            // every rank holds its own blocks: norms and times over the whole job
+            num = pool.sum(num); numc = pool.sum(numc); den = pool.sum(den);
+            const auto mx = [](const double& a, const double& b) { return a > b ? a : b; };
+            ta = pool.reduce(ta, mx); tb = pool.reduce(tb, mx); tc = pool.reduce(tc, mx);
+            if (!pool.isroot()) return;
             const double cells_total = double(nb)*nb*nb*double(nc)*nc*nc;
             std::printf("{\"solver\": \"tgv_shim_demo\", \"blocks\": %d, \"cells_per_block\": %d, \"steps\": %d, \"scheme\": %d, "
                         "\"reference_gpu_basic_cell_stage_updates_per_s\": %.6e, \"b200_cell_stage_updates_per_s\": %.6e, "
                         "\"b200_fused_cell_stage_updates_per_s\": %.6e, \"speedup\": %.2f, \"speedup_fused\": %.2f, "
-                        "\"rel_l2\": %.3e, \"rel_l2_fused\": %.3e, \"umax\": %.6f}\n",
+                        "\"rel_l2\": %.3e, \"rel_l2_fused\": %.3e, \"umax\": %.6f, \"gpus\": %d}\n",
                         nb, nc, nsteps, scheme, cells_total*4*nsteps/ta, cells_total*4*nsteps/tb, cells_total*4*nsteps/tc, ta/tb, ta/tc,
-                        std::sqrt(num/den), std::sqrt(numc/den), umax);
+                        std::sqrt(num/den), std::sqrt(numc/den), umax, ngpu);
         };
         if (scheme == 0) both(spade::omni::compose(tscheme, vscheme));
         else

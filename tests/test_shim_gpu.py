@@ -39,3 +39,21 @@ def test_spade_api_solver_on_a_stretched_grid_through_the_shim():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["rel_l2_convective"] < 1e-12
     assert line["rel_l2_hybrid_fused_vs_unfused"] < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_spade_api_solver_on_two_gpus_in_one_process(scheme):
+    """The reference's own multi-GPU model: one host thread per GPU inside one process (compute_env_t::exec,
+    compute_pool.h:497-514). The drop-in's exchange packs each message straight into the peer GPU's receive buffer."""
+    import torch
+    if not os.path.exists(BIN):
+        pytest.skip("integration/_build/tgv_shim_demo not built (needs /root/reference at build time)")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([BIN, "2", "16", "2", str(scheme), "2"], capture_output=True, text=True, timeout=300, cwd=os.path.dirname(BIN))
+    assert out.returncode == 0, out.stdout + out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["gpus"] == 2
+    assert line["rel_l2"] < 1e-12
+    assert line["rel_l2_fused"] < 1e-12
