@@ -942,6 +942,8 @@ class integrator_t:
         self._plan = None
         self._scratch = None
         self._fuse_exchange = bool(fuse_exchange)
+        self._two_streams = os.environ.get("SPB_TWO_STREAMS", "1") != "0"
+        self._side = None
         self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
         if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
             f = rhs_calc.flux
@@ -1028,12 +1030,28 @@ class integrator_t:
             if self.stage_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            for b0, b1 in runs_first:
-                launch(b0, b1)
-            if overlap:
-                ex.begin(nxt)
+            if overlap and self._two_streams:
+                # rank-boundary blocks on a high-priority side stream, their messages packed and posted from it; the rank-interior
+                # blocks run on the main stream AT THE SAME TIME (both read q_in only and write disjoint cells), so the small
+                # boundary launches leave no partial waves behind and the messages fly under the interior kernel
+                if self._side is None:
+                    self._side = torch.cuda.Stream(priority=-1)
+                main, side = torch.cuda.current_stream(), self._side
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for b0, b1 in runs_first:
+                        launch(b0, b1)
+                    ex.begin(nxt)
                 for b0, b1 in runs_second:
                     launch(b0, b1)
+                main.wait_stream(side)
+            else:
+                for b0, b1 in runs_first:
+                    launch(b0, b1)
+                if overlap:
+                    ex.begin(nxt)
+                    for b0, b1 in runs_second:
+                        launch(b0, b1)
             if self.stage_events is not None:
                 e1.record()
                 # algorithmic bytes per interior cell of this launch: q in, q out, residual registers read / written, and one
