@@ -24,7 +24,20 @@ extern "C"
         cudaStream_t st = (cudaStream_t)stream;
         if (f->sgs == SPB_SGS_WALE) return flux_div_sgs(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr);
         if (f->sgs != SPB_SGS_NONE) { set_error("spb_flux_div: unknown SGS model"); return SPB_ERR_BAD_ARG; }
-        if (g->metric_dev) return flux_div_curv(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr);
+        if (g->metric_dev)
+        {
+            // general coordinates: the one-ghost-cell functors stay on the narrow kernel (its CURV instantiation), the rest and
+            // non-uniform lattices run on the wide kernel
+            int rc = SPB_ERR_UNSUPPORTED;
+#define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
+                rc = launch_fdiv_narrow<C, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st, nullptr, nullptr, nullptr)
+            SPB_NARROW(SPB_CONV_TOTANI, 1);
+            SPB_NARROW(SPB_CONV_TOTANI, 0);
+            SPB_NARROW(SPB_CONV_NONE,   1);
+#undef SPB_NARROW
+            if (rc != SPB_ERR_UNSUPPORTED) return rc;
+            return flux_div_curv(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr);
+        }
 #define SPB_CASE(C, D, V) if (f->conv == C && f->diss == D && (f->visc != 0) == (V != 0)) \
             return launch_fdiv<C, D, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st)
 #define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
@@ -69,6 +82,17 @@ extern "C"
         S.gm1 = f->gamma - 1.0; S.inv_gm1 = 1.0/(f->gamma - 1.0); S.inv_R = 1.0/f->R;
         cudaStream_t st = (cudaStream_t)stream;
         if (f->sgs != SPB_SGS_NONE && f->sgs != SPB_SGS_WALE) { set_error("spb_flux_div_rk_stage: unknown SGS model"); return SPB_ERR_BAD_ARG; }
+        if (g->metric_dev && f->sgs == SPB_SGS_NONE)
+        {
+            int rc = SPB_ERR_UNSUPPORTED;
+#define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
+                rc = launch_fdiv_narrow<C, V>(g, q_in, sd->out, P, 0, lb_begin, lb_end, st, q_out, &S, exch)
+            SPB_NARROW(SPB_CONV_TOTANI, 1);
+            SPB_NARROW(SPB_CONV_TOTANI, 0);
+            SPB_NARROW(SPB_CONV_NONE,   1);
+#undef SPB_NARROW
+            if (rc != SPB_ERR_UNSUPPORTED) return rc;
+        }
         if (g->metric_dev || f->sgs == SPB_SGS_WALE)
         {
             if (exch) { set_error("spb_flux_div_rk_stage_exchange: ghost fusion is implemented for identity coordinates without an SGS model (use spb_flux_div_rk_stage + spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }

@@ -69,6 +69,7 @@ namespace spb
             int tma_store;
             int ghost;                      // fused stage: also store the finished q planes into the same-rank neighbours' ghost cells
             double idx[3], cdx[3];          // uniform lattice: 1/dx and 0.25/dx
+            int lm;                         // general coordinates: row length of the metric tables (spb_grid::metric_lm)
         };
 
         // One tensor map per neighbour direction e = (ex+1) + 3*(ey+1) + 9*(ez+1): a view of q_out whose extents are exactly
@@ -168,7 +169,13 @@ namespace spb
             }
         };
 
-        template <int CONV, int VISC, bool UNIF, bool FUSED, int TI, int TJ>
+        // CURV: general (diagonal) coordinates (spb_grid_set_metric; reference core/coord_system.h:250-267,295-302 with
+        // flux_div_basic.h:49-71). Everything a face needs is separable: the tangential differences a cell publishes carry
+        // 1/m_t of the cell's own row / column / plane (which is the face centre's tangential coordinate), the normal
+        // difference of a face carries 1/m_n at the face, the finished flux is scaled by the area factor m_t1 m_t2 and the
+        // divergence of a cell by J = 1/(m0 m1 m2). Row 0 of a table = m (as info::metric sees it), row 1 = 1/m at the cell
+        // centres, row 2 = 1/m at the faces.
+        template <int CONV, int VISC, bool UNIF, bool FUSED, int TI, int TJ, bool CURV = false>
         __global__ void __launch_bounds__(NTHREADS, 2)
         flux_div_narrow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_rhs,
                                const __grid_constant__ CUtensorMap tmap_qout, const __grid_constant__ CUtensorMap tmap_in0,
@@ -176,7 +183,7 @@ namespace spb
                                const __grid_constant__ FluxParams P, const __grid_constant__ Dims G,
                                const __grid_constant__ Stage S, const double* __restrict__ inv_dx_tab,
                                const __grid_constant__ GhostMaps GM, const int* __restrict__ nbr_tab,
-                               double* __restrict__ qout_raw)
+                               double* __restrict__ qout_raw, const double* __restrict__ met)
         {
             using L = Lay<TI, TJ>;
             constexpr int TIp = L::TIp, PLANE_BYTES = L::PLANE_BYTES, PLANE_STRIDE = L::PLANE_STRIDE, PW = L::PW, PSZ = L::PSZ;
@@ -205,6 +212,9 @@ namespace spb
             const int ni_t = min(TI, G.nx[0] - i0);
             const int nj_t = min(TJ, G.nx[1] - j0);
             const Spacing<UNIF> H(G, inv_dx_tab, lb);
+            // metric rows of this block: MT(d, row, idx); indices are clamped so that idle lanes of ragged tiles stay in range
+            const double* mt = CURV ? met + lb*9*(long long)G.lm : nullptr;
+            auto MT = [&](const int d, const int row, const int idx) { return __ldg(mt + (d*3 + row)*G.lm + min(idx, G.np[d])); };
 
             // TMA coordinates (fused (v,i) dimension first); the box starts one cell early if the halo start is odd
             const int ash = (i0 + G.ng[0] - 1) & 1;
@@ -260,13 +270,24 @@ namespace spb
                 double rhom = density(P.R, qm[0], qm[1]);
                 double rho0 = density(P.R, q0[0], q0[1]);
                 if (!active) { rhom = 1.0; rho0 = 1.0; }
+                // scales of this column: tangential differences (cx, cy), normal differences of the lower x / y face (gx, gy),
+                // area factors and the in-plane part of the Jacobian
+                const int ipc = i0 + il + G.ng[0], jpc = j0 + jl + G.ng[1];
+                double cx = H.c0, cy = H.c1, gx = H.i0, gy = H.i1, ar0 = 1.0, ar1 = 1.0, jij = 1.0, jkm = 1.0;
+                if (CURV)
+                {
+                    const double r0 = MT(0, 1, ipc), r1 = MT(1, 1, jpc);
+                    cx = H.c0*r0; cy = H.c1*r1; jij = r0*r1;
+                    gx = H.i0*MT(0, 2, ipc); gy = H.i1*MT(1, 2, jpc);
+                    ar0 = MT(0, 0, ipc); ar1 = MT(1, 0, jpc);
+                }
                 double dpc = 0.0, dpxw = 0.0, dpyw = 0.0;
                 if (VISC)
                 {
                     const double* pl = ring;
-                    dpc  = H.c0*(pl[co + 5 + 2] - pl[co - 5 + 2]) + H.c1*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
-                    dpxw = H.c0*(pl[co + 5 + 4] - pl[co - 5 + 4]);
-                    dpyw = H.c1*(pl[co + 5*TIp + 4] - pl[co - 5*TIp + 4]);
+                    dpc  = cx*(pl[co + 5 + 2] - pl[co - 5 + 2]) + cy*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
+                    dpxw = cx*(pl[co + 5 + 4] - pl[co - 5 + 4]);
+                    dpyw = cy*(pl[co + 5*TIp + 4] - pl[co - 5*TIp + 4]);
                 }
                 double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
                 const long long cell0 = lb*G.block_stride
@@ -285,25 +306,44 @@ namespace spb
                     double dxu = 0.0, dxv = 0.0, dxw = 0.0, dyu = 0.0, dyv = 0.0, dyw = 0.0;
                     if (VISC)
                     {
-                        dxu = H.c0*(plk[5 + 2] - plk[-5 + 2]);
-                        dxv = H.c0*(plk[5 + 3] - plk[-5 + 3]);
-                        dxw = H.c0*(plk[5 + 4] - plk[-5 + 4]);
-                        dyu = H.c1*(plk[5*TIp + 2] - plk[-5*TIp + 2]);
-                        dyv = H.c1*(plk[5*TIp + 3] - plk[-5*TIp + 3]);
-                        dyw = H.c1*(plk[5*TIp + 4] - plk[-5*TIp + 4]);
+                        dxu = cx*(plk[5 + 2] - plk[-5 + 2]);
+                        dxv = cx*(plk[5 + 3] - plk[-5 + 3]);
+                        dxw = cx*(plk[5 + 4] - plk[-5 + 4]);
+                        dyu = cy*(plk[5*TIp + 2] - plk[-5*TIp + 2]);
+                        dyv = cy*(plk[5*TIp + 3] - plk[-5*TIp + 3]);
+                        dyw = cy*(plk[5*TIp + 4] - plk[-5*TIp + 4]);
                     }
                     const double cZ = dxu + dyv;
+                    // plane k: z scales (the same for the whole plane)
+                    double cz = H.c2, gz = H.i2, ar2 = 1.0, jk = 1.0;
+                    if (CURV)
+                    {
+                        const int kp = k + G.ng[2];
+                        jk = MT(2, 1, kp); cz = H.c2*jk; gz = H.i2*MT(2, 2, kp); ar2 = MT(2, 0, kp);
+                    }
                     // z-face k-1/2: registers only, overlaps the wait for plane k+1. acc carries the divergence of a cell:
                     // lower-face fluxes are added as they are computed, the neighbours' (upper-face) fluxes are subtracted
                     // after barrier (2).
                     {
                         double Fz[5];
-                        face<CONV, VISC, 2>(P, qm, q0, rhom, rho0, dpc + cZ, dpxw + dxw, dpyw + dyw, H.i2, Fz);
+                        face<CONV, VISC, 2>(P, qm, q0, rhom, rho0, dpc + cZ, dpxw + dxw, dpyw + dyw, gz, Fz);
+                        if (CURV)
+                        {
+                            const double az = ar0*ar1;
+                            #pragma unroll
+                            for (int v = 0; v < 5; ++v) Fz[v] *= az;
+                        }
                         if (k >= 1)
                         {
                             double r[5];
                             #pragma unroll
                             for (int v = 0; v < 5; ++v) r[v] = fma(-Fz[v], H.i2, acc[v]);      // rhs of cell k-1
+                            if (CURV)
+                            {
+                                const double jac = jij*jkm;                                     // J of cell k-1
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) r[v] *= jac;
+                            }
                             if (FUSED)
                             {
                                 // the inputs of this cell were fetched by cp.async into this thread's own staging slots
@@ -378,9 +418,9 @@ namespace spb
                     double cX = 0.0, cY = 0.0, dzu = 0.0, dzv = 0.0;
                     if (VISC && k < nz)
                     {
-                        const double dzw = H.c2*(qp[4] - qm[4]);
-                        dzu = H.c2*(qp[2] - qm[2]);
-                        dzv = H.c2*(qp[3] - qm[3]);
+                        const double dzw = cz*(qp[4] - qm[4]);
+                        dzu = cz*(qp[2] - qm[2]);
+                        dzv = cz*(qp[3] - qm[3]);
                         cX = dyv + dzw; cY = dzw + dxu;
                     }
                     if (k < nz)
@@ -404,7 +444,13 @@ namespace spb
                             const double rhoL = pub[P_RHO*PSZ + pl_];
                             double ac = 0.0, b = 0.0, d = 0.0;
                             if (VISC) { ac = pub[P_CX*PSZ + pl_] + cX; b = pub[P_DYU*PSZ + pl_] + dyu; d = pub[P_DZU*PSZ + pl_] + dzu; }
-                            face<CONV, VISC, 0>(P, qL, q0, rhoL, rho0, ac, b, d, H.i0, F);
+                            face<CONV, VISC, 0>(P, qL, q0, rhoL, rho0, ac, b, d, gx, F);
+                            if (CURV)
+                            {
+                                const double ax = ar1*ar2;
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) F[v] *= ax;
+                            }
                             if (active)
                             {
                                 #pragma unroll
@@ -421,7 +467,13 @@ namespace spb
                             const double rhoL = pub[P_RHO*PSZ + pl_];
                             double ac = 0.0, b = 0.0, d = 0.0;
                             if (VISC) { ac = pub[P_CY*PSZ + pl_] + cY; b = pub[P_DZV*PSZ + pl_] + dzv; d = pub[P_DXV*PSZ + pl_] + dxv; }
-                            face<CONV, VISC, 1>(P, qL, q0, rhoL, rho0, ac, b, d, H.i1, F);
+                            face<CONV, VISC, 1>(P, qL, q0, rhoL, rho0, ac, b, d, gy, F);
+                            if (CURV)
+                            {
+                                const double ay = ar2*ar0;
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) F[v] *= ay;
+                            }
                             if (active)
                             {
                                 #pragma unroll
@@ -442,6 +494,7 @@ namespace spb
                         }
                     }
                     rhom = rho0; rho0 = rhop;
+                    jkm = jk;
                     dpc = cZ; dpxw = dxw; dpyw = dyw;
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) { qm[v] = q0[v]; q0[v] = qp[v]; }
@@ -459,6 +512,17 @@ namespace spb
                 const int  cci = col_lo ? -1 : ni_t;
                 const int rl = min(lane, TI - 1);                // 16-wide tiles: the upper half of the warp has no row cell (its loads stay inside the plane)
                 const int co_r0 = cell_off(rl, -1), co_r1 = cell_off(rl, nj_t), co_c = cell_off(cci, ccj);
+                // scales of the edge cells: the row cells sit in column i0 + rl, the column cells in row j0 + ccj
+                double ecx = H.c0, ecy = H.c1, egy = H.i1, egx = H.i0, ear0 = 1.0, ear1 = 1.0;
+                if (CURV)
+                {
+                    ecx = H.c0*MT(0, 1, i0 + rl + G.ng[0]);
+                    ecy = H.c1*MT(1, 1, j0 + ccj + G.ng[1]);
+                    egy = H.i1*MT(1, 2, j0 + nj_t + G.ng[1]);          // upper y-face of the tile
+                    egx = H.i0*MT(0, 2, i0 + ni_t + G.ng[0]);          // upper x-face of the tile
+                    ear0 = MT(0, 0, i0 + rl + G.ng[0]);
+                    ear1 = MT(1, 0, j0 + ccj + G.ng[1]);
+                }
                 // z-neighbours (k-1, k) of the edge cells roll through registers: v,w for the row cells, u,w for the column cell
                 double r0m[2], r00[2], r1m[2], r10[2], ccm[2], cc0[2];
                 {
@@ -490,6 +554,8 @@ namespace spb
                     // ---- before (1): publish the lower halo, and prepare what the upper faces need from their R cells
                     double uCY = 0.0, uDzv = 0.0, uDxv = 0.0, xCX = 0.0, xDyu = 0.0, xDzu = 0.0;
                     double uRho = 1.0, xRho = 1.0;
+                    double ecz = H.c2, ear2 = 1.0;
+                    if (CURV) { ecz = H.c2*MT(2, 1, k + G.ng[2]); ear2 = MT(2, 0, k + G.ng[2]); }
                     if (k < nz)
                     {
                         if (row_on)
@@ -499,12 +565,12 @@ namespace spb
                             uRho = density(P.R, plk[co_r1], plk[co_r1 + 1]);
                             if (VISC)
                             {
-                                pub[P_CY*PSZ + po]  = H.c2*(r0p[1] - r0m[1]) + H.c0*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
-                                pub[P_DZV*PSZ + po] = H.c2*(r0p[0] - r0m[0]);
-                                pub[P_DXV*PSZ + po] = H.c0*(plk[co_r0 + 5 + 3] - plk[co_r0 - 5 + 3]);
-                                uCY  = H.c2*(r1p[1] - r1m[1]) + H.c0*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
-                                uDzv = H.c2*(r1p[0] - r1m[0]);
-                                uDxv = H.c0*(plk[co_r1 + 5 + 3] - plk[co_r1 - 5 + 3]);
+                                pub[P_CY*PSZ + po]  = ecz*(r0p[1] - r0m[1]) + ecx*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
+                                pub[P_DZV*PSZ + po] = ecz*(r0p[0] - r0m[0]);
+                                pub[P_DXV*PSZ + po] = ecx*(plk[co_r0 + 5 + 3] - plk[co_r0 - 5 + 3]);
+                                uCY  = ecz*(r1p[1] - r1m[1]) + ecx*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
+                                uDzv = ecz*(r1p[0] - r1m[0]);
+                                uDxv = ecx*(plk[co_r1 + 5 + 3] - plk[co_r1 - 5 + 3]);
                             }
                         }
                         if (col_on)
@@ -512,9 +578,9 @@ namespace spb
                             xRho = density(P.R, plk[co_c], plk[co_c + 1]);
                             if (VISC)
                             {
-                                xCX  = H.c1*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]) + H.c2*(ccp[1] - ccm[1]);
-                                xDyu = H.c1*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
-                                xDzu = H.c2*(ccp[0] - ccm[0]);
+                                xCX  = ecy*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]) + ecz*(ccp[1] - ccm[1]);
+                                xDyu = ecy*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
+                                xDzu = ecz*(ccp[0] - ccm[0]);
                             }
                             if (col_lo)
                             {
@@ -542,7 +608,13 @@ namespace spb
                             const double rhoL = pub[P_RHO*PSZ + pl_];
                             double ac = 0.0, b = 0.0, d = 0.0;
                             if (VISC) { ac = pub[P_CY*PSZ + pl_] + uCY; b = pub[P_DZV*PSZ + pl_] + uDzv; d = pub[P_DXV*PSZ + pl_] + uDxv; }
-                            face<CONV, VISC, 1>(P, qL, qR, rhoL, uRho, ac, b, d, H.i1, F);
+                            face<CONV, VISC, 1>(P, qL, qR, rhoL, uRho, ac, b, d, egy, F);
+                            if (CURV)
+                            {
+                                const double ay = ear2*ear0;
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) F[v] *= ay;
+                            }
                             #pragma unroll
                             for (int v = 0; v < 5; ++v) Fy[(nj_t*TI + lane)*5 + v] = F[v];
                         }
@@ -555,7 +627,13 @@ namespace spb
                             const double rhoL = pub[P_RHO*PSZ + pl_];
                             double ac = 0.0, b = 0.0, d = 0.0;
                             if (VISC) { ac = pub[P_CX*PSZ + pl_] + xCX; b = pub[P_DYU*PSZ + pl_] + xDyu; d = pub[P_DZU*PSZ + pl_] + xDzu; }
-                            face<CONV, VISC, 0>(P, qL, qR, rhoL, xRho, ac, b, d, H.i0, F);
+                            face<CONV, VISC, 0>(P, qL, qR, rhoL, xRho, ac, b, d, egx, F);
+                            if (CURV)
+                            {
+                                const double ax = ear1*ear2;
+                                #pragma unroll
+                                for (int v = 0; v < 5; ++v) F[v] *= ax;
+                            }
                             #pragma unroll
                             for (int v = 0; v < 5; ++v) Fx[(ccj*(TI + 1) + ni_t)*5 + v] = F[v];
                         }
@@ -776,6 +854,7 @@ namespace spb
         G.block_stride = g->block_stride;
         G.lb0 = lb_begin;
         G.increment = increment;
+        G.lm = g->metric_lm;
         G.tma_store = tma_store;
         const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
         if (nblk <= 0) return 0;
@@ -795,10 +874,16 @@ namespace spb
         {
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev, GM, nbr_tab, q_out);
+            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev, GM, nbr_tab, q_out, g->metric_dev);
             SPB_LAUNCH_CHECK();
             return 0;
         };
+        if (g->metric_dev)
+        {
+            // general coordinates: the computational lattice must be uniform (per-block dxi with a metric is the wide kernel's job)
+            if (!uniform) { set_error("spb_flux_div: general coordinates on a non-uniform block lattice run on the wide kernel"); return SPB_ERR_UNSUPPORTED; }
+            return stage ? go(flux_div_narrow_kernel<CONV, VISC, true, true, TI, TJ, true>) : go(flux_div_narrow_kernel<CONV, VISC, true, false, TI, TJ, true>);
+        }
         if (stage) return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, true, TI, TJ>) : go(flux_div_narrow_kernel<CONV, VISC, false, true, TI, TJ>);
         return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, false, TI, TJ>) : go(flux_div_narrow_kernel<CONV, VISC, false, false, TI, TJ>);
     }

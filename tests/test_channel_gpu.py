@@ -112,3 +112,46 @@ def test_wall_bounded_fused_stage_path_matches_oracle(scheme):
     got = ti.solution().to_host()
     assert rel_l2(got, want) < 1e-12
     assert rel_l2(got - q0, want - q0) < 1e-9
+
+
+@pytest.mark.parametrize("stretched", [False, True])
+def test_config1_channel_at_full_size(stretched):
+    """BASELINE.json configs[0] at its full size: 4x4x4 blocks of 16^3 cells, 2 exchange cells, x/z periodic, isothermal
+    no-slip walls in y, body force, totani_lr + visc_lr, rk4, 10 steps (6 on the tanh-stretched grid) against the oracle."""
+    from oracle import port, ref
+    nb, n, ng = (4, 4, 4), (16, 16, 16), 2
+    periodic = (1, 0, 1)
+    bounds = [0.0, 2 * np.pi, -1.0, 1.0, 0.0, np.pi]
+    nsteps = 6 if stretched else 10
+    cfg = oracle_cfg(nb, n, ng, scheme=0, integrator=0, periodic=periodic, bounds=bounds)
+    bc = ref.make_bc(mask=(0, 0, 1, 1, 0, 0), a=(1, -1, -1, -1, -1), b=(0, 2 * WALL_T, 0, 0, 0), force=(40.0, 0.0, 0.0))
+    q0 = make_state(nb, n, ng, seed=101, bounds=bounds)
+    q0 = port.boundary_fill(cfg, bc, port.exchange(cfg, q0.ravel())).reshape(q0.shape)
+    maps = (None, ("tanh", -1.0, 1.0, 0.1, 4.0), None)
+    dt = (0.05 if stretched else 0.2) * (2.0 / 64) / port.reduce_umax(cfg, q0.ravel())
+    if stretched:
+        port.set_coords(ref.make_coords(maps))
+    try:
+        want = port.advance_channel(cfg, bc, q0.ravel(), dt, nsteps).reshape(q0.shape)
+    finally:
+        port.set_coords(None)
+    import spade_b200.api as sp
+    coords = sp.diagonal_coords(None, sp.integrated_tanh_1D(-1.0, 1.0, 0.1, 4.0), None) if stretched else sp.identity()
+    grid = sp.cartesian_grid_t(n, sp.cartesian_blocks_t(nb, bounds), coords, sp.pool_t(0, 1))
+    gas = sp.ideal_gas_t(GAMMA, RGAS)
+    flux = sp.flux_desc(product_flux(0))
+    qa, ra = sp.grid_array.from_host(grid, q0), sp.grid_array(grid, 0.0)
+    ex = sp.make_exchange(qa, periodic)
+    wall, force = sp.noslip_isothermal_wall(WALL_T), sp.body_force_t(40.0)
+
+    def calc_rhs(r, qq, t):
+        sp.flux_div(qq, r, flux, sp.overwrite)
+        sp.source_term(qq, r, force)
+
+    ti = sp.integrator_t(sp.time_axis_t(0.0, dt), sp.rk4_t, sp.integrator_data_t(qa, ra, sp.rk4_t), calc_rhs,
+                         sp.exchange_bc_t(ex, sp.boundary.ymin | sp.boundary.ymax, wall), sp.state_transform_t(gas))
+    for _ in range(nsteps):
+        ti.advance()
+    got = ti.solution().to_host()
+    assert rel_l2(got, want) < 1e-12
+    assert rel_l2(got - q0, want - q0) < 1e-9
