@@ -230,7 +230,11 @@ def ours(args):
         raise SystemExit("bench.py: no CUDA device; spade_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL's send/recv kernels on a high-priority stream: they need a few CTA slots while the stage kernel fills every SM,
+        # and at normal priority they would only be scheduled once that grid drains (no overlap)
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = os.environ.get("SPB_NCCL_HIGH_PRIO", "1") != "0"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     pool = sp.pool_t.from_torch()
     n = max(world, 1)
     lat = tuple(args.lattice) if args.lattice else LATTICE_1GPU

@@ -232,6 +232,20 @@ int spb_exchange_unpack(spb_exchange* e, double* q_dev, int peer, const double* 
  * cudaDeviceEnablePeerAccess). Same element order as spb_exchange_pack. */
 int spb_exchange_pack_peer(spb_exchange* e, const double* q_dev, int peer, double* peer_recvbuf_dev, void* stream);
 
+/* One process per GPU: the receive buffers are exported through CUDA IPC (spb_ipc_export / spb_ipc_import), the pack kernel of
+ * a rank stores its message straight into the neighbour's buffer over NVLink (spb_exchange_pack_peer) and raises the
+ * neighbour's flag (spb_flag_signal, stream-ordered after the pack); the neighbour's stream waits on its own flag
+ * (spb_flag_wait) before spb_exchange_unpack. No SM of either GPU is held by a communication kernel while the RHS kernel
+ * runs, unlike NCCL send/recv (reference counterpart: exchange_message_t::send_all with cudaMemcpyPeer,
+ * exchange_message.h:14-56, compute_pool.h:93-99). spb_dev_alloc returns zero-filled cudaMalloc memory (IPC-shareable). */
+int spb_dev_alloc(void** out, size_t bytes);
+int spb_dev_free(void* p);
+int spb_ipc_export(const void* dev_ptr, unsigned char handle[64]);
+int spb_ipc_import(const unsigned char handle[64], void** out);
+int spb_ipc_close(void* p);
+int spb_flag_signal(unsigned long long* flag_dev, unsigned long long value, void* stream);
+int spb_flag_wait(const unsigned long long* flag_dev, unsigned long long value, void* stream);
+
 /* ---- domain-boundary ghost fill: replaces algs::boundary_fill(arr, boundaries, kern) ------------
  * reference src/grid/boundary_fill.h:32-133. One call fills ONE boundary (idir, pm): pm = 0 the lower, 1 the upper
  * face of the block lattice along idir. `blocks_host` lists the local blocks on that face

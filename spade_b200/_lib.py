@@ -92,6 +92,13 @@ SYMBOLS = {
     "spb_exchange_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "spb_exchange_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "spb_exchange_pack_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "spb_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "spb_dev_free": (C.c_int, [C.c_void_p]),
+    "spb_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "spb_ipc_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "spb_ipc_close": (C.c_int, [C.c_void_p]),
+    "spb_flag_signal": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
+    "spb_flag_wait": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     "spb_boundary_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _i64p, C.c_int64, C.POINTER(BcDesc), C.c_void_p]),
     "spb_source_term": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SourceDesc), C.c_void_p]),
     "spb_last_error": (C.c_char_p, []),

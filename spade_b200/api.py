@@ -579,6 +579,7 @@ class arr_exchange_t:
         self.recv_cells = [int(lib().spb_exchange_recv_cells(self._h, p)) for p in range(self.pool.size())]
         self._sendbuf, self._recvbuf = {}, {}
         self._runs, self._reqs = None, []
+        self._p2p = None                # decided at the first exchange (collective): peer-memory path or NCCL send/recv
 
     def __del__(self):
         try:
@@ -646,12 +647,79 @@ class arr_exchange_t:
             self._runs = (runs(True), runs(False))
         return self._runs
 
+    # ---- peer-memory path (one process per GPU on one node): no communication kernel holds an SM -----------------
+    def _setup_p2p(self):
+        """Receive buffers (two, used alternately: a neighbour may already pack its next message while this rank still unpacks
+        the previous one) and arrival flags in raw device memory, exported through CUDA IPC and mapped by the neighbours.
+        Returns False (and the NCCL path stays) if the backend is not NCCL, SPB_P2P=0, or any rank fails to map a handle."""
+        import torch.distributed as dist
+        self._p2p = False
+        if self.pool.size() == 1 or os.environ.get("SPB_P2P", "1") == "0" or dist.get_backend(self.pool.group) != "nccl":
+            return False
+        me, n = self.pool.rank(), self.pool.size()
+        own, export, ok = {}, {}, True
+        try:
+            for p in range(n):
+                if p == me or not self.recv_cells[p]:
+                    continue
+                ptrs = []
+                for _ in range(2):
+                    b = C.c_void_p()
+                    check(lib().spb_dev_alloc(C.byref(b), NVAR * 8 * self.recv_cells[p]))
+                    ptrs.append(b)
+                f = C.c_void_p()
+                check(lib().spb_dev_alloc(C.byref(f), 16))                       # two 8-byte flags, zero-filled
+                own[p] = (ptrs, f)
+                hs = []
+                for b in ptrs + [f]:
+                    h = C.create_string_buffer(64)
+                    check(lib().spb_ipc_export(b, h))
+                    hs.append(h.raw)
+                export[p] = hs
+        except SpbError:
+            ok = False
+        gathered = [None] * n
+        dist.all_gather_object(gathered, (ok, export), group=self.pool.group)
+        ok = all(g[0] for g in gathered)
+        remote = {}
+        if ok:
+            try:
+                for p in range(n):
+                    if p == me or not self.send_cells[p]:
+                        continue
+                    hs = gathered[p][1][me]                                  # rank p's buffers for messages from me
+                    mapped = []
+                    for h in hs:
+                        out = C.c_void_p()
+                        check(lib().spb_ipc_import(h, C.byref(out)))
+                        mapped.append(out)
+                    remote[p] = (mapped[:2], mapped[2])
+            except (SpbError, KeyError):
+                ok = False
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pool.group)
+        if int(flag.item()) == 0:
+            return False
+        self._own, self._remote, self._seq, self._p2p = own, remote, 0, True
+        return True
+
     def begin(self, array):
-        """First half of exchange(): pack the off-rank messages and post the sends/receives (NCCL runs them on its own
-        stream, ordered after the packs). Kernels launched after this call overlap the NVLink transfers."""
+        """First half of exchange(): the off-rank messages leave. Peer-memory path: each message is packed STRAIGHT INTO the
+        neighbour's receive buffer over NVLink and the neighbour's arrival flag is raised behind it (stream order). NCCL
+        path: pack into a send buffer and post the sends/receives (NCCL runs them on its own stream, ordered after the
+        packs). Kernels launched after this call overlap the transfers."""
         self._reqs = []
         if self.pool.size() > 1:
             st = _stream_ptr()
+            if self._p2p is None:
+                self._setup_p2p()
+            if self._p2p:
+                self._seq += 1
+                par = self._seq & 1
+                for p, (bufs, flags) in self._remote.items():
+                    check(lib().spb_exchange_pack_peer(self._h, _dptr(array.data), p, bufs[par], st))
+                    check(lib().spb_flag_signal(C.c_void_p(flags.value + 8 * par), self._seq, st))
+                return
             self._buffers()
             for p, buf in self._sendbuf.items():
                 check(lib().spb_exchange_pack(self._h, _dptr(array.data), p, _dptr(buf), st))
@@ -662,6 +730,12 @@ class arr_exchange_t:
         st = _stream_ptr()
         if local:
             check(lib().spb_exchange_local(self._h, _dptr(array.data), st))
+        if self.pool.size() > 1 and self._p2p:
+            par = self._seq & 1
+            for p, (bufs, flags) in self._own.items():
+                check(lib().spb_flag_wait(C.c_void_p(flags.value + 8 * par), self._seq, st))
+                check(lib().spb_exchange_unpack(self._h, _dptr(array.data), p, bufs[par], st))
+            return
         for r in self._reqs:
             r.wait()
         self._reqs = []

@@ -2,6 +2,7 @@
 #include "spb_common.cuh"
 #include <mutex>
 #include <cmath>
+#include <cstring>
 
 namespace spb
 {
@@ -112,6 +113,32 @@ extern "C"
         return 0;
     }
     int spb_grid_has_metric(const spb_grid* g) { return (g && g->metric_dev) ? 1 : 0; }
+
+    // ---- peer-memory plumbing for one-process-per-GPU runs: raw (IPC-shareable) allocations, IPC handles, stream-ordered flags
+    int spb_dev_alloc(void** out, size_t bytes)
+    {
+        if (!out) { spb::set_error("spb_dev_alloc: null argument"); return SPB_ERR_BAD_ARG; }
+        SPB_CUDA(cudaMalloc(out, bytes ? bytes : 8));
+        SPB_CUDA(cudaMemset(*out, 0, bytes ? bytes : 8));
+        return 0;
+    }
+    int spb_dev_free(void* p) { if (p) SPB_CUDA(cudaFree(p)); return 0; }
+    int spb_ipc_export(const void* dev_ptr, unsigned char handle[64])
+    {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        cudaIpcMemHandle_t h;
+        SPB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+        memcpy(handle, &h, 64);
+        return 0;
+    }
+    int spb_ipc_import(const unsigned char handle[64], void** out)
+    {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, 64);
+        SPB_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+        return 0;
+    }
+    int spb_ipc_close(void* p) { if (p) SPB_CUDA(cudaIpcCloseMemHandle(p)); return 0; }
 
     void spb_grid_destroy(spb_grid* g)
     {

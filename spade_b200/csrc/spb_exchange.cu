@@ -257,6 +257,24 @@ namespace spb
     }
 }
 
+namespace spb
+{
+    // the stores of the kernels that precede this one in the stream have been performed (kernel boundary); the fence orders
+    // them before the flag for an observer on another GPU
+    __global__ void flag_signal_kernel(unsigned long long* flag, const unsigned long long value)
+    {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(flag) = value;
+        __threadfence_system();
+    }
+    __global__ void flag_wait_kernel(const unsigned long long* flag, const unsigned long long value)
+    {
+        const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(flag);
+        while (*f < value) __nanosleep(200);
+        __threadfence_system();
+    }
+}
+
 extern "C"
 {
     int spb_exchange_create(spb_exchange** out, const int nb[3], const int nx[3], const int ng[3], const int periodic[3], int rank, int nranks)
@@ -425,6 +443,23 @@ extern "C"
     int spb_exchange_pack_peer(spb_exchange* e, const double* q_dev, int peer, double* peer_recvbuf_dev, void* stream)
     {
         return spb_exchange_pack(e, q_dev, peer, peer_recvbuf_dev, stream);
+    }
+
+    // Stream-ordered flags in (peer) device memory: the sender raises the receiver's flag after the pack kernel that stored the
+    // message into the receiver's buffer; the receiver's stream spins on its own flag before it unpacks. Values only grow.
+    int spb_flag_signal(unsigned long long* flag_dev, unsigned long long value, void* stream)
+    {
+        if (!flag_dev) { spb::set_error("spb_flag_signal: null flag"); return SPB_ERR_BAD_ARG; }
+        spb::flag_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, value);
+        SPB_LAUNCH_CHECK();
+        return 0;
+    }
+    int spb_flag_wait(const unsigned long long* flag_dev, unsigned long long value, void* stream)
+    {
+        if (!flag_dev) { spb::set_error("spb_flag_wait: null flag"); return SPB_ERR_BAD_ARG; }
+        spb::flag_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, value);
+        SPB_LAUNCH_CHECK();
+        return 0;
     }
 
     int spb_exchange_unpack(spb_exchange* e, double* q_dev, int peer, const double* recvbuf_dev, void* stream)

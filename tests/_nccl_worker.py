@@ -17,7 +17,9 @@ from util import GAMMA, RGAS, make_state, oracle_cfg, product_flux, rel_l2, zero
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     rank, world = dist.get_rank(), dist.get_world_size()
     import spade_b200.api as sp
     from oracle import port

@@ -36,7 +36,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     pool = sp.pool_t.from_torch()
     n, B, NG = world, a.block, 2
     lat = (a.lattice[0], a.lattice[1], a.lattice[2] * n)
