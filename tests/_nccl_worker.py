@@ -66,7 +66,7 @@ def main():
         assert umax == port.reduce_umax(cfg, want.ravel()) or abs(umax / port.reduce_umax(cfg, want.ravel()) - 1) < 1e-12
     dist.barrier()
     dist.destroy_process_group()
-    print(f"rank {rank} ok")
+    print(f"rank {rank} ok p2p={int(bool(ex._p2p))}")
 
 
 if __name__ == "__main__":
