@@ -282,3 +282,35 @@ def test_cuda_source_term_divides_by_the_jacobian(coords_off):
     qa, ra = sp.grid_array.from_host(grid, q), sp.grid_array.from_host(grid, rhs0)
     sp.source_term(qa, ra, sp.body_force_t(*force))
     assert rel_l2(ra.to_host(), want) < 1e-14
+
+
+def test_python_coordinate_mirror_matches_the_oracle_mappings():
+    """spade_b200.api.diagonal_coords / integrated_tanh_1D / scaled_coord_1D / quad_1D (numpy) against the C restatement of
+    core/coord_system.h:54-177, and the metric tables handed to spb_grid_set_metric against the oracle's geometry (CPU only)."""
+    import spade_b200.api as sp
+    from oracle import port, ref
+    cd = ref.make_coords((("scaled", 2.0), ("tanh", -1.0, 1.0, 0.1, 1.3), ("quad",)))
+    maps = [sp.scaled_coord_1D(2.0), sp.integrated_tanh_1D(-1.0, 1.0, 0.1, 1.3), sp.quad_1D()]
+    xs = np.linspace(-1.1, 1.9, 41)
+    for d, m in enumerate(maps):
+        want_x = np.array([port.coord_map(cd, d, x) for x in xs])
+        want_m = np.array([port.coord_deriv(cd, d, x) for x in xs])
+        assert np.allclose(m.map(xs), want_x, rtol=1e-14, atol=1e-15)
+        assert np.allclose(m.coord_deriv(xs), want_m, rtol=1e-14, atol=1e-15)
+    nb, n, ng = (2, 2, 1), (8, 4, 4), 2
+    for metric_at in ("physical", "computational"):
+        grid = sp.cartesian_grid_t(n, sp.cartesian_blocks_t(nb, BOUNDS), sp.diagonal_coords(*maps, metric_at=metric_at), sp.pool_t(0, 1))
+        area, jac, face = grid.metric_tables((ng,) * 3)
+        for d in range(3):
+            assert area[d].shape == (4, n[d] + 2 * ng) and face[d].shape == (4, n[d] + 2 * ng + 1)
+            lb = 3
+            b = (lb % nb[0], (lb // nb[0]) % nb[1], lb // (nb[0] * nb[1]))
+            bsize = (BOUNDS[2 * d + 1] - BOUNDS[2 * d]) / nb[d]
+            lo = BOUNDS[2 * d] + b[d] * bsize
+            dx = (lo + bsize - lo) / n[d]
+            for i in range(-ng, n[d] + ng):
+                xc = lo + (i + 0.5) * dx
+                assert np.isclose(jac[d][lb, i + ng], port.coord_deriv(cd, d, xc), rtol=1e-14)
+                xa = port.coord_map(cd, d, xc) if metric_at == "physical" else xc
+                assert np.isclose(area[d][lb, i + ng], port.coord_deriv(cd, d, xa), rtol=1e-13)
+                assert np.isclose(face[d][lb, i + ng], port.coord_deriv(cd, d, lo + i * dx), rtol=1e-14)

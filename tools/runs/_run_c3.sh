@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 900 python -m pytest tests/test_curvilinear.py tests/test_shim_gpu.py -m gpu -q 2>&1 | tail -5
 (cd integration/_build && ./channel_curv_demo 4 32 3) 2>&1 | tail -2 | tee $O/curv_demo.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # config 3 on 8 GPUs: 1024 x 512 x 512 cells, 8192 blocks of 32^3, stretched y, walls, hybrid + visc
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 nvidia-smi -L | head -8
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_c5.log 2>&1; echo "pytest rc=$?"; tail -30 $O/pytest_gpu_c5.log
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e | python -c "

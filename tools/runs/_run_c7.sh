@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 900 python -m pytest tests/test_curvilinear.py tests/test_channel_gpu.py -m gpu -x -q 2>&1 | tail -15
 timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_curvilinear.py --deselect tests/test_channel_gpu.py 2>&1 | tail -5

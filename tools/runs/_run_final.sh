@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-end verification on one B200: parity suite, smoke, headline bench, ncu launch list of the bench command
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_final.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu_final.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

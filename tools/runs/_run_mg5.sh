@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 240 python -m pytest tests/test_multigpu_nccl.py -m gpu -x -q 2>&1 | tail -6
 run() { name=$1; lat=$2; shift; shift

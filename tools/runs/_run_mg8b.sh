@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 200 python -m pytest tests/test_multigpu_nccl.py -m gpu -x -q -k "4-1" 2>&1 | tail -4
 for L in "8 8 8" "16 16 16"; do

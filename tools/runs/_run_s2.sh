@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 nvidia-smi -L
 timeout 900 python -m pytest tests/test_shim_gpu.py tests/test_multigpu_nccl.py -m gpu -x -q 2>&1 | tail -15

@@ -1,7 +1,7 @@
 #!/bin/bash
 # weak-scaling sweeps on one 8-GPU box: configs[1] shape (512^3 per GPU) and configs[3] (256^3 per GPU) at N = 1, 2, 4, 8
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 for N in 1 2 4 8; do
   for L in "16 16 16" "8 8 8"; do
