@@ -342,14 +342,32 @@ namespace spade::b200
     };
     template <typename flux_func_t> inline flux_div_rhs_t<flux_func_t> flux_div_rhs(const flux_func_t& f) { return flux_div_rhs_t<flux_func_t>{f}; }
 
+    // algs::boundary_fill on a raw device buffer in the layout of `arr` (defined below)
+    template <typename arr_t> inline void boundary_fill_ptr(const arr_t& arr, double* ptr, const boundary::identifier_t& boundaries, const spb_bc_desc& d);
+    struct mirror_kernel;
+    inline spb_bc_desc mirror_desc(const mirror_kernel& k);
+
+    // The boundary callback of a solver as a named type: `handle.exchange(q, pool);` and, for a wall-bounded solver, the
+    // `algs::boundary_fill(q, boundaries, kern)` that follows it (bc = exchange + boundary_fill).
     template <typename handle_t, typename group_t> struct exchange_bc_t
     {
         handle_t* handle;
         group_t*  group;
+        bool has_fill = false;
+        boundary::identifier_t which{};
+        spb_bc_desc bc{};
+        template <typename sol_arr_t> void fill(const sol_arr_t& q, double* ptr) const { if (has_fill) boundary_fill_ptr(q, ptr, which, bc); }
         template <typename sol_arr_t, typename time_t>
-        void operator()(sol_arr_t& q, const time_t&) const { handle->exchange(q, *group); }
+        void operator()(sol_arr_t& q, const time_t&) const { handle->exchange(q, *group); fill(q, dev_ptr(q)); check(spb_sync(nullptr), "spb_sync"); }
     };
     template <typename handle_t, typename group_t> inline exchange_bc_t<handle_t, group_t> exchange_bc(handle_t& h, group_t& g) { return exchange_bc_t<handle_t, group_t>{&h, &g}; }
+    template <typename handle_t, typename group_t>
+    inline exchange_bc_t<handle_t, group_t> exchange_bc(handle_t& h, group_t& g, const boundary::identifier_t& boundaries, const mirror_kernel& kern)
+    {
+        exchange_bc_t<handle_t, group_t> out{&h, &g};
+        out.has_fill = true; out.which = boundaries; out.bc = mirror_desc(kern);
+        return out;
+    }
 
     template <typename T> struct is_flux_div_rhs : std::false_type {};
     template <typename F> struct is_flux_div_rhs<flux_div_rhs_t<F>> : std::true_type {};
@@ -379,7 +397,7 @@ namespace spade::b200
         static mirror_kernel noslip_adiabatic() { mirror_kernel k; k.a[2] = k.a[3] = k.a[4] = -1.0; return k; }
         static mirror_kernel symmetry() { mirror_kernel k; k.use_normal = true; k.a_normal = -1.0; return k; }
     };
-    template <typename arr_t> inline void boundary_fill_desc(arr_t& arr, const boundary::identifier_t& boundaries, const spb_bc_desc& d)
+    template <typename arr_t> inline void boundary_fill_ptr(const arr_t& arr, double* ptr, const boundary::identifier_t& boundaries, const spb_bc_desc& d)
     {
         require_supported_array<arr_t>();
         const auto& grid = arr.get_grid();
@@ -390,17 +408,25 @@ namespace spade::b200
             std::vector<int64_t> blocks;
             for (const auto lb: geom.boundary_blocks[ib].data(device::cpu)) blocks.push_back((int64_t)lb);
             if (blocks.empty()) continue;
-            check(spb_boundary_fill(grid_handle(arr), dev_ptr(arr), ib/2, ib%2, blocks.data(), (int64_t)blocks.size(), &d, nullptr), "spb_boundary_fill");
+            check(spb_boundary_fill(grid_handle(arr), ptr, ib/2, ib%2, blocks.data(), (int64_t)blocks.size(), &d, nullptr), "spb_boundary_fill");
         }
+    }
+    template <typename arr_t> inline void boundary_fill_desc(arr_t& arr, const boundary::identifier_t& boundaries, const spb_bc_desc& d)
+    {
+        boundary_fill_ptr(arr, dev_ptr(arr), boundaries, d);
         check(spb_sync(nullptr), "spb_sync");
     }
-    template <typename arr_t> inline void boundary_fill(arr_t& arr, const boundary::identifier_t& boundaries, const mirror_kernel& k)
+    inline spb_bc_desc mirror_desc(const mirror_kernel& k)
     {
         spb_bc_desc d{};
         d.kind = SPB_BC_MIRROR;
         for (int v = 0; v < 5; ++v) { d.a[v] = k.a[v]; d.b[v] = k.b[v]; }
         d.use_normal = k.use_normal ? 1 : 0; d.a_normal = k.a_normal;
-        boundary_fill_desc(arr, boundaries, d);
+        return d;
+    }
+    template <typename arr_t> inline void boundary_fill(arr_t& arr, const boundary::identifier_t& boundaries, const mirror_kernel& k)
+    {
+        boundary_fill_desc(arr, boundaries, mirror_desc(k));
     }
     template <typename arr_t, const int order> inline void boundary_fill(arr_t& arr, const boundary::identifier_t& boundaries, const boundary::extrap_t<order>&)
     {
@@ -656,33 +682,22 @@ namespace spade::time_integration
             axis.time() = t_start + tfrac[i]*dt;
             if constexpr (b200::is_exchange_bc<boundary_t>::value)
             {
-                // the ghost cells fed by other ranks (other GPUs of this process): packed straight into the peers' buffers
-                if (ghosts_done && boundary.group->size() > 1) boundary.handle->exchange_messages(bufs[cur], *boundary.group);
-            }
-            if (cur == 0)
-            {
-                if (!ghosts_done) boundary(q, axis.time());
+                // the callback's work on the raw stage buffer (the result may sit in the scratch buffer): same-rank ghosts unless the
+                // kernel wrote them, the ghost cells fed by other ranks (other GPUs of this process: packed straight into the peers'
+                // buffers), then the wall fills of a channel solver
+                if (!ghosts_done) b200::check(spb_exchange_local(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local");
+                if (boundary.group->size() > 1) boundary.handle->exchange_messages(bufs[cur], *boundary.group);
+                boundary.fill(q, bufs[cur]);
             }
             else
             {
-                // the stage result sits in the scratch buffer: the boundary callback needs a SPADE array, so it is applied after
-                // the last stage only when the result is back in q; in between the fused ghost stores (or a device-side local
-                // exchange on the raw buffer) keep the ghosts current
-                if (!ghosts_done)
+                // opaque boundary callback: it needs a SPADE array, so the state is brought back into q first
+                if (cur == 1)
                 {
-                    if constexpr (b200::is_exchange_bc<boundary_t>::value)
-                    {
-                        b200::check(spb_exchange_local(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local");
-                        boundary.handle->exchange_messages(bufs[cur], *boundary.group);
-                    }
-                    else
-                    {
-                        // opaque boundary callback: bring the state back into q so that the callback sees a SPADE array
-                        cudaMemcpyAsync(bufs[0], bufs[1], sizeof(double)*nd, cudaMemcpyDeviceToDevice, nullptr);
-                        cur = 0;
-                        boundary(q, axis.time());
-                    }
+                    cudaMemcpyAsync(bufs[0], bufs[1], sizeof(double)*nd, cudaMemcpyDeviceToDevice, nullptr);
+                    cur = 0;
                 }
+                boundary(q, axis.time());
             }
         }
         if (cur == 1) cudaMemcpyAsync(bufs[0], bufs[1], sizeof(double)*nd, cudaMemcpyDeviceToDevice, nullptr);    // odd number of stages

@@ -1,5 +1,6 @@
 // Stretched-grid solver written against SPADE's own API (reference headers #included at build time only), BASELINE config 3
-// style: coords::diagonal_coords(scaled x, integrated_tanh_1D y, identity z), 2 exchange cells, rk4_t.
+// style: coords::diagonal_coords(scaled x, integrated_tanh_1D y, identity z), x/z periodic, no-slip isothermal walls in y
+// (exchange + boundary_fill), 2 exchange cells, rk4_t.
 //   A. the reference's generic CUDA path (flux_div tag `basic`) for the convective functor totani_lr — the only kind of
 //      functor the reference can evaluate on general coordinates (omni/infos/info_gradient.h:83), and only once the two
 //      parameter declarations of core/coord_system.h:255,274 are repaired (integration/Makefile does that on a temporary
@@ -7,7 +8,8 @@
 //   B. the drop-in (tag `b200`, b200::make_exchange) on the same grid object: the shim reads the mapping objects of the
 //      grid and hands the library its separable metric tables (spb_grid_set_metric);
 //   C. the drop-in running the config-3 functor (hybrid totani/fweno + ducros + visc_lr) on the same stretched grid with
-//      lambdas (flux_div + update + exchange) and with named callbacks (one fused kernel per stage): no reference
+//      lambdas (flux_div + update + exchange + boundary_fill) and with named callbacks (b200::exchange_bc(handle, pool,
+//      boundaries, wall): one fused kernel per stage, then the ghost copies and the wall fill on the stage buffer): no reference
 //      counterpart exists for the viscous / sensor terms, so C checks the two drop-in paths against each other.
 // Prints one JSON line. Usage: channel_curv_demo [blocks_per_dim=2] [cells_per_block=16] [steps=2]
 #include <chrono>
@@ -17,6 +19,18 @@
 #include <vector>
 #include "spade.h"
 #include "spade_b200_shim.hpp"
+
+// The reference never initialises the "not a domain boundary" flags of its block arrangement (core/bounding_box.h:20,
+// grid/cartesian_blocks.h:53,58-65), so the pruning of non-periodic neighbours in grid/exchange_config.h:336-342 reads heap
+// garbage and a wall-bounded grid can lose transactions from run to run. As in oracle/ref_driver.cc, zero-filled heap blocks
+// give the evidently intended `false`; nothing in the reference is changed.
+#include <new>
+void* operator new(std::size_t n) { void* p = std::calloc(1, n ? n : 1); if (!p) std::abort(); return p; }
+void* operator new[](std::size_t n) { return ::operator new(n); }
+void operator delete(void* p) noexcept { std::free(p); }
+void operator delete[](void* p) noexcept { std::free(p); }
+void operator delete(void* p, std::size_t) noexcept { std::free(p); }
+void operator delete[](void* p, std::size_t) noexcept { std::free(p); }
 
 using real_t = double;
 using prim_t = spade::fluid_state::prim_t<real_t>;
@@ -45,7 +59,15 @@ int main(int argc, char** argv)
         spade::coords::diagonal_coords coords(xc, yc, zc);
         spade::grid::cartesian_blocks_t blocks(num_blocks, bounds);
         spade::grid::cartesian_grid_t grid(cells, blocks, coords, pool);
-        spade::ctrs::array<bool, 3> periodic(true, true, true);
+        spade::ctrs::array<bool, 3> periodic(true, false, true);            // walls in y
+        const auto walls = spade::boundary::ymin || spade::boundary::ymax;
+        const auto wall_b200 = spade::b200::mirror_kernel::noslip_isothermal(t0);
+        const auto wall_ref  = [=] _sp_hybrid (const prim_t& q_image, const int idir)
+        {
+            prim_t g;
+            g.p() = q_image.p(); g.T() = 2.0*t0 - q_image.T(); g.u() = -q_image.u(); g.v() = -q_image.v(); g.w() = -q_image.w();
+            return g;
+        };
         spade::fluid_state::ideal_gas_t<real_t> air(gamma, rgas);
         spade::viscous_laws::constant_viscosity_t<real_t> vlaw(mu, 0.72);
         spade::convective::totani_lr tscheme(air);
@@ -98,13 +120,13 @@ int main(int argc, char** argv)
                 cudaMemcpy(out.data(), &sol.data[0], sizeof(real_t)*out.size(), cudaMemcpyDeviceToHost);
             };
             if constexpr (mode == 2)
-                go(spade::b200::flux_div_rhs(flux_func), spade::b200::exchange_bc(new_handle, pool));
+                go(spade::b200::flux_div_rhs(flux_func), spade::b200::exchange_bc(new_handle, pool, walls, wall_b200));
             else if constexpr (mode == 1)
                 go([&](auto& rr, const auto& qq, const auto&) { spade::pde_algs::flux_div(qq, rr, flux_func, spade::algs::make_traits(spade::pde_algs::b200, spade::pde_algs::overwrite)); },
-                   [&](auto& qq, const auto&) { new_handle.exchange(qq, pool); });
+                   [&](auto& qq, const auto&) { new_handle.exchange(qq, pool); spade::b200::boundary_fill(qq, walls, wall_b200); });
             else
                 go([&](auto& rr, const auto& qq, const auto&) { spade::pde_algs::flux_div(qq, rr, flux_func, spade::algs::make_traits(spade::pde_algs::basic, spade::pde_algs::overwrite)); },
-                   [&](auto& qq, const auto&) { ref_handle.exchange(qq, pool); });
+                   [&](auto& qq, const auto&) { ref_handle.exchange(qq, pool); spade::algs::boundary_fill(qq, walls, wall_ref); });
         };
         auto rel = [](const std::vector<real_t>& a, const std::vector<real_t>& b)
         {
