@@ -583,6 +583,14 @@ class arr_exchange_t:
 
     def __del__(self):
         try:
+            if getattr(self, "_p2p", None):
+                for bufs, flags in self._remote.values():
+                    for b in list(bufs) + [flags]:
+                        lib().spb_ipc_close(b)
+                for bufs, flags in self._own.values():
+                    for b in list(bufs) + [flags]:
+                        lib().spb_dev_free(b)
+                self._p2p = False
             if getattr(self, "_h", None):
                 lib().spb_exchange_destroy(self._h)
                 self._h = None
