@@ -91,19 +91,25 @@ extern "C"
             for (int d = 0; d < 3; ++d)
             {
                 double* row = tab.data() + ((size_t)lb*3 + d)*3*lm;
+                // Only the entries of interior cells and of their faces are ever read (a face's tangential metrics are those of
+                // the interior cell row it belongs to). A mapping may fold or flatten beyond the domain boundary
+                // (integrated_tanh_1D does): entries out there are kept when usable and neutralised otherwise.
+                const int lo = g->ng[d], hi = g->ng[d] + g->nx[d];
+                auto usable = [](const double x) { return x != 0.0 && std::isfinite(x); };
                 for (int i = 0; i < g->np[d]; ++i)
                 {
                     const double a = m->area[d][lb*g->np[d] + i], j = m->jac[d][lb*g->np[d] + i];
-                    // (a mapping may fold beyond the domain boundary — integrated_tanh_1D does — so ghost entries can be negative)
-                    if (!(a != 0.0) || !(j != 0.0) || !std::isfinite(a) || !std::isfinite(j)) { spb::set_error("spb_grid_set_metric: coordinate derivatives must be finite and nonzero"); return SPB_ERR_BAD_ARG; }
-                    row[i] = a;
-                    row[lm + i] = 1.0/j;
+                    const bool used = i >= lo && i < hi;
+                    if (used && (!usable(a) || !usable(j))) { spb::set_error("spb_grid_set_metric: coordinate derivatives of interior cells must be finite and nonzero"); return SPB_ERR_BAD_ARG; }
+                    row[i] = usable(a) ? a : 1.0;
+                    row[lm + i] = usable(j) ? 1.0/j : 1.0;
                 }
                 for (int i = 0; i <= g->np[d]; ++i)
                 {
                     const double f = m->face[d][lb*(g->np[d] + 1) + i];
-                    if (!(f != 0.0) || !std::isfinite(f)) { spb::set_error("spb_grid_set_metric: coordinate derivatives must be finite and nonzero"); return SPB_ERR_BAD_ARG; }
-                    row[2*lm + i] = 1.0/f;
+                    const bool used = i >= lo && i <= hi;
+                    if (used && !usable(f)) { spb::set_error("spb_grid_set_metric: coordinate derivatives at the faces of interior cells must be finite and nonzero"); return SPB_ERR_BAD_ARG; }
+                    row[2*lm + i] = usable(f) ? 1.0/f : 1.0;
                 }
             }
         if (g->nlb == 0) return 0;

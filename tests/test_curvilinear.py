@@ -314,3 +314,18 @@ def test_python_coordinate_mirror_matches_the_oracle_mappings():
                 xa = port.coord_map(cd, d, xc) if metric_at == "physical" else xc
                 assert np.isclose(area[d][lb, i + ng], port.coord_deriv(cd, d, xa), rtol=1e-13)
                 assert np.isclose(face[d][lb, i + ng], port.coord_deriv(cd, d, lo + i * dx), rtol=1e-14)
+
+
+@pytest.mark.gpu
+def test_cuda_mapping_that_degenerates_beyond_the_wall_is_accepted():
+    """quad_1D has dz/dzeta = 2 zeta = 0 at zeta = 0: with 4 exchange cells of width 0.125 below zeta = 0.5 the outermost ghost
+    FACE sits exactly there (and integrated_tanh_1D folds beyond |eta| = 1.2). Only the entries of interior cells and their
+    faces are read by the kernels, so the grid must be accepted and cent_keep<8> + visc_lr must still match the oracle."""
+    from oracle import ref
+    nb, n, ng = (1, 1, 2), (12, 20, 6), 4
+    bounds = [0.0, 2 * np.pi, -1.0, 1.0, 0.5, 2.0]
+    maps = (("scaled", 2.0), ("tanh", -1.0, 1.0, 0.1, 4.0), ("quad",))
+    q = make_state(nb, n, ng, seed=14, bounds=bounds)
+    want = oracle_flux_div(oracle_cfg(nb, n, ng, scheme=14, bounds=bounds), ref.make_coords(maps), q)
+    got = run_product(nb, n, ng, q, 14, bounds, maps)
+    assert rel_l2(got, want) < TOL
