@@ -34,7 +34,7 @@ for coords_on in (False, True):
     tg.advance()
     print("ok generic", float(tg.solution().data.abs().max()), flush=True)
 PY
-for tool in memcheck racecheck; do
+for tool in ${SAN_TOOLS:-memcheck racecheck}; do
   timeout 420 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_case2.py > $O/sanitizer2_$tool.log 2>&1; echo "$tool rc=$?"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok|Error|hazard|Invalid" $O/sanitizer2_$tool.log | head -30
 done
