@@ -13,8 +13,8 @@ except Exception as e:
     print('$name failed', e); print(open('$O/bench_mg4_$name.err').read()[-600:])
 PY
 }
+# (a variant with NCCL_P2P_USE_CUDA_MEMCPY=1 hung until the timeout on this NCCL build and was removed)
 run base SPB_NCCL_HIGH_PRIO=1
-run cememcpy SPB_NCCL_HIGH_PRIO=1 NCCL_P2P_USE_CUDA_MEMCPY=1
 run chan8 SPB_NCCL_HIGH_PRIO=1 NCCL_MIN_P2P_NCHANNELS=8 NCCL_MAX_P2P_NCHANNELS=8
 run chan1 SPB_NCCL_HIGH_PRIO=1 NCCL_MIN_P2P_NCHANNELS=1 NCCL_MAX_P2P_NCHANNELS=1
 run onestream SPB_NCCL_HIGH_PRIO=1 SPB_TWO_STREAMS=0
