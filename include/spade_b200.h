@@ -152,9 +152,10 @@ int spb_flux_div_rk_stage(const spb_grid* g, const double* q_in_dev, double* q_o
  * (the same-rank transactions of `exch`, reference src/grid/make_exchange.h:166-203): after the call q_out needs no
  * spb_exchange_local, only the messages of other ranks (spb_exchange_pack / unpack). The ghost values are bit-identical
  * to a separate exchange of q_out. With lb_begin/lb_end the ghost cells fed by blocks outside the range are not
- * written. SPB_ERR_UNSUPPORTED if the plan holds same-rank transactions other than the 26 canonical injection
- * boxes or the number of exchange cells along i is odd; the caller then uses spb_flux_div_rk_stage +
- * spb_exchange_local. exch == NULL is spb_flux_div_rk_stage. */
+ * written. The one-ghost-cell functor set sends the ghosts from a dedicated warp (TMA stores of the staged plane; 2 exchange
+ * cells along i), every other functor set stores them from the threads that own the cells (any number of exchange cells).
+ * SPB_ERR_UNSUPPORTED if the plan holds same-rank transactions other than the 26 canonical injection boxes (AMR
+ * interpolation); the caller then uses spb_flux_div_rk_stage + spb_exchange_local. exch == NULL is spb_flux_div_rk_stage. */
 typedef struct spb_exchange spb_exchange;
 int spb_flux_div_rk_stage_exchange(const spb_grid* g, const double* q_in_dev, double* q_out_dev, const spb_flux_desc* flux,
                                    const spb_stage_desc* stage, spb_exchange* exch, int64_t lb_begin, int64_t lb_end,

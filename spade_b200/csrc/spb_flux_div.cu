@@ -22,7 +22,7 @@ extern "C"
         if (lb_begin < 0 || lb_end > g->nlb || lb_begin > lb_end) { set_error("spb_flux_div: bad block range"); return SPB_ERR_BAD_ARG; }
         const FluxParams P = make_params(f);
         cudaStream_t st = (cudaStream_t)stream;
-        if (f->sgs == SPB_SGS_WALE) return flux_div_sgs(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr);
+        if (f->sgs == SPB_SGS_WALE) return flux_div_sgs(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr, nullptr);
         if (f->sgs != SPB_SGS_NONE) { set_error("spb_flux_div: unknown SGS model"); return SPB_ERR_BAD_ARG; }
         if (g->metric_dev)
         {
@@ -36,7 +36,7 @@ extern "C"
             SPB_NARROW(SPB_CONV_NONE,   1);
 #undef SPB_NARROW
             if (rc != SPB_ERR_UNSUPPORTED) return rc;
-            return flux_div_curv(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr);
+            return flux_div_curv(g, q_dev, rhs_dev, f, P, increment, lb_begin, lb_end, st, nullptr, nullptr, nullptr);
         }
 #define SPB_CASE(C, D, V) if (f->conv == C && f->diss == D && (f->visc != 0) == (V != 0)) \
             return launch_fdiv<C, D, V>(g, q_dev, rhs_dev, P, increment, lb_begin, lb_end, st)
@@ -93,22 +93,19 @@ extern "C"
 #undef SPB_NARROW
             if (rc != SPB_ERR_UNSUPPORTED) return rc;
         }
-        if (g->metric_dev || f->sgs == SPB_SGS_WALE)
-        {
-            if (exch) { set_error("spb_flux_div_rk_stage_exchange: ghost fusion is implemented for identity coordinates without an SGS model (use spb_flux_div_rk_stage + spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
-            if (f->sgs == SPB_SGS_WALE) return flux_div_sgs(g, q_in, sd->out, f, P, 0, lb_begin, lb_end, st, q_out, &S);
-            return flux_div_curv(g, q_in, sd->out, f, P, 0, lb_begin, lb_end, st, q_out, &S);
-        }
+        // wide stencils, the WALE closure and general coordinates on the wide kernel: the same-rank ghost cells are stored by the
+        // threads that own the source cells (no separate spb_exchange_local), for any number of exchange cells
+        if (f->sgs == SPB_SGS_WALE) return flux_div_sgs(g, q_in, sd->out, f, P, 0, lb_begin, lb_end, st, q_out, &S, exch);
+        if (g->metric_dev) return flux_div_curv(g, q_in, sd->out, f, P, 0, lb_begin, lb_end, st, q_out, &S, exch);
 #define SPB_NARROW(C, V) if (f->conv == C && f->diss == SPB_DISS_NONE && (f->visc != 0) == (V != 0)) \
             return launch_fdiv_narrow<C, V>(g, q_in, sd->out, P, 0, lb_begin, lb_end, st, q_out, &S, exch)
         SPB_NARROW(SPB_CONV_TOTANI, 1);
         SPB_NARROW(SPB_CONV_TOTANI, 0);
         SPB_NARROW(SPB_CONV_NONE,   1);
 #undef SPB_NARROW
-        // wide stencils: the stage update rides on the rhs kernel; no ghost fusion there (the caller runs spb_exchange_local)
-        if (exch) { set_error("spb_flux_div_rk_stage_exchange: ghost fusion is implemented for the one-ghost-cell functor set (use spb_flux_div_rk_stage + spb_exchange_local)"); return SPB_ERR_UNSUPPORTED; }
+        // wide stencils: the stage update rides on the rhs kernel; with a plan the owning threads also store the same-rank ghosts
 #define SPB_WIDE(C, D) if (f->conv == C && f->diss == D && f->visc != 0) \
-            return launch_fdiv<C, D, 1, true>(g, q_in, sd->out, P, 0, lb_begin, lb_end, st, q_out, &S)
+            return launch_fdiv<C, D, 1, true>(g, q_in, sd->out, P, 0, lb_begin, lb_end, st, q_out, &S, exch)
         SPB_WIDE(SPB_CONV_TOTANI,     SPB_DISS_FWENO);
         SPB_WIDE(SPB_CONV_CENT_KEEP4, SPB_DISS_NONE);
         SPB_WIDE(SPB_CONV_CENT_KEEP4, SPB_DISS_FWENO);

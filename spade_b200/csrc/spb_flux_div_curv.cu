@@ -7,10 +7,10 @@
 namespace spb
 {
     int flux_div_curv(const spb_grid* g, const double* q, double* rhs, const spb_flux_desc* f, const FluxParams& P, int increment,
-                      int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage)
+                      int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage, spb_exchange* exch)
     {
 #define SPB_CASE(C, D, V) if (f->conv == C && f->diss == D && (f->visc != 0) == (V != 0)) \
-            return stage ? launch_fdiv<C, D, V, true,  true>(g, q, rhs, P, 0, lb_begin, lb_end, stream, q_out, stage) \
+            return stage ? launch_fdiv<C, D, V, true,  true>(g, q, rhs, P, 0, lb_begin, lb_end, stream, q_out, stage, exch) \
                          : launch_fdiv<C, D, V, false, true>(g, q, rhs, P, increment, lb_begin, lb_end, stream)
         SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_NONE,  1);
         SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_NONE,  0);

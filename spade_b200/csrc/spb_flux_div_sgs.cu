@@ -8,10 +8,10 @@ namespace spb
 {
     template <bool CURV>
     static int sgs_dispatch(const spb_grid* g, const double* q, double* rhs, const spb_flux_desc* f, const FluxParams& P, int increment,
-                            int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage)
+                            int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage, spb_exchange* exch)
     {
 #define SPB_CASE(C, D) if (f->conv == C && f->diss == D) \
-            return stage ? launch_fdiv<C, D, 1, true,  CURV, true>(g, q, rhs, P, 0, lb_begin, lb_end, stream, q_out, stage) \
+            return stage ? launch_fdiv<C, D, 1, true,  CURV, true>(g, q, rhs, P, 0, lb_begin, lb_end, stream, q_out, stage, exch) \
                          : launch_fdiv<C, D, 1, false, CURV, true>(g, q, rhs, P, increment, lb_begin, lb_end, stream)
         SPB_CASE(SPB_CONV_TOTANI,     SPB_DISS_NONE);
         SPB_CASE(SPB_CONV_NONE,       SPB_DISS_NONE);
@@ -24,11 +24,11 @@ namespace spb
     }
 
     int flux_div_sgs(const spb_grid* g, const double* q, double* rhs, const spb_flux_desc* f, const FluxParams& P, int increment,
-                     int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage)
+                     int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage, spb_exchange* exch)
     {
         if (!f->visc) { set_error("spb_flux_div: an SGS model needs visc_lr"); return SPB_ERR_BAD_ARG; }
         if (!(f->sgs_prt > 0.0)) { set_error("spb_flux_div: wale_t needs a positive turbulent Prandtl number"); return SPB_ERR_BAD_ARG; }
-        return g->metric_dev ? sgs_dispatch<true>(g, q, rhs, f, P, increment, lb_begin, lb_end, stream, q_out, stage)
-                             : sgs_dispatch<false>(g, q, rhs, f, P, increment, lb_begin, lb_end, stream, q_out, stage);
+        return g->metric_dev ? sgs_dispatch<true>(g, q, rhs, f, P, increment, lb_begin, lb_end, stream, q_out, stage, exch)
+                             : sgs_dispatch<false>(g, q, rhs, f, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
     }
 }

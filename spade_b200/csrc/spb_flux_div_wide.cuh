@@ -71,7 +71,7 @@ namespace spb
     __global__ void __launch_bounds__(FdivSmem<stencil_halo<CONV, DISS>::value>::NT, 2)
     flux_div_kernel(const __grid_constant__ CUtensorMap tmap_q, double* __restrict__ rhs, const FluxParams P,
                     const FdivDims G, const double* __restrict__ inv_dx_tab, double* __restrict__ q_out, const StageParams ST,
-                    const double* __restrict__ met)
+                    const double* __restrict__ met, const int* __restrict__ nbr)
     {
         constexpr int H = stencil_halo<CONV, DISS>::value;
         using S = FdivSmem<H>;
@@ -241,8 +241,40 @@ namespace spb
                     const double ir = rcp_nr(rho);
                     const double un = ir*mx, vn = ir*my, wn = ir*mz;
                     const double pn = ST.gm1*fma(-0.5*rho, fma(un, un, fma(vn, vn, wn*wn)), rhoE);
+                    const double Tn = pn*ir*ST.inv_R;
                     double* qo = q_out + c;
-                    qo[0] = pn; qo[1] = pn*ir*ST.inv_R; qo[2] = un; qo[3] = vn; qo[4] = wn;
+                    qo[0] = pn; qo[1] = Tn; qo[2] = un; qo[3] = vn; qo[4] = wn;
+                    if (nbr)
+                    {
+                        // Fused same-rank ghost exchange (make_exchange.h:166-203): a cell of the source box of direction e goes to
+                        // cell (i - ex n0, j - ey n1, k - ez n2) of neighbour e (get_transaction.h:54-86). Only the cells of the
+                        // block's outer shell take part; nbr[27 lb + e] is the destination block or -1 (spb_exchange.cu).
+                        const int ci = i0 + il, cj = j0 + jl, ck = k - 1;
+                        const bool xl = ci < G.ng[0], xh = ci >= G.nx[0] - G.ng[0];
+                        const bool yl = cj < G.ng[1], yh = cj >= G.nx[1] - G.ng[1];
+                        const bool zl = ck < G.ng[2], zh = ck >= G.nx[2] - G.ng[2];
+                        if (xl || xh || yl || yh || zl || zh)
+                        {
+                            const int* nb = nbr + 27*lb;
+                            // the directions a cell takes part in form a contiguous range per axis: {-1 if low} + {0} + {+1 if high}
+                            for (int ez = zl ? -1 : 0; ez <= (zh ? 1 : 0); ++ez)
+                            {
+                                for (int ey = yl ? -1 : 0; ey <= (yh ? 1 : 0); ++ey)
+                                {
+                                    for (int ex = xl ? -1 : 0; ex <= (xh ? 1 : 0); ++ex)
+                                    {
+                                        if (ex == 0 && ey == 0 && ez == 0) continue;
+                                        const int dst = nb[(ex + 1) + 3*(ey + 1) + 9*(ez + 1)];
+                                        if (dst < 0) continue;
+                                        double* o = q_out + dst*G.block_stride
+                                            + 5ll*((ci - ex*G.nx[0] + G.ng[0]) + (long long)G.np[0]*((cj - ey*G.nx[1] + G.ng[1])
+                                            + (long long)G.np[1]*(ck - ez*G.nx[2] + G.ng[2])));
+                                        o[0] = pn; o[1] = Tn; o[2] = un; o[3] = vn; o[4] = wn;
+                                    }
+                                }
+                            }
+                        }
+                    }
                 }
             }
 
@@ -313,7 +345,8 @@ namespace spb
 
     template <int CONV, int DISS, int VISC, bool FUSED = false, bool CURV = false, bool SGS = false>
     static int launch_fdiv(const spb_grid* g, const double* q, double* rhs, const FluxParams& P, int increment,
-                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out = nullptr, const StageParams* stage = nullptr)
+                           int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out = nullptr, const StageParams* stage = nullptr,
+                           spb_exchange* exch = nullptr)
     {
         constexpr int H = stencil_halo<CONV, DISS>::value;
         using S = FdivSmem<H>;
@@ -341,6 +374,9 @@ namespace spb
         G.lb0 = lb_begin;
         G.increment = increment;
         G.lm = g->metric_lm;
+        // fused same-rank ghost exchange: the neighbour table of the plan (refused for plans with non-canonical transactions)
+        const int* nbr_tab = nullptr;
+        if (FUSED && exch) { int rc = exchange_fuse_table(exch, g->nx, g->ng, g->nlb, &nbr_tab); if (rc) return rc; }
         if (CURV && !g->metric_dev) { set_error("spb_flux_div: general-coordinate kernel without a metric (spb_grid_set_metric)"); return SPB_ERR_BAD_ARG; }
         const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
         if (nblk <= 0) return 0;
@@ -348,7 +384,7 @@ namespace spb
         StageParams SP{};
         if (stage) SP = *stage;
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-        kern<<<(unsigned)nblk, S::NT, S::BYTES, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP, g->metric_dev);
+        kern<<<(unsigned)nblk, S::NT, S::BYTES, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP, g->metric_dev, nbr_tab);
         SPB_LAUNCH_CHECK();
         return 0;
     }
@@ -369,8 +405,8 @@ namespace spb
 
     // LES closure visc_lr<sgs_visc_t<constant_viscosity_t, wale_t>> (spb_flux_div_sgs.cu): identity and general coordinates
     int flux_div_sgs(const spb_grid* g, const double* q, double* rhs, const spb_flux_desc* f, const FluxParams& P, int increment,
-                     int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage);
+                     int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage, spb_exchange* exch);
     // general coordinates (spb_flux_div_curv.cu): every functor combination through the wide kernel with CURV = true
     int flux_div_curv(const spb_grid* g, const double* q, double* rhs, const spb_flux_desc* f, const FluxParams& P, int increment,
-                      int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage);
+                      int64_t lb_begin, int64_t lb_end, cudaStream_t stream, double* q_out, const StageParams* stage, spb_exchange* exch);
 }

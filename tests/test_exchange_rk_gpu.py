@@ -216,3 +216,37 @@ def test_checkpoint_file_is_the_reference_byte_order(tmp_path):
     part = sp2.grid_array(grid2, 0.0)
     sp2.io.binary_read(f, part)
     assert np.array_equal(part.to_host(), q[grid2.first_block:grid2.first_block + grid2.num_local_blocks])
+
+
+@pytest.mark.parametrize("scheme,ng", [(1, 2), (2, 2), (12, 2), (13, 3), (14, 4)])
+@pytest.mark.parametrize("nb,n,periodic", [((2, 1, 2), (40, 12, 8), (1, 1, 1)), ((3, 2, 1), (32, 8, 16), (1, 0, 1)),
+                                           ((1, 1, 1), (16, 16, 16), (1, 1, 1))])
+def test_wide_fused_stage_kernel_fills_same_rank_ghosts_bit_exact(scheme, ng, nb, n, periodic):
+    """The wide-stencil stage kernels (hybrid WENO, cent_keep<4|6|8>, WALE closure) with an exchange plan: the threads that own
+    the cells of a block's outer shell also store them into the neighbours' ghost cells, for 2, 3 and 4 exchange cells. Ghosts
+    bit-identical to an exchange of the result, everything bit-identical to the kernel followed by a separate exchange."""
+    from oracle import port
+    q0 = make_state(nb, n, ng, seed=37, jump=scheme in (1, 12))
+    cfg = oracle_cfg(nb, n, ng, scheme=scheme, integrator=0, periodic=periodic)
+    dt = 0.2 * (2 * np.pi / (nb[0] * n[0])) / port.reduce_umax(cfg, q0.ravel())
+    sp, blocks, grid = product_setup(nb, n, ng)
+    gas = sp.ideal_gas_t(GAMMA, RGAS)
+    results = []
+    for bc_object in (True, False):
+        qa = sp.grid_array.from_host(grid, q0, (ng,) * 3)
+        ra = sp.grid_array(grid, 0.0, (ng,) * 3)
+        ex = sp.make_exchange(qa, periodic)
+        ti = sp.integrator_t(sp.time_axis_t(0.0, dt), sp.rk4_t, sp.integrator_data_t(qa, ra, sp.rk4_t),
+                             sp.flux_div_rhs_t(product_flux(scheme), sp.overwrite),
+                             sp.exchange_bc_t(ex) if bc_object else (lambda qq, t: ex.exchange(qq)), sp.state_transform_t(gas))
+        n0 = sp.launch_count()
+        ti.advance()
+        ti.advance()
+        if bc_object:
+            assert ti._fuse_exchange and sp.launch_count() - n0 == 2 * 4
+        results.append(ti.solution().to_host())
+    got, sep = results
+    assert np.array_equal(got, sep)
+    assert np.array_equal(got, port.exchange(cfg, got.ravel()).reshape(got.shape))
+    want = port.advance(cfg, q0.ravel(), dt, 2).reshape(q0.shape)
+    assert rel_l2(interior(got, ng), interior(want, ng)) < 1e-12
