@@ -75,3 +75,27 @@ def test_host_mirror_tables_match_reference_rk_tables():
         assert abs(float(sum(alg.accum)) - 1.0) < 1e-15                              # consistency of every table
         for row, c in zip(alg.table, alg.dt):
             assert sum(row) == c
+
+
+def test_shim_recognises_every_functor_type_of_the_implemented_set():
+    """integration/api_surface_check.cc (compiled in the dev container against the unmodified reference headers + the shim):
+    spade::b200::flux_desc over every functor type; the POD descriptor must carry the functor's own members. Host-only."""
+    import subprocess
+    exe = os.path.join(ROOT, "integration", "_build", "api_surface_check")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build/api_surface_check not built (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60, cwd=os.path.dirname(exe))
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = {}
+    for line in out.stdout.strip().splitlines():
+        name, rest = line[:44].strip(), line[44:].split()
+        rows[name] = dict(kv.split("=") for kv in rest)
+    assert len(rows) == 13
+    assert rows["totani_lr"]["conv"] == "1" and rows["cent_keep<2>"]["conv"] == "1"
+    assert rows["cent_keep<6> + visc_lr"]["conv"] == "4" and rows["cent_keep<8>"]["conv"] == "5"
+    assert rows["fweno_t"]["conv"] == "3" and rows["weno_t<rusanov_t>"]["conv"] == "3"
+    w = rows["hybrid(totani, fweno, ducros, full) + wale"]
+    assert (w["diss"], w["blend"], w["visc"], w["sgs"], w["cw"], w["delta"], w["prt"], w["eps"]) == ("1", "0", "1", "1", "0.55", "0.1", "0.9", "0.01")
+    assert rows["hybrid(cent_keep<4>, fweno, ducros, diss)"]["blend"] == "1"
+    assert rows["hybrid(totani, weno_t<rusanov_t>, ducros)"]["diss"] == "1"
+    assert float(rows["visc_lr"]["beta"]) == pytest.approx(-2.0 * 1.8e-5 / 3.0, rel=1e-5)
