@@ -197,3 +197,18 @@ def test_generic_integrate_advance_bit_exact(ref_lib, integ, hs):
     want = ref_lib.advance_generic(cfg, q0, 1e-5, 2, hs)
     assert np.array_equal(port.advance_generic(cfg, q0, 1e-5, 2, hs), want)
     assert rel_l2(want, q0) > 1e-5
+
+
+@pytest.mark.parametrize("ng", [1, 3, 4])
+@pytest.mark.parametrize("periodic", [(1, 1, 1), (1, 0, 1)])
+def test_exchange_with_other_exchange_depths_bit_exact(ref_lib, ng, periodic):
+    """1, 3 and 4 exchange cells (visc_lr alone, cent_keep<6>, cent_keep<8>): ghost fill and tables against the reference."""
+    from oracle import port
+    nb, n = (2, 2, 1), (8, 4, 4)
+    q = zero_ghosts(make_state(nb, n, ng, seed=4), ng)
+    cfg = oracle_cfg(nb, n, ng, periodic=periodic, nranks=2)
+    assert np.array_equal(port.exchange(cfg, q.ravel()), ref_lib.exchange(cfg, q.ravel()))
+    for rank in range(2):
+        s0, r0, o0 = ref_lib.exchange_tables(cfg, rank)
+        s1, r1, o1 = port.exchange_tables(cfg, rank)
+        assert np.array_equal(s0, s1) and np.array_equal(r0, r1) and np.array_equal(o0, o1)
