@@ -1,0 +1,131 @@
+"""Manufactured-solution order check (the reference's closest thing to a known-answer test is development/mms/main.cc —
+trig fields for p, T, u, v, w, analytic -div(F_conv) and div(tau), observed order over a sequence of grids; it checks orders,
+not values). Independent sanity test of the physics: the oracle restatement (bit-exact against the reference, and the 1e-12
+yardstick of the CUDA path) must converge to the analytic right-hand side at the design order of each functor, on uniform
+and on stretched (diagonal_coords) grids. CPU only; the analytic RHS comes from sympy.
+
+Fields as development/mms/main.cc:61-65 with alpha = 1 on the periodic box [0, 2 pi)^3 (2 pi-periodic, positive p and T)."""
+import numpy as np
+import pytest
+
+from util import interior, oracle_cfg
+
+GAMMA, RGAS, MU, PR = 1.4, 287.15, 0.5, 0.72
+
+
+def build_analytic():
+    import sympy as sy
+    x, y, z = sy.symbols("x y z")
+    p = 5.0 + 2.0 * sy.cos(3 * x) * sy.sin(2 * y) + sy.sin(4 * z)
+    T = 10.0 + 2.0 * sy.cos(2 * x) * sy.sin(3 * y) + sy.sin(4 * z)
+    u = sy.sin(3 * x) * sy.cos(2 * y) * sy.cos(2 * z)
+    v = sy.cos(3 * x) * sy.cos(2 * y) * sy.cos(3 * z)
+    w = sy.sin(3 * x) * sy.sin(2 * y) * sy.cos(4 * z)
+    vel, X = [u, v, w], [x, y, z]
+    rho = p / (RGAS * T)
+    Et = RGAS * T / (GAMMA - 1.0) + 0.5 * (u * u + v * v + w * w)
+    # convective: rhs = -div F, F_d = (rho u_d, (rho Et + p) u_d, rho u u_d + p delta_xd, ...)
+    conv = [-sum(sy.diff(rho * vel[d], X[d]) for d in range(3)),
+            -sum(sy.diff((rho * Et + p) * vel[d], X[d]) for d in range(3))]
+    for c in range(3):
+        conv.append(-sum(sy.diff(rho * vel[c] * vel[d], X[d]) for d in range(3)) - sy.diff(p, X[c]))
+    # viscous (viscous.h:39-80): rhs = +div tau (momentum), +div(u.tau + cond grad T) (energy); beta = -2 mu / 3
+    div = sum(sy.diff(vel[d], X[d]) for d in range(3))
+    tau = [[MU * (sy.diff(vel[i], X[j]) + sy.diff(vel[j], X[i])) + (-2.0 * MU / 3.0 * div if i == j else 0) for j in range(3)] for i in range(3)]
+    cond = (GAMMA * RGAS / (GAMMA - 1.0)) * (MU / PR)
+    visc = [sy.Integer(0),
+            sum(sy.diff(sum(vel[i] * tau[i][d] for i in range(3)) + cond * sy.diff(T, X[d]), X[d]) for d in range(3))]
+    for c in range(3):
+        visc.append(sum(sy.diff(tau[c][d], X[d]) for d in range(3)))
+    f = lambda e: sy.lambdify((x, y, z), e, "numpy")
+    return dict(state=[f(e) for e in (p, T, u, v, w)], conv=[f(e) for e in conv], visc=[f(e) for e in visc])
+
+
+@pytest.fixture(scope="module")
+def analytic():
+    return build_analytic()
+
+
+def _grid(nb, n, ng, bounds, maps):
+    """physical cell-centre coordinates of every padded cell, [nlb] lists of (X, Y, Z) meshes in the array's index order"""
+    from oracle import port, ref
+    cd = ref.make_coords(maps, metric_at_physical=False) if maps else None
+    out = []
+    for lb in range(nb[0] * nb[1] * nb[2]):
+        b = (lb % nb[0], (lb // nb[0]) % nb[1], lb // (nb[0] * nb[1]))
+        ax = []
+        for d in range(3):
+            bs = (bounds[2 * d + 1] - bounds[2 * d]) / nb[d]
+            lo = bounds[2 * d] + b[d] * bs
+            xc = lo + (np.arange(-ng, n[d] + ng) + 0.5) * (bs / n[d])
+            ax.append(np.array([port.coord_map(cd, d, t) for t in xc]) if cd is not None else xc)
+        Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+        out.append((X, Y, Z))
+    return cd, out
+
+
+def _error(analytic, scheme, which, ncell, ng, maps=None):
+    from oracle import port
+    nb, n = (2, 1, 1), (ncell // 2, ncell, ncell)
+    two_pi = 2 * np.pi
+    # stretched case: x = 2 xi on [0, pi), y and z identity: still periodic in physical space
+    bounds = [0.0, np.pi if maps else two_pi, 0.0, two_pi, 0.0, two_pi]
+    cd, meshes = _grid(nb, n, ng, bounds, maps)
+    q = np.zeros((2, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng, 5))
+    want = np.zeros_like(q)
+    for lb, (X, Y, Z) in enumerate(meshes):
+        for v in range(5):
+            q[lb, ..., v] = analytic["state"][v](X, Y, Z)
+            want[lb, ..., v] = np.broadcast_to(analytic[which][v](X, Y, Z), X.shape)
+    cfg = oracle_cfg(nb, n, ng, scheme=scheme, mu=MU, prandtl=PR, bounds=bounds)
+    port.set_coords(cd)
+    try:
+        got = port.flux_div(cfg, q.ravel()).reshape(q.shape)
+    finally:
+        port.set_coords(None)
+    d = interior(got, ng) - interior(want, ng)
+    return float(np.sqrt((d ** 2).mean()) / np.sqrt((interior(want, ng) ** 2).mean()))
+
+
+@pytest.mark.parametrize("scheme,which,ng,order,sizes", [
+    (3, "conv", 2, 2, (16, 32, 64)),      # totani_lr
+    (4, "visc", 2, 2, (16, 32, 64)),      # visc_lr
+    (7, "conv", 2, 4, (16, 32, 64)),      # cent_keep<4>
+    (15, "conv", 3, 6, (48, 64, 96)),     # cent_keep<6>: 5.4, 5.7, 5.8 -> 6 over 32..96 cells (wavenumber-4 fields)
+    (16, "conv", 4, 8, (48, 64, 96)),     # cent_keep<8>: 7.0, 7.5, 7.7 -> 8
+])
+def test_observed_order_on_a_uniform_grid(analytic, scheme, which, ng, order, sizes):
+    errs = [_error(analytic, scheme, which, n, ng) for n in sizes]
+    rates = [np.log(errs[i] / errs[i + 1]) / np.log(sizes[i + 1] / sizes[i]) for i in range(len(sizes) - 1)]
+    assert rates[-1] > order - (0.35 if order <= 4 else 0.5), (errs, rates)
+    assert errs[-1] < errs[0]
+
+
+@pytest.mark.parametrize("scheme,which,order", [(3, "conv", 2), (4, "visc", 2), (7, "conv", 4)])
+def test_observed_order_on_a_scaled_grid(analytic, scheme, which, order):
+    """x = 2 xi (scaled_coord_1D): Jacobian, metric vectors and the gradient transform at work on the analytic solution"""
+    sizes = (16, 32, 64)
+    maps = (("scaled", 2.0), None, None)
+    errs = [_error(analytic, scheme, which, n, 2, maps) for n in sizes]
+    rates = [np.log(errs[i] / errs[i + 1]) / np.log(2.0) for i in range(2)]
+    assert rates[-1] > order - 0.35, (errs, rates)
+
+
+def test_wale_eddy_viscosity_vanishes_in_pure_shear():
+    """The property WALE is built for (Nicoud & Ducros 1999; reference development/subgrid/main.cc checks the model against its
+    analytic value): in a pure shear u(y) the traceless symmetric part of the squared velocity-gradient tensor is zero, so
+    mu_t = 0 and visc_lr over sgs_visc_t must give exactly the laminar result; in a general field it must not."""
+    from oracle import port
+    from util import make_state
+    nb, n, ng = (1, 2, 1), (8, 8, 8), 2
+    q = np.zeros((2, 12, 12, 12, 5))
+    y = np.concatenate([(np.arange(-ng, n[1] + ng) + 0.5) * (np.pi / 8) + lb * np.pi for lb in range(2)]).reshape(2, 12)
+    q[..., 0], q[..., 1] = 101325.0, 300.0
+    q[..., 2] = 30.0 * np.sin(y)[:, None, :, None]
+    lam = port.flux_div(oracle_cfg(nb, n, ng, scheme=0), q.ravel())
+    les = port.flux_div(oracle_cfg(nb, n, ng, scheme=11), q.ravel())
+    assert np.array_equal(lam, les)
+    q = make_state(nb, n, ng, seed=5)
+    lam = port.flux_div(oracle_cfg(nb, n, ng, scheme=0), q.ravel())
+    les = port.flux_div(oracle_cfg(nb, n, ng, scheme=11), q.ravel())
+    assert np.linalg.norm(les - lam) > 1e-4 * np.linalg.norm(lam)
