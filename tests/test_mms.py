@@ -129,3 +129,25 @@ def test_wale_eddy_viscosity_vanishes_in_pure_shear():
     lam = port.flux_div(oracle_cfg(nb, n, ng, scheme=0), q.ravel())
     les = port.flux_div(oracle_cfg(nb, n, ng, scheme=11), q.ravel())
     assert np.linalg.norm(les - lam) > 1e-4 * np.linalg.norm(lam)
+
+
+def test_ducros_sensor_switches_the_dissipative_flux_off_in_solid_rotation():
+    """state_sensor::ducros_t (state_sensor.h:32-42; the reference checks it against its analytic value in
+    development/shock-sense/main.cc:60-101): theta^2/(theta^2 + |omega|^2 + eps) is exactly 0 for a solid-body rotation (the
+    discrete divergence of a linear field vanishes), so hybrid_scheme_t(totani, fweno, ducros, diss_flux) = F0 + 0 F1 must equal
+    totani_lr + visc_lr bit for bit; a compressing field switches the WENO flux on."""
+    from oracle import port
+    nb, n, ng = (1, 1, 1), (8, 8, 8), 2
+    ax = (np.arange(-ng, 8 + ng) + 0.5) * 0.25 - 1.0
+    Z, Y, X = np.meshgrid(ax, ax, ax, indexing="ij")
+    q = np.zeros((1, 12, 12, 12, 5))
+    q[0, ..., 0], q[0, ..., 1] = 101325.0, 300.0
+    q[0, ..., 2], q[0, ..., 3] = -8.0 * Y, 8.0 * X
+    bounds = [-1.0, 1.0] * 3
+    central = port.flux_div(oracle_cfg(nb, n, ng, scheme=0, bounds=bounds), q.ravel())
+    hybrid = port.flux_div(oracle_cfg(nb, n, ng, scheme=8, bounds=bounds), q.ravel())
+    assert np.array_equal(central, hybrid)
+    q[0, ..., 2], q[0, ..., 3], q[0, ..., 4] = -8.0 * X, -8.0 * Y, -8.0 * Z          # pure compression: sensor ~ 1
+    central = port.flux_div(oracle_cfg(nb, n, ng, scheme=0, bounds=bounds), q.ravel())
+    hybrid = port.flux_div(oracle_cfg(nb, n, ng, scheme=8, bounds=bounds), q.ravel())
+    assert np.linalg.norm(hybrid - central) > 1e-3 * np.linalg.norm(central)
