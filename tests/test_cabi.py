@@ -99,3 +99,37 @@ def test_shim_recognises_every_functor_type_of_the_implemented_set():
     assert rows["hybrid(cent_keep<4>, fweno, ducros, diss)"]["blend"] == "1"
     assert rows["hybrid(totani, weno_t<rusanov_t>, ducros)"]["diss"] == "1"
     assert float(rows["visc_lr"]["beta"]) == pytest.approx(-2.0 * 1.8e-5 / 3.0, rel=1e-5)
+
+
+def test_fused_stage_plans_reproduce_every_rk_table():
+    """Host logic of integrator_t: the per-stage plan of the fused kernel (at most two residual inputs and one output per stage,
+    the final combination prepared one stage early) must be algebraically the Butcher table (explicit.h:27-116) for every
+    scheme it accepts. Emulated with scalars: w' = lambda(t) w, conserved variable w, no kernels involved."""
+    import spade_b200.api as sp
+
+    def rhs(w, t):
+        return (-0.7 + 0.3 * np.cos(t)) * w + 0.2 * np.sin(3 * t)
+
+    for alg in (sp.rk2_t, sp.rk4_t, sp.ssprk3_t, sp.ssprk34_t, sp.rk38r_t, sp.rk2hs_t, sp.ssprk3hs_t):
+        plan = sp.integrator_t._fused_plan(alg)
+        n, dt, t0, w0 = alg.rows(), 0.05, 0.3, 1.7
+        # classical form: k_i = f(w0 + dt sum_j a_ij k_j, t0 + c_i dt); w1 = w0 + dt sum_i b_i k_i
+        k = []
+        for i in range(n):
+            wi = w0 + dt * sum(float(alg.table[i][j]) * k[j] for j in range(i))
+            k.append(rhs(wi, t0 + float(alg.dt[i]) * dt))
+        want = w0 + dt * sum(float(alg.accum[i]) * k[i] for i in range(n))
+        if plan is None:
+            continue
+        # the plan: stage i sees w (the running state), evaluates r = f(w, t_i), then
+        #   w <- w + dt (cq_self r + sum cq_a reg[in_a]);   reg[out] <- co_self r + sum co_a reg[in_a]
+        w, reg = w0, {}
+        for i, st in enumerate(plan):
+            r = rhs(w, t0 + float(alg.dt[i]) * dt)
+            ins = [reg[key] for key in st["in"]]
+            new_w = w + dt * (st["cq_self"] * r + sum(c * x for c, x in zip(st["cq"], ins)))
+            if st["out"] is not None:
+                reg[st["out"]] = st["co_self"] * r + sum(c * x for c, x in zip(st["co"], ins))
+            w = new_w
+        assert abs(w - want) < 1e-14 * abs(want), alg.name
+    assert sp.integrator_t._fused_plan(sp.rk4_t) is not None and sp.integrator_t._fused_plan(sp.ssprk3_t) is not None
