@@ -161,6 +161,27 @@ int spb_flux_div_rk_stage_exchange(const spb_grid* g, const double* q_in_dev, do
                                    const spb_stage_desc* stage, spb_exchange* exch, int64_t lb_begin, int64_t lb_end,
                                    void* stream);
 
+/* Stage plan of the fused path for a Butcher table (the ONE planner both host sides use: include/spade_b200_shim.hpp and
+ * spade_b200/api.py). `diffs` is row-major [n][n]: diffs[i][j] = a_{i+1,j} - a_{i,j} (last row: b_j - a_{n-1,j}) evaluated
+ * in double exactly as the reference forms its update coefficients (ratio_diff_t + coeff_value_t,
+ * src/time-integration/advance.h:47-55, 84-92), WITHOUT dt. plan[i] describes stage i: which residual registers the stage
+ * kernel reads (`in`, at most two), with which coefficients they enter q_out (cq) and the written register (co), and which
+ * register it writes (`out`, -1 = none). A final update that needs more than two earlier residuals gets their combination
+ * C prepared by the stage before it in register n-2 (rk4: C = k0/6 + k1/3 - 2 k2/3, so an RK4 step reads 5 and writes 3
+ * residual planes instead of 10 and 4). Returns SPB_ERR_UNSUPPORTED when a stage would need more than two inputs (the
+ * caller then runs flux_div + spb_rk_update), SPB_ERR_BAD_ARG for n outside 1..8. Host-only, no GPU needed.
+ * After a fused step the registers differ from the reference's: k_{n-1} is never written and register n-2 may hold C. */
+typedef struct spb_stage_plan
+{
+    int    nin;            /* residual registers read (0..2) */
+    int    in[2];          /* their indices */
+    double cq[2], co[2];   /* coefficients into q_out (multiply by dt) and into the written register */
+    double cq_self;        /* coefficient of this stage's own rhs in q_out (multiply by dt) */
+    double co_self;        /* coefficient of this stage's own rhs in the written register */
+    int    out;            /* register written, -1 = none */
+} spb_stage_plan;
+int spb_rk_fused_plan(int n, const double* diffs, spb_stage_plan* plan);
+
 /* ---- RK stage update: replaces detail::transform_advance_to -----------------------------------
  * reference src/time-integration/advance.h:57-102: per interior cell
  *   w = cons(q); w += sum_j coeff[j]*k_j  (only j with coeff[j] != 0, in order); q = prim(w)
@@ -223,6 +244,10 @@ int64_t spb_exchange_first_block(const spb_exchange* e);           /* global id 
  * order inside the message is the reference's: transaction order, ix + nx*(iy + ny*iz), v fastest. */
 int64_t spb_exchange_send_cells(const spb_exchange* e, int peer);
 int64_t spb_exchange_recv_cells(const spb_exchange* e, int peer);
+/* mask[lb] = 1 for every local block that is the source of an off-rank send transaction — injection AND interpolation
+ * (patch_fill_t donors) — 0 otherwise; nlb = number of local blocks. The overlapped schedule advances these blocks first,
+ * sends their messages and advances the rest while the messages fly. Host-only. */
+int spb_exchange_boundary_blocks(const spb_exchange* e, int64_t nlb, unsigned char* mask);
 /* same-rank transactions: q(dst) = q(src) on the device (make_exchange.h:166-203). */
 int spb_exchange_local(spb_exchange* e, double* q_dev, void* stream);
 /* pack q into the contiguous message for `peer` (make_exchange.h:136-164) / unpack (340-369). */

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspade_b200.so")
+# SPB_B200_LIB: development override (timing experiments build differently named copies of the same library)
+LIB_PATH = os.environ.get("SPB_B200_LIB") or os.path.join(_HERE, "libspade_b200.so")
 
 
 class FluxDesc(C.Structure):
@@ -22,6 +23,12 @@ class StageDesc(C.Structure):
     """spb_stage_desc (include/spade_b200.h)."""
     _fields_ = [("nin", C.c_int), ("inp", C.c_void_p * 2), ("cq_self", C.c_double), ("cq", C.c_double * 2),
                 ("out", C.c_void_p), ("co_self", C.c_double), ("co", C.c_double * 2)]
+
+
+class StagePlan(C.Structure):
+    """spb_stage_plan (include/spade_b200.h)."""
+    _fields_ = [("nin", C.c_int), ("inp", C.c_int * 2), ("cq", C.c_double * 2), ("co", C.c_double * 2),
+                ("cq_self", C.c_double), ("co_self", C.c_double), ("out", C.c_int)]
 
 
 SPB_ERR_BAD_ARG, SPB_ERR_UNSUPPORTED, SPB_ERR_NO_DEVICE, SPB_ERR_DRIVER = 10001, 10002, 10003, 10004
@@ -69,6 +76,7 @@ SYMBOLS = {
                                                  C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "spb_rk_update": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, _dp, C.c_double,
                                 C.c_double, C.c_void_p]),
+    "spb_rk_fused_plan": (C.c_int, [C.c_int, _dp, C.POINTER(StagePlan)]),
     "spb_axpy_roundtrip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]),
     "spb_ssprk3_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                    C.c_double, C.c_double, C.c_void_p]),
@@ -83,6 +91,7 @@ SYMBOLS = {
     "spb_exchange_destroy": (None, [C.c_void_p]),
     "spb_exchange_num_send": (C.c_int64, [C.c_void_p]),
     "spb_exchange_num_recv": (C.c_int64, [C.c_void_p]),
+    "spb_exchange_boundary_blocks": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_ubyte)]),
     "spb_exchange_tables": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p]),
     "spb_exchange_local_blocks": (C.c_int64, [C.c_void_p]),
     "spb_exchange_first_block": (C.c_int64, [C.c_void_p]),

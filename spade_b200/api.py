@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BcDesc, FluxDesc, SourceDesc, SpbError, StageDesc, check, int3, lib
+from ._lib import BcDesc, FluxDesc, SourceDesc, SpbError, StageDesc, StagePlan, check, int3, lib
 
 NVAR = 5
 
@@ -76,8 +76,14 @@ class pool_t:
             return value
         import torch.distributed as dist
         dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        if op == RED_MAX:
+            # a NaN on any rank must survive (a diverged field has to stop the CFL logic): reduce (value, is-NaN) together
+            bad = value != value
+            t = torch.tensor([-np.inf if bad else value, 1.0 if bad else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            return float("nan") if float(t[1].item()) > 0.0 else float(t[0].item())
         t = torch.tensor([value], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == RED_MAX else dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return float(t.item())
 
 
@@ -628,30 +634,24 @@ class arr_exchange_t:
         return dist.batch_isend_irecv(ops) if ops else []
 
     def boundary_block_runs(self):
-        """Local block ranges [b0, b1) that own a cell another rank needs (the source blocks of the off-rank send
-        transactions), as sorted disjoint runs, and the complementary runs: the stage kernel runs on the first set, its
-        messages leave, and the second set is computed while they are in flight."""
+        """Local block ranges [b0, b1) that own a cell another rank needs — the source blocks of the off-rank send
+        transactions, injection AND interpolation (AMR donors), from spb_exchange_boundary_blocks — as sorted disjoint
+        runs, and the complementary runs: the stage kernel runs on the first set, its messages leave, and the second set is
+        computed while they are in flight."""
         if self._runs is None:
-            send, _, _ = self.tables()
             nlb = self.grid.num_local_blocks
-            me = self.pool.rank()
-            mark = np.zeros(nlb + 1, dtype=bool)
-            off = send[send[:, 2] != me]
-            mark[off[:, 8]] = True
-            mark[nlb] = False
+            mark = np.zeros(max(nlb, 1), dtype=np.uint8)
+            check(lib().spb_exchange_boundary_blocks(self._h, nlb, mark.ctypes.data_as(C.POINTER(C.c_ubyte))))
+            mark = mark[:nlb].astype(bool)
 
             def runs(flag):
-                out, b = [], 0
-                while b < nlb:
-                    if mark[b] == flag:
-                        e = b
-                        while e < nlb and mark[e] == flag:
-                            e += 1
-                        out.append((b, e))
-                        b = e
-                    else:
-                        b += 1
-                return out
+                idx = np.flatnonzero(mark == flag)
+                if len(idx) == 0:
+                    return []
+                cuts = np.flatnonzero(np.diff(idx) > 1)
+                starts = np.concatenate(([idx[0]], idx[cuts + 1]))
+                ends = np.concatenate((idx[cuts], [idx[-1]])) + 1
+                return [(int(a), int(b)) for a, b in zip(starts, ends)]
             self._runs = (runs(True), runs(False))
         return self._runs
 
@@ -1044,38 +1044,23 @@ class integrator_t:
 
     @staticmethod
     def _fused_plan(s):
-        """Per stage: which residual registers are read, which one is written, and the coefficients (without dt).
-        diffs[i][j] is the coefficient difference (a_{i+1,j} - a_{i,j}; last row: b_j - a_{n-1,j}) exactly as
-        advance.h:47-55,84-92 forms it. A final update that needs more than two earlier residuals gets their
-        combination C prepared by the stage before it (rk4: C = k0/6 + k1/3 - 2 k2/3)."""
+        """Per stage: which residual registers are read, which one is written, and the coefficients (without dt), from
+        spb_rk_fused_plan — the one planner both host sides share. diffs[i][j] is the coefficient difference
+        (a_{i+1,j} - a_{i,j}; last row: b_j - a_{n-1,j}) exactly as advance.h:47-55,84-92 forms it. A final update that needs
+        more than two earlier residuals gets their combination C prepared by the stage before it in register n-2
+        (rk4: C = k0/6 + k1/3 - 2 k2/3). None if a stage would need more than two inputs."""
         n = s.rows()
         rows = s.table + [s.accum]
-        diffs = [[_ratio_diff_value(c, p) for c, p in zip(rows[i + 1], rows[i])] for i in range(n)]
-        final_prior = [j for j in range(n - 1) if diffs[n - 1][j] != 0.0]
-        use_c = len(final_prior) > 2
-        plan = []
-        for i in range(n):
-            d = diffs[i]
-            st = {"cq_self": d[i], "in": [], "cq": [], "co": [], "out": None, "co_self": 0.0}
-            if i == n - 1 and use_c:
-                st["in"], st["cq"], st["co"] = [("c", n - 2)], [1.0], [0.0]
-            else:
-                prior = [j for j in range(i) if d[j] != 0.0]
-                extra = [j for j in final_prior if j < i and j not in prior] if (use_c and i == n - 2) else []
-                ins = sorted(prior + extra)
-                if len(ins) > 2:
-                    return None
-                st["in"] = [("k", j) for j in ins]
-                st["cq"] = [d[j] for j in ins]
-                st["co"] = [0.0] * len(ins)
-                if use_c and i == n - 2:
-                    st["out"], st["co_self"], st["co"] = ("c", n - 2), diffs[n - 1][i], [diffs[n - 1][j] for j in ins]
-                else:
-                    needed_later = any(diffs[m][i] != 0.0 for m in range(i + 1, n))
-                    if needed_later:
-                        st["out"], st["co_self"], st["co"] = ("k", i), 1.0, [0.0] * len(ins)
-            plan.append(st)
-        return plan
+        diffs = (C.c_double * (n * n))(*[_ratio_diff_value(c, p) for i in range(n) for c, p in zip(rows[i + 1], rows[i])])
+        raw = (StagePlan * n)()
+        rc = lib().spb_rk_fused_plan(n, diffs, raw)
+        if rc == _lib.SPB_ERR_UNSUPPORTED:
+            return None
+        check(rc)
+        # registers are named by their index ("k", j); register n-2 may hold the combination C instead of k_{n-2}
+        return [{"cq_self": st.cq_self, "in": [("k", st.inp[a]) for a in range(st.nin)], "cq": [st.cq[a] for a in range(st.nin)],
+                 "co": [st.co[a] for a in range(st.nin)], "out": ("k", st.out) if st.out >= 0 else None, "co_self": st.co_self}
+                for st in raw]
 
     def _advance_fused(self):
         ax, dt, d = self.axis, self.axis.dt, self.data

@@ -349,6 +349,16 @@ extern "C"
         e->send.resize(nsend); e->recv.resize(nrecv);
         for (int64_t i = 0; i < nsend; ++i) std::copy(send + 16*i, send + 16*i + 16, e->send[i].f);
         for (int64_t i = 0; i < nrecv; ++i) std::copy(recv + 16*i, recv + 16*i + 16, e->recv[i].f);
+        // the kernels trust these tables: ranks inside the group, boxes inside the padded block, local ids >= -1
+        for (const auto* list: {&e->send, &e->recv})
+            for (const auto& t: *list)
+            {
+                bool ok = t.f[1] >= 0 && t.f[1] < nranks && t.f[2] >= 0 && t.f[2] < nranks && t.f[8] >= -1 && t.f[15] >= -1;
+                for (int d = 0; d < 3 && ok; ++d)
+                    ok = t.f[9+d] >= 0 && t.f[5+d] >= -ng[d] && t.f[5+d] + t.f[9+d] <= nx[d] + ng[d]
+                                       && t.f[12+d] >= -ng[d] && t.f[12+d] + t.f[9+d] <= nx[d] + ng[d];
+                if (!ok) { set_error("spb_exchange_create_from_tables: a transaction has a rank outside the group or a box outside the padded block"); delete e; return SPB_ERR_BAD_ARG; }
+            }
         finish_plan(e);
         *out = e;
         return 0;
@@ -412,6 +422,20 @@ extern "C"
             offs[6*p+2] = e->send_rank_off[p]; offs[6*p+3] = e->send_rank_cnt[p];
             offs[6*p+4] = e->recv_rank_off[p]; offs[6*p+5] = e->recv_rank_cnt[p];
         }
+        return 0;
+    }
+
+    int spb_exchange_boundary_blocks(const spb_exchange* e, int64_t nlb, unsigned char* mask)
+    {
+        if (!e || !mask || nlb < 0) { spb::set_error("spb_exchange_boundary_blocks: bad argument"); return SPB_ERR_BAD_ARG; }
+        std::fill(mask, mask + nlb, (unsigned char)0);
+        for (const auto* list: {&e->send, &e->isend})
+            for (const auto& t: *list)
+            {
+                if (t.f[2] == e->rank) continue;
+                if (t.f[8] < 0 || t.f[8] >= nlb) { spb::set_error("spb_exchange_boundary_blocks: a send transaction names a block outside [0, nlb)"); return SPB_ERR_BAD_ARG; }
+                mask[t.f[8]] = 1;
+            }
         return 0;
     }
 

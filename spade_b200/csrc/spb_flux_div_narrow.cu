@@ -21,6 +21,14 @@
 #include "spb_tma.cuh"
 #include "spb_flux.cuh"
 
+// Timing-only experiment switches (tools/runs/r02_exp.sh builds libspade_b200_exp<N>.so with -DSPB_EXP=N; the results of
+// those builds are WRONG by construction, they bound what a restructuring could gain): bit 0 drops barrier (2), bit 1
+// drops the flux hand-off through shared memory, bit 2 drops the published differences.
+#ifndef SPB_EXP
+#define SPB_EXP 0
+#endif
+#define SPB_BAR2() do { if (!(SPB_EXP & 1)) __syncthreads(); } while (0)
+
 namespace spb
 {
     namespace nrw
@@ -29,7 +37,9 @@ namespace spb
         // up to 16 cells along i, which would leave half of every 32-wide row idle. Everything below is written on TI, TJ.
         constexpr int NCOMPUTE = 256;                   // 8 compute warps, one cell column per thread
         constexpr int NCW = NCOMPUTE/32;
-        constexpr int NTHREADS = NCOMPUTE + 64;         // + edge warp + ghost warp
+        constexpr int NTHREADS = NCOMPUTE + 64;         // + edge warp + ghost warp (fused stage with the same-rank ghost exchange)
+        constexpr int NTHREADS_NOGHOST = NCOMPUTE + 32; // + edge warp: 288 threads leave 112 registers per thread at 2 CTAs per SM
+        template <int N> struct IC { static constexpr int v = N; };
         constexpr int NP = 3;                           // ring slots: planes k, k+1 resident, k+2 in flight
         constexpr int NPUB = 7;                         // rho, cX, Dy.u, Dz.u, cY, Dz.v, Dx.v
         template <int TI_, int TJ_> struct Lay
@@ -175,8 +185,8 @@ namespace spb
         // difference of a face carries 1/m_n at the face, the finished flux is scaled by the area factor m_t1 m_t2 and the
         // divergence of a cell by J = 1/(m0 m1 m2). Row 0 of a table = m (as info::metric sees it), row 1 = 1/m at the cell
         // centres, row 2 = 1/m at the faces.
-        template <int CONV, int VISC, bool UNIF, bool FUSED, int TI, int TJ, bool CURV = false>
-        __global__ void __launch_bounds__(NTHREADS, 2)
+        template <int CONV, int VISC, bool UNIF, bool FUSED, int TI, int TJ, bool CURV = false, bool GHOSTW = false>
+        __global__ void __launch_bounds__(GHOSTW ? NTHREADS : NTHREADS_NOGHOST, 2)
         flux_div_narrow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_rhs,
                                const __grid_constant__ CUtensorMap tmap_qout, const __grid_constant__ CUtensorMap tmap_in0,
                                const __grid_constant__ CUtensorMap tmap_in1, double* __restrict__ rhs,
@@ -201,7 +211,7 @@ namespace spb
 
             const int tid = threadIdx.x;
             const int lane = tid & 31, warp = tid >> 5;
-            const bool is_edge = (warp == NCW), is_ghost = (warp == NCW + 1);
+            const bool is_edge = (warp == NCW), is_ghost = GHOSTW && (warp == NCW + 1);
 
             int t = blockIdx.x;
             const int ti = t % G.tiles_i; t /= G.tiles_i;
@@ -262,18 +272,22 @@ namespace spb
                 const int co = cell_off(il, jl);
                 const int po = pidx(il, jl);
                 const int so = (jl*TI + il)*5;                  // this thread's slot in the staging tiles
-                // loop-carried state: own column k-1, k, k+1; density of cells k-1 and k; tangential differences of
-                // cell k-1 needed by the next z-face; the divergence accumulator of cell k-1
-                double qm[5], q0[5], qp[5];
+                // loop-carried state: the own column lives in three register sets (cells k-1, k, k+1) whose roles rotate with
+                // the ring period, so the k loop is unrolled by 3 and no register is ever moved: per cell the state q, its
+                // density, the in-plane differences the next z-face needs (dc = Dx.u + Dy.v, dxw, dyw) and the plane's 1/m_z
+                struct Col { double q[5]; double rho, dc, dxw, dyw, jk; };
+                Col A, B, C3;
                 #pragma unroll
-                for (int v = 0; v < 5; ++v) { qm[v] = ring[co + v]; q0[v] = ring[PLANE_STRIDE + co + v]; qp[v] = q0[v]; }
-                double rhom = density(P.R, qm[0], qm[1]);
-                double rho0 = density(P.R, q0[0], q0[1]);
-                if (!active) { rhom = 1.0; rho0 = 1.0; }
+                for (int v = 0; v < 5; ++v) { A.q[v] = ring[co + v]; B.q[v] = ring[PLANE_STRIDE + co + v]; C3.q[v] = B.q[v]; }
+                A.rho = density(P.R, A.q[0], A.q[1]);
+                B.rho = density(P.R, B.q[0], B.q[1]);
+                if (!active) { A.rho = 1.0; B.rho = 1.0; }
+                C3.rho = 1.0;
+                A.jk = B.jk = C3.jk = 1.0;
                 // scales of this column: tangential differences (cx, cy), normal differences of the lower x / y face (gx, gy),
                 // area factors and the in-plane part of the Jacobian
                 const int ipc = i0 + il + G.ng[0], jpc = j0 + jl + G.ng[1];
-                double cx = H.c0, cy = H.c1, gx = H.i0, gy = H.i1, ar0 = 1.0, ar1 = 1.0, jij = 1.0, jkm = 1.0;
+                double cx = H.c0, cy = H.c1, gx = H.i0, gy = H.i1, ar0 = 1.0, ar1 = 1.0, jij = 1.0;
                 if (CURV)
                 {
                     const double r0 = MT(0, 1, ipc), r1 = MT(1, 1, jpc);
@@ -281,13 +295,13 @@ namespace spb
                     gx = H.i0*MT(0, 2, ipc); gy = H.i1*MT(1, 2, jpc);
                     ar0 = MT(0, 0, ipc); ar1 = MT(1, 0, jpc);
                 }
-                double dpc = 0.0, dpxw = 0.0, dpyw = 0.0;
+                A.dc = A.dxw = A.dyw = 0.0; B.dc = B.dxw = B.dyw = 0.0; C3.dc = C3.dxw = C3.dyw = 0.0;
                 if (VISC)
                 {
                     const double* pl = ring;
-                    dpc  = cx*(pl[co + 5 + 2] - pl[co - 5 + 2]) + cy*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
-                    dpxw = cx*(pl[co + 5 + 4] - pl[co - 5 + 4]);
-                    dpyw = cy*(pl[co + 5*TIp + 4] - pl[co - 5*TIp + 4]);
+                    A.dc  = cx*(pl[co + 5 + 2] - pl[co - 5 + 2]) + cy*(pl[co + 5*TIp + 3] - pl[co - 5*TIp + 3]);
+                    A.dxw = cx*(pl[co + 5 + 4] - pl[co - 5 + 4]);
+                    A.dyw = cy*(pl[co + 5*TIp + 4] - pl[co - 5*TIp + 4]);
                 }
                 double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
                 const long long cell0 = lb*G.block_stride
@@ -295,38 +309,45 @@ namespace spb
                 const long long kstride = 5ll*G.np[0]*G.np[1];
                 __syncthreads();                                                // (0) plane 0 consumed
 
-                int sk = 1, sp = 2;                                             // slots of planes pk and pk+1
-                for (int k = 0; k <= nz; ++k)
+                // one k step; SK / SP = ring slots of planes k and k+1 (compile-time: every shared-memory address of the step is
+                // an immediate offset), m / c / p = the register sets of cells k-1, k, k+1, par = mbarrier parity of plane k+1
+                auto step = [&](auto sk_tag, auto sp_tag, const int k, Col& m, Col& c, Col& p, const uint32_t par)
                 {
+                    constexpr int SK = decltype(sk_tag)::v, SP = decltype(sp_tag)::v;
                     const int pk = k + 1;                       // plane index of k
-                    const double* plk = ring + sk*PLANE_STRIDE + co;
-                    const double* plp = ring + sp*PLANE_STRIDE + co;
+                    const double* plk = ring + SK*PLANE_STRIDE + co;
+                    const double* plp = ring + SP*PLANE_STRIDE + co;
 
-                    // in-plane scaled central differences of cell k (plane k has been resident since the previous step)
+                    // in-plane neighbours of cell k (plane k has been resident since the previous step): u, v, w of the x- and
+                    // y-neighbours. The lower ones are kept: they are 3 of the 5 values the lower x / y face needs after (1).
+                    double xl[3] = {0.0, 0.0, 0.0}, yl[3] = {0.0, 0.0, 0.0};
                     double dxu = 0.0, dxv = 0.0, dxw = 0.0, dyu = 0.0, dyv = 0.0, dyw = 0.0;
                     if (VISC)
                     {
-                        dxu = cx*(plk[5 + 2] - plk[-5 + 2]);
-                        dxv = cx*(plk[5 + 3] - plk[-5 + 3]);
-                        dxw = cx*(plk[5 + 4] - plk[-5 + 4]);
-                        dyu = cy*(plk[5*TIp + 2] - plk[-5*TIp + 2]);
-                        dyv = cy*(plk[5*TIp + 3] - plk[-5*TIp + 3]);
-                        dyw = cy*(plk[5*TIp + 4] - plk[-5*TIp + 4]);
+                        #pragma unroll
+                        for (int v = 0; v < 3; ++v) { xl[v] = plk[-5 + 2 + v]; yl[v] = plk[-5*TIp + 2 + v]; }
+                        dxu = cx*(plk[5 + 2] - xl[0]);
+                        dxv = cx*(plk[5 + 3] - xl[1]);
+                        dxw = cx*(plk[5 + 4] - xl[2]);
+                        dyu = cy*(plk[5*TIp + 2] - yl[0]);
+                        dyv = cy*(plk[5*TIp + 3] - yl[1]);
+                        dyw = cy*(plk[5*TIp + 4] - yl[2]);
                     }
                     const double cZ = dxu + dyv;
+                    c.dc = cZ; c.dxw = dxw; c.dyw = dyw;
                     // plane k: z scales (the same for the whole plane)
-                    double cz = H.c2, gz = H.i2, ar2 = 1.0, jk = 1.0;
+                    double cz = H.c2, gz = H.i2, ar2 = 1.0;
                     if (CURV)
                     {
                         const int kp = k + G.ng[2];
-                        jk = MT(2, 1, kp); cz = H.c2*jk; gz = H.i2*MT(2, 2, kp); ar2 = MT(2, 0, kp);
+                        c.jk = MT(2, 1, kp); cz = H.c2*c.jk; gz = H.i2*MT(2, 2, kp); ar2 = MT(2, 0, kp);
                     }
                     // z-face k-1/2: registers only, overlaps the wait for plane k+1. acc carries the divergence of a cell:
                     // lower-face fluxes are added as they are computed, the neighbours' (upper-face) fluxes are subtracted
                     // after barrier (2).
                     {
                         double Fz[5];
-                        face<CONV, VISC, 2>(P, qm, q0, rhom, rho0, dpc + cZ, dpxw + dxw, dpyw + dyw, gz, Fz);
+                        face<CONV, VISC, 2>(P, m.q, c.q, m.rho, c.rho, m.dc + cZ, m.dxw + dxw, m.dyw + dyw, gz, Fz);
                         if (CURV)
                         {
                             const double az = ar0*ar1;
@@ -340,13 +361,12 @@ namespace spb
                             for (int v = 0; v < 5; ++v) r[v] = fma(-Fz[v], H.i2, acc[v]);      // rhs of cell k-1
                             if (CURV)
                             {
-                                const double jac = jij*jkm;                                     // J of cell k-1
+                                const double jac = jij*m.jk;                                    // J of cell k-1
                                 #pragma unroll
                                 for (int v = 0; v < 5; ++v) r[v] *= jac;
                             }
                             if (FUSED)
                             {
-                                // the inputs of this cell were fetched by cp.async into this thread's own staging slots
                                 double w[5], o[5];
                                 #pragma unroll
                                 for (int v = 0; v < 5; ++v) { w[v] = S.cq_self*r[v]; o[v] = S.co_self*r[v]; }
@@ -375,10 +395,10 @@ namespace spb
                                     for (int v = 0; v < 5; ++v) stage_k[so + v] = o[v];
                                 }
                                 // prim -> cons (fluid_state.h:103-116), add the increment, cons -> prim (fluid_state.h:119-135)
-                                const double u2 = fma(qm[2], qm[2], fma(qm[3], qm[3], qm[4]*qm[4]));
-                                const double rho  = rhom + w[0];
-                                const double rhoE = fma(0.5*rhom, u2, qm[0]*S.inv_gm1) + w[1];
-                                const double mx = fma(rhom, qm[2], w[2]), my = fma(rhom, qm[3], w[3]), mz = fma(rhom, qm[4], w[4]);
+                                const double u2 = fma(m.q[2], m.q[2], fma(m.q[3], m.q[3], m.q[4]*m.q[4]));
+                                const double rho  = m.rho + w[0];
+                                const double rhoE = fma(0.5*m.rho, u2, m.q[0]*S.inv_gm1) + w[1];
+                                const double mx = fma(m.rho, m.q[2], w[2]), my = fma(m.rho, m.q[3], w[3]), mz = fma(m.rho, m.q[4], w[4]);
                                 const double ir = fast_rcp(active ? rho : 1.0);
                                 const double un = ir*mx, vn = ir*my, wn = ir*mz;
                                 const double pn = S.gm1*fma(-0.5*rho, fma(un, un, fma(vn, vn, wn*wn)), rhoE);
@@ -409,23 +429,23 @@ namespace spb
                     }
                     if (pk + 1 < nplanes)
                     {
-                        mbar_wait(&bars[sp], ((pk + 1)/NP) & 1);
+                        mbar_wait(&bars[SP], par);
                         #pragma unroll
-                        for (int v = 0; v < 5; ++v) qp[v] = plp[v];
+                        for (int v = 0; v < 5; ++v) p.q[v] = plp[v];
                     }
-                    double rhop = density(P.R, qp[0], qp[1]);           // stale at k = nz, never used
-                    if (!active) rhop = 1.0;
+                    p.rho = density(P.R, p.q[0], p.q[1]);               // stale at k = nz, never used
+                    if (!active) p.rho = 1.0;
                     double cX = 0.0, cY = 0.0, dzu = 0.0, dzv = 0.0;
                     if (VISC && k < nz)
                     {
-                        const double dzw = cz*(qp[4] - qm[4]);
-                        dzu = cz*(qp[2] - qm[2]);
-                        dzv = cz*(qp[3] - qm[3]);
+                        const double dzw = cz*(p.q[4] - m.q[4]);
+                        dzu = cz*(p.q[2] - m.q[2]);
+                        dzv = cz*(p.q[3] - m.q[3]);
                         cX = dyv + dzw; cY = dzw + dxu;
                     }
-                    if (k < nz)
+                    if (k < nz && !(SPB_EXP & 4))
                     {
-                        pub[P_RHO*PSZ + po] = rho0;
+                        pub[P_RHO*PSZ + po] = c.rho;
                         if (VISC)
                         {
                             pub[P_CX*PSZ + po] = cX; pub[P_DYU*PSZ + po] = dyu; pub[P_DZU*PSZ + po] = dzu;
@@ -438,20 +458,21 @@ namespace spb
                     {
                         {
                             double qL[5], F[5];
+                            qL[0] = plk[-5]; qL[1] = plk[-5 + 1];
                             #pragma unroll
-                            for (int v = 0; v < 5; ++v) qL[v] = plk[-5 + v];
+                            for (int v = 0; v < 3; ++v) qL[2 + v] = VISC ? xl[v] : plk[-5 + 2 + v];
                             const int pl_ = po - 1;
-                            const double rhoL = pub[P_RHO*PSZ + pl_];
+                            const double rhoL = (SPB_EXP & 4) ? m.rho : pub[P_RHO*PSZ + pl_];
                             double ac = 0.0, b = 0.0, d = 0.0;
-                            if (VISC) { ac = pub[P_CX*PSZ + pl_] + cX; b = pub[P_DYU*PSZ + pl_] + dyu; d = pub[P_DZU*PSZ + pl_] + dzu; }
-                            face<CONV, VISC, 0>(P, qL, q0, rhoL, rho0, ac, b, d, gx, F);
+                            if (VISC && !(SPB_EXP & 4)) { ac = pub[P_CX*PSZ + pl_] + cX; b = pub[P_DYU*PSZ + pl_] + dyu; d = pub[P_DZU*PSZ + pl_] + dzu; }
+                            face<CONV, VISC, 0>(P, qL, c.q, rhoL, c.rho, ac, b, d, gx, F);
                             if (CURV)
                             {
                                 const double ax = ar1*ar2;
                                 #pragma unroll
                                 for (int v = 0; v < 5; ++v) F[v] *= ax;
                             }
-                            if (active)
+                            if (active && !(SPB_EXP & 2))
                             {
                                 #pragma unroll
                                 for (int v = 0; v < 5; ++v) Fx[(jl*(TI + 1) + il)*5 + v] = F[v];
@@ -461,20 +482,21 @@ namespace spb
                         }
                         {
                             double qL[5], F[5];
+                            qL[0] = plk[-5*TIp]; qL[1] = plk[-5*TIp + 1];
                             #pragma unroll
-                            for (int v = 0; v < 5; ++v) qL[v] = plk[-5*TIp + v];
+                            for (int v = 0; v < 3; ++v) qL[2 + v] = VISC ? yl[v] : plk[-5*TIp + 2 + v];
                             const int pl_ = po - PW;
-                            const double rhoL = pub[P_RHO*PSZ + pl_];
+                            const double rhoL = (SPB_EXP & 4) ? m.rho : pub[P_RHO*PSZ + pl_];
                             double ac = 0.0, b = 0.0, d = 0.0;
-                            if (VISC) { ac = pub[P_CY*PSZ + pl_] + cY; b = pub[P_DZV*PSZ + pl_] + dzv; d = pub[P_DXV*PSZ + pl_] + dxv; }
-                            face<CONV, VISC, 1>(P, qL, q0, rhoL, rho0, ac, b, d, gy, F);
+                            if (VISC && !(SPB_EXP & 4)) { ac = pub[P_CY*PSZ + pl_] + cY; b = pub[P_DZV*PSZ + pl_] + dzv; d = pub[P_DXV*PSZ + pl_] + dxv; }
+                            face<CONV, VISC, 1>(P, qL, c.q, rhoL, c.rho, ac, b, d, gy, F);
                             if (CURV)
                             {
                                 const double ay = ar2*ar0;
                                 #pragma unroll
                                 for (int v = 0; v < 5; ++v) F[v] *= ay;
                             }
-                            if (active)
+                            if (active && !(SPB_EXP & 2))
                             {
                                 #pragma unroll
                                 for (int v = 0; v < 5; ++v) Fy[(jl*TI + il)*5 + v] = F[v];
@@ -483,8 +505,8 @@ namespace spb
                             for (int v = 0; v < 5; ++v) acc[v] = fma(F[v], H.i1, acc[v]);
                         }
                     }
-                    __syncthreads();                                            // (2) fluxes visible; pub, plane k, staging tiles free
-                    if (k < nz)
+                    SPB_BAR2();                                                 // (2) fluxes visible; pub, plane k, staging tiles free
+                    if (k < nz && !(SPB_EXP & 2))
                     {
                         #pragma unroll
                         for (int v = 0; v < 5; ++v)
@@ -493,12 +515,16 @@ namespace spb
                             acc[v] = fma(-Fy[((jl + 1)*TI + il)*5 + v], H.i1, acc[v]);
                         }
                     }
-                    rhom = rho0; rho0 = rhop;
-                    jkm = jk;
-                    dpc = cZ; dpxw = dxw; dpyw = dyw;
-                    #pragma unroll
-                    for (int v = 0; v < 5; ++v) { qm[v] = q0[v]; q0[v] = qp[v]; }
-                    sk = sp; sp = (sp + 1 == NP) ? 0 : sp + 1;
+                };
+                // plane p lives in slot p % 3 and cell k in plane k + 1: k = 3 kb + u has planes (k, k+1) in slots ((u+1)%3, (u+2)%3);
+                // plane k + 2 = 3 (kb + (u+2)/3) + (u+2)%3 completes phase kb + (u+2)/3 of its slot's mbarrier
+                for (int k = 0, kb = 0; k <= nz; k += 3, ++kb)
+                {
+                    step(IC<1>{}, IC<2>{}, k, A, B, C3, (uint32_t)(kb & 1));
+                    if (k + 1 > nz) break;
+                    step(IC<2>{}, IC<0>{}, k + 1, B, C3, A, (uint32_t)((kb + 1) & 1));
+                    if (k + 2 > nz) break;
+                    step(IC<0>{}, IC<1>{}, k + 2, C3, A, B, (uint32_t)((kb + 1) & 1));
                 }
             }
             else if (is_edge)
@@ -523,13 +549,16 @@ namespace spb
                     ear0 = MT(0, 0, i0 + rl + G.ng[0]);
                     ear1 = MT(1, 0, j0 + ccj + G.ng[1]);
                 }
-                // z-neighbours (k-1, k) of the edge cells roll through registers: v,w for the row cells, u,w for the column cell
-                double r0m[2], r00[2], r1m[2], r10[2], ccm[2], cc0[2];
+                // z-neighbours (k-1, k, k+1) of the edge cells live in three rotating register sets like the compute warps'
+                // columns: v,w of the two row cells, u,w of the column cell
+                struct ECol { double r0[2], r1[2], cc[2]; };
+                ECol EA, EB, EC;
                 {
                     const double* pa = ring; const double* pb = ring + PLANE_STRIDE;
-                    r0m[0] = pa[co_r0 + 3]; r0m[1] = pa[co_r0 + 4]; r00[0] = pb[co_r0 + 3]; r00[1] = pb[co_r0 + 4];
-                    r1m[0] = pa[co_r1 + 3]; r1m[1] = pa[co_r1 + 4]; r10[0] = pb[co_r1 + 3]; r10[1] = pb[co_r1 + 4];
-                    ccm[0] = pa[co_c + 2];  ccm[1] = pa[co_c + 4];  cc0[0] = pb[co_c + 2];  cc0[1] = pb[co_c + 4];
+                    EA.r0[0] = pa[co_r0 + 3]; EA.r0[1] = pa[co_r0 + 4]; EB.r0[0] = pb[co_r0 + 3]; EB.r0[1] = pb[co_r0 + 4];
+                    EA.r1[0] = pa[co_r1 + 3]; EA.r1[1] = pa[co_r1 + 4]; EB.r1[0] = pb[co_r1 + 3]; EB.r1[1] = pb[co_r1 + 4];
+                    EA.cc[0] = pa[co_c + 2];  EA.cc[1] = pa[co_c + 4];  EB.cc[0] = pb[co_c + 2];  EB.cc[1] = pb[co_c + 4];
+                    EC = EB;
                 }
                 __syncthreads();                                                // (0) plane 0 consumed
                 if (lane == 0 && NP < nplanes)
@@ -537,19 +566,19 @@ namespace spb
                     mbar_arrive_expect_tx(&bars[0], PLANE_BYTES);
                     tma_load_4d(ring, &tmap_q, &bars[0], c0, c1, c2base + NP, (int)lb);
                 }
-                int sk = 1, sp = 2;
-                for (int k = 0; k <= nz; ++k)
+                auto estep = [&](auto sk_tag, auto sp_tag, const int k, ECol& m, ECol& c, ECol& p, const uint32_t par)
                 {
+                    constexpr int SK = decltype(sk_tag)::v, SP = decltype(sp_tag)::v;
                     const int pk = k + 1;
-                    const double* plk = ring + sk*PLANE_STRIDE;
-                    const double* plp = ring + sp*PLANE_STRIDE;
-                    double r0p[2] = {0.0, 0.0}, r1p[2] = {0.0, 0.0}, ccp[2] = {0.0, 0.0};
+                    const double* plk = ring + SK*PLANE_STRIDE;
+                    const double* plp = ring + SP*PLANE_STRIDE;
+                    p.r0[0] = p.r0[1] = p.r1[0] = p.r1[1] = p.cc[0] = p.cc[1] = 0.0;
                     if (pk + 1 < nplanes)
                     {
-                        mbar_wait(&bars[sp], ((pk + 1)/NP) & 1);
-                        r0p[0] = plp[co_r0 + 3]; r0p[1] = plp[co_r0 + 4];
-                        r1p[0] = plp[co_r1 + 3]; r1p[1] = plp[co_r1 + 4];
-                        ccp[0] = plp[co_c + 2];  ccp[1] = plp[co_c + 4];
+                        mbar_wait(&bars[SP], par);
+                        p.r0[0] = plp[co_r0 + 3]; p.r0[1] = plp[co_r0 + 4];
+                        p.r1[0] = plp[co_r1 + 3]; p.r1[1] = plp[co_r1 + 4];
+                        p.cc[0] = plp[co_c + 2];  p.cc[1] = plp[co_c + 4];
                     }
                     // ---- before (1): publish the lower halo, and prepare what the upper faces need from their R cells
                     double uCY = 0.0, uDzv = 0.0, uDxv = 0.0, xCX = 0.0, xDyu = 0.0, xDzu = 0.0;
@@ -565,11 +594,11 @@ namespace spb
                             uRho = density(P.R, plk[co_r1], plk[co_r1 + 1]);
                             if (VISC)
                             {
-                                pub[P_CY*PSZ + po]  = ecz*(r0p[1] - r0m[1]) + ecx*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
-                                pub[P_DZV*PSZ + po] = ecz*(r0p[0] - r0m[0]);
+                                pub[P_CY*PSZ + po]  = ecz*(p.r0[1] - m.r0[1]) + ecx*(plk[co_r0 + 5 + 2] - plk[co_r0 - 5 + 2]);
+                                pub[P_DZV*PSZ + po] = ecz*(p.r0[0] - m.r0[0]);
                                 pub[P_DXV*PSZ + po] = ecx*(plk[co_r0 + 5 + 3] - plk[co_r0 - 5 + 3]);
-                                uCY  = ecz*(r1p[1] - r1m[1]) + ecx*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
-                                uDzv = ecz*(r1p[0] - r1m[0]);
+                                uCY  = ecz*(p.r1[1] - m.r1[1]) + ecx*(plk[co_r1 + 5 + 2] - plk[co_r1 - 5 + 2]);
+                                uDzv = ecz*(p.r1[0] - m.r1[0]);
                                 uDxv = ecx*(plk[co_r1 + 5 + 3] - plk[co_r1 - 5 + 3]);
                             }
                         }
@@ -578,9 +607,9 @@ namespace spb
                             xRho = density(P.R, plk[co_c], plk[co_c + 1]);
                             if (VISC)
                             {
-                                xCX  = ecy*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]) + ecz*(ccp[1] - ccm[1]);
+                                xCX  = ecy*(plk[co_c + 5*TIp + 3] - plk[co_c - 5*TIp + 3]) + ecz*(p.cc[1] - m.cc[1]);
                                 xDyu = ecy*(plk[co_c + 5*TIp + 2] - plk[co_c - 5*TIp + 2]);
-                                xDzu = ecz*(ccp[0] - ccm[0]);
+                                xDzu = ecz*(p.cc[0] - m.cc[0]);
                             }
                             if (col_lo)
                             {
@@ -593,7 +622,10 @@ namespace spb
                     __syncthreads();                                            // (1)
                     if (lane == 0 && G.tma_store && k >= 1)
                     {
-                        if (!FUSED || S.has_out) tma_store_4d(&tmap_rhs, stage_k, 5*i0, j0, k - 1, (int)lb);
+                        // `increment` trait: the same staged plane leaves as a tensor reduction (rhs += tile, one fp64 add per
+                        // element at the L2: bit-identical to a load-add-store, and the SMs never read rhs)
+                        if (!FUSED && G.increment) tma_reduce_add_4d(&tmap_rhs, stage_k, 5*i0, j0, k - 1, (int)lb);
+                        else if (!FUSED || S.has_out) tma_store_4d(&tmap_rhs, stage_k, 5*i0, j0, k - 1, (int)lb);
                         if (FUSED) tma_store_4d(&tmap_qout, stage_q, 5*i0, j0, k - 1, (int)lb);
                         tma_store_commit();
                     }
@@ -639,7 +671,7 @@ namespace spb
                         }
                     }
                     if (lane == 0 && G.tma_store) tma_store_wait_read<0>();     // staging tiles are rewritten after (2)
-                    __syncthreads();                                            // (2)
+                    SPB_BAR2();                                                 // (2)
                     if (FUSED && lane == 0 && S.nin > 0 && k < nz)
                     {
                         // input tiles of cell plane k (its rhs completes in the next step) land in the staging tiles, which
@@ -659,19 +691,23 @@ namespace spb
                         const int pnew = pk + NP;
                         if (pnew < nplanes)
                         {
-                            mbar_arrive_expect_tx(&bars[sk], PLANE_BYTES);
-                            tma_load_4d(ring + sk*PLANE_STRIDE, &tmap_q, &bars[sk], c0, c1, c2base + pnew, (int)lb);
+                            mbar_arrive_expect_tx(&bars[SK], PLANE_BYTES);
+                            tma_load_4d(ring + SK*PLANE_STRIDE, &tmap_q, &bars[SK], c0, c1, c2base + pnew, (int)lb);
                             if (pnew + 1 < nplanes) tma_prefetch_4d(&tmap_q, c0, c1, c2base + pnew + 1, (int)lb);   // and the one after into L2
                         }
                     }
-                    r0m[0] = r00[0]; r0m[1] = r00[1]; r00[0] = r0p[0]; r00[1] = r0p[1];
-                    r1m[0] = r10[0]; r1m[1] = r10[1]; r10[0] = r1p[0]; r10[1] = r1p[1];
-                    ccm[0] = cc0[0]; ccm[1] = cc0[1]; cc0[0] = ccp[0]; cc0[1] = ccp[1];
-                    sk = sp; sp = (sp + 1 == NP) ? 0 : sp + 1;
+                };
+                for (int k = 0, kb = 0; k <= nz; k += 3, ++kb)
+                {
+                    estep(IC<1>{}, IC<2>{}, k, EA, EB, EC, (uint32_t)(kb & 1));
+                    if (k + 1 > nz) break;
+                    estep(IC<2>{}, IC<0>{}, k + 1, EB, EC, EA, (uint32_t)((kb + 1) & 1));
+                    if (k + 2 > nz) break;
+                    estep(IC<0>{}, IC<1>{}, k + 2, EC, EA, EB, (uint32_t)((kb + 1) & 1));
                 }
                 if (lane == 0 && G.tma_store) tma_store_wait<0>();
             }
-            else
+            else if (GHOSTW)
             {
                 // ======================= ghost warp: same-rank ghost exchange of the finished q_out plane =======================
                 // A cell of the source box of direction e = (ex,ey,ez) goes to cell (i - ex n0, j - ey n1, k - ez n2) of the
@@ -751,7 +787,7 @@ namespace spb
                         }
                     }
                     if (gdst >= 0) tma_store_wait_read<0>();                    // stage_q is refilled after (2)
-                    __syncthreads();                                            // (2)
+                    SPB_BAR2();                                                 // (2)
                 }
                 if (gdst >= 0) tma_store_wait<0>();
             }
@@ -795,7 +831,7 @@ namespace spb
         const cuuint64_t idims[4] = {(cuuint64_t)5*g->nx[0], (cuuint64_t)g->nx[1], (cuuint64_t)g->nx[2], (cuuint64_t)g->nlb};
         const cuuint32_t ibox[4]  = {(cuuint32_t)(5*TI), (cuuint32_t)TJ, 1, 1};
         const bool aligned = (org % 2 == 0);
-        int tma_store = (!increment && aligned && rhs && (((uintptr_t)rhs) % 16 == 0)) ? 1 : 0;
+        int tma_store = (aligned && rhs && (((uintptr_t)rhs) % 16 == 0)) ? 1 : 0;
         if (tma_store && make_map(&tr, rhs + org, idims, strides, ibox, CU_TENSOR_MAP_L2_PROMOTION_NONE, "rhs")) tma_store = 0;
         if (!tma_store) tr = tq;
         tqo = tq;
@@ -870,11 +906,11 @@ namespace spb
         for (int d = 0; d < 3; ++d) { G.idx[d] = g->inv_dx_host[3*lb_begin + d]; G.cdx[d] = 0.25*G.idx[d]; }
         Stage S{};
         if (stage) S = *stage;
-        auto go = [&](auto kern) -> int
+        auto go = [&](auto kern, const int nthreads = NTHREADS_NOGHOST) -> int
         {
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            kern<<<(unsigned)nblk, NTHREADS, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev, GM, nbr_tab, q_out, g->metric_dev);
+            kern<<<(unsigned)nblk, nthreads, SMEM_BYTES, stream>>>(tq, tr, tqo, ti0, ti1, rhs, P, G, S, g->inv_dx_dev, GM, nbr_tab, q_out, g->metric_dev);
             SPB_LAUNCH_CHECK();
             return 0;
         };
@@ -882,8 +918,11 @@ namespace spb
         {
             // general coordinates: the computational lattice must be uniform (per-block dxi with a metric is the wide kernel's job)
             if (!uniform) { set_error("spb_flux_div: general coordinates on a non-uniform block lattice run on the wide kernel"); return SPB_ERR_UNSUPPORTED; }
+            if (stage && G.ghost) return go(flux_div_narrow_kernel<CONV, VISC, true, true, TI, TJ, true, true>, NTHREADS);
             return stage ? go(flux_div_narrow_kernel<CONV, VISC, true, true, TI, TJ, true>) : go(flux_div_narrow_kernel<CONV, VISC, true, false, TI, TJ, true>);
         }
+        // the fused stage with the same-rank ghost exchange carries a tenth warp (the ghost warp)
+        if (stage && G.ghost) return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, true, TI, TJ, false, true>, NTHREADS) : go(flux_div_narrow_kernel<CONV, VISC, false, true, TI, TJ, false, true>, NTHREADS);
         if (stage) return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, true, TI, TJ>) : go(flux_div_narrow_kernel<CONV, VISC, false, true, TI, TJ>);
         return uniform ? go(flux_div_narrow_kernel<CONV, VISC, true, false, TI, TJ>) : go(flux_div_narrow_kernel<CONV, VISC, false, false, TI, TJ>);
     }

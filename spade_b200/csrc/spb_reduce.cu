@@ -8,7 +8,8 @@ namespace spb
 {
     struct RedDims { int nx[3], ng[3], np[3]; long long ncells; };
 
-    template <int OP> __device__ __forceinline__ double red_op(double a, double b) { return OP == SPB_RED_MAX ? fmax(a, b) : a + b; }
+    // max keeps a NaN once it has seen one (fmax would drop it and a diverged field would report a finite CFL speed)
+    template <int OP> __device__ __forceinline__ double red_op(double a, double b) { return OP == SPB_RED_MAX ? ((a < b || b != b) ? b : a) : a + b; }
     template <int OP> __device__ __forceinline__ double red_identity() { return OP == SPB_RED_MAX ? -1.7976931348623157e308 : 0.0; }
 
     template <int FN> __device__ __forceinline__ double red_fn(const double* __restrict__ q, int ivar, double gamma, double R)

@@ -154,6 +154,44 @@ namespace spb
 
 extern "C"
 {
+    // the planner of the fused path, shared by both host sides (see include/spade_b200.h)
+    int spb_rk_fused_plan(int n, const double* diffs, spb_stage_plan* plan)
+    {
+        if (n < 1 || n > 8 || !diffs || !plan) { spb::set_error("spb_rk_fused_plan: bad argument"); return SPB_ERR_BAD_ARG; }
+        auto D = [&](int i, int j) { return diffs[i*n + j]; };
+        int nfinal = 0;
+        for (int j = 0; j + 1 < n; ++j) if (D(n - 1, j) != 0.0) ++nfinal;
+        const bool use_c = nfinal > 2;
+        for (int i = 0; i < n; ++i)
+        {
+            spb_stage_plan& st = plan[i];
+            st = spb_stage_plan{};
+            st.out = -1;
+            st.cq_self = D(i, i);
+            if (i == n - 1 && use_c) { st.nin = 1; st.in[0] = n - 2; st.cq[0] = 1.0; continue; }      // register n-2 holds C
+            for (int j = 0; j < i; ++j)
+            {
+                const bool prior = D(i, j) != 0.0;
+                const bool extra = use_c && i == n - 2 && D(n - 1, j) != 0.0;
+                if (!prior && !extra) continue;
+                if (st.nin == 2) { spb::set_error("spb_rk_fused_plan: a stage needs more than two residual inputs"); return SPB_ERR_UNSUPPORTED; }
+                st.in[st.nin] = j; st.cq[st.nin] = D(i, j); st.co[st.nin] = 0.0; ++st.nin;
+            }
+            if (use_c && i == n - 2)
+            {
+                st.out = n - 2; st.co_self = D(n - 1, i);
+                for (int a = 0; a < st.nin; ++a) st.co[a] = D(n - 1, st.in[a]);
+            }
+            else
+            {
+                bool later = false;
+                for (int m = i + 1; m < n; ++m) later = later || D(m, i) != 0.0;
+                if (later) { st.out = i; st.co_self = 1.0; }
+            }
+        }
+        return 0;
+    }
+
     int spb_axpy_roundtrip(const spb_grid* g, double* sol_dev, double* resid_dev, double c, int subtract, void* stream)
     {
         using namespace spb;

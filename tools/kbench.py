@@ -48,7 +48,7 @@ def main():
     dt = 1e-7
 
     def timeit(name, fn, bytes_per_cell):
-        if a.only and a.only not in name:
+        if a.only and not any(o in name for o in a.only.split(';')):
             return
         for _ in range(3):
             fn()

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) probe(double* out, int stride)
             a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
             a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
         }
-        if (MODE == 1 || MODE == 4)                      // 4 LDS.64 (stride in doubles chosen by the host)
+        if (MODE == 1 || MODE == 4 || MODE == 6)         // 4 LDS.64 (stride in doubles chosen by the host)
         {
             const volatile double* q = p;
             a0 += q[0]; a1 += q[1]; a2 += q[2]; a3 += q[3];
@@ -35,10 +35,21 @@ __global__ void __launch_bounds__(256) probe(double* out, int stride)
             double2 x = {q[0].x, q[0].y}, y = {q[256].x, q[256].y};
             a0 += x.x; a1 += x.y; a2 += y.x; a3 += y.y;
         }
-        if (MODE == 3 || MODE == 5)                      // 4 64-bit shuffles (8 SHFL.32)
+        if (MODE == 3 || MODE == 5 || MODE == 6)         // 4 64-bit shuffles (8 SHFL.32)
         {
             a0 += __shfl_up_sync(0xffffffffu, a4, 1); a1 += __shfl_up_sync(0xffffffffu, a5, 1);
             a2 += __shfl_up_sync(0xffffffffu, a6, 1); a3 += __shfl_up_sync(0xffffffffu, a7, 1);
+        }
+        if (MODE == 7 && (t & 31) == 0)                  // 4 LDS.64 issued by ONE lane of each warp (halo hand-off of a boundary lane)
+        {
+            const volatile double* q = p;
+            a0 += q[0]; a1 += q[1]; a2 += q[2]; a3 += q[3];
+        }
+        if (MODE == 8)                                   // 4 STS.64
+        {
+            volatile double* q = sm + (t*stride) % (256*5);
+            q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3;
+            a0 += 1e-9;
         }
     }
     out[blockIdx.x*256 + t] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
@@ -72,5 +83,8 @@ int main()
     run<3>("SHFL 64-bit x4", 1, 4, "warp-shfl64");
     run<4>("DFMA x8 + LDS.64 x4", 5, 8, "warp-DFMA");
     run<5>("DFMA x8 + SHFL64 x4", 1, 8, "warp-DFMA");
+    run<6>("LDS.64 x4 + SHFL64 x4", 5, 4, "warp-LDS.64 (and as many shfl64)");
+    run<7>("LDS.64 x4, one lane per warp", 5, 4, "warp-LDS.64");
+    run<8>("STS.64 x4 stride 5", 5, 4, "warp-STS.64");
     return 0;
 }
