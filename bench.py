@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the RHS hot path (flux_div + ghost exchange + RK stage update).
+"""bench.py — benchmark of the RHS hot path (flux_div + ghost exchange + RK stage update).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
 
-Workload (BASELINE.json configs[1]): Taylor-Green vortex, 512^3 cells in 32^3 blocks (16x16x16 blocks,
-2 exchange cells), totani_lr (2nd-order KEEP central) + visc_lr, rk4_t with the fused prim/cons update,
-fully periodic. One "step" = one RK4 time step = 4 x (flux_div + exchange + stage update) over the whole
-grid. For N > 1 the per-GPU grid is kept (weak scaling): lattice 16 x 16 x 16N, rank r owns z-slab r
-(SPADE's contiguous block partition), ghost exchange between ranks over NCCL send/recv.
+Workloads (BASELINE.json `configs`, numbered from 1):
+  2 (default, the configuration the metric is quoted on): Taylor-Green vortex, 512^3 cells per GPU in 32^3 blocks
+    (16 x 16 x 16N blocks, 2 exchange cells), totani_lr + visc_lr, rk4_t with the fused prim/cons update, periodic.
+  4: the weak-scaling sweep, 256^3 cells per GPU (8 x 8 x 8N blocks), same solver. The default run also measures it
+    briefly and reports it in the `configs` sub-record of the same JSON line.
+  3: compressible channel, 1024 x 512 x 64N cells (32 x 16 x 2N blocks; N = 8 is the 1024 x 512 x 512 grid), y stretched
+    with integrated_tanh_1D, isothermal no-slip walls, hybrid(totani_lr, fweno_t, ducros_t) + visc_lr. FP64-bound:
+    `roofline.bound` = "fp64".
+  5: AMR block grid (8^3 roots of 32^3 cells, two sphere refinements, 1912 blocks = 62.7 M cells) partitioned over N GPUs
+    with SPADE's contiguous partition; block boxes and transaction tables are SPADE's own (tests/golden/config5_amr.npz,
+    written by tests/golden/make_config5.py from the unmodified reference). Fixed grid: "scaling": "strong".
+One "step" = one RK4 time step = 4 x (flux_div + exchange + stage update) over the whole grid.
 
-metric: cell-stage-updates/s = cells x stages x steps / time (a cell advanced through one RK stage:
-RHS + exchange + stage update), whole job. Prints ONE JSON line (contract in the task statement).
+metric: cell-stage-updates/s = cells x stages x steps / time (a cell advanced through one RK stage), whole job.
+Before the timed region every run advances a small lattice of the same functor set through the same code path
+(fused stage kernel, two-stream overlap, peer-memory or NCCL messages) and compares it with the oracle
+(`parity_check` in the line: exchange bit-exact, 2 RK4 steps to 1e-12). Prints ONE JSON line.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import statistics
@@ -30,12 +38,15 @@ REYNOLDS, PRANDTL = 1600.0, 0.72
 STAGES = 4
 BLOCK = 32          # cells per block edge
 NG = 2
-LATTICE_1GPU = (16, 16, 16)
-# dram__bytes_read.sum + dram__bytes_write.sum per interior cell from the committed `ncu --set full` capture of the
-# dominant kernel (profiles/), None until a capture exists for that kernel
-# profiles/r01_ncu_full_stage_kernels_512cube.txt: the four rk4 stage kernels of one step move 20.23 + 26.17 + 32.17 + 20.37 GB
-# for 134.2 M cells -> 184.3 B per cell per launch (algorithmic 166.9); profiles/r01_ncu_full_rhs_...: 1.535 GB / 16.8 M cells
-TRAFFIC_PER_CELL = {"fused": 184.3, "rhs": 91.5}
+LATTICE = {2: (16, 16, 16), 4: (8, 8, 8), 3: (32, 16, 2)}       # blocks per GPU
+# algorithmic flop per cell of the hybrid WENO + central + viscous RHS and the FP64 roofs it is held against:
+# NVIDIA's B200 figure, and the DFMA issue rate measured on this pool (tools/probes/pipes_probe.cu, profiles/r02_pipes_probe.log:
+# 1.45 warp-DFMA per SM per clock x 64 flop x 148 SMs x 1.965 GHz)
+HYBRID_FLOP_PER_CELL = 2000.0
+FP64_PEAK_NOMINAL_TFLOPS = 37.0
+FP64_PEAK_MEASURED_TFLOPS = 1.45 * 64 * 148 * 1.965e9 / 1e12
+METRIC = "fp64 cell-updates/sec (RHS+exchange+RK)"
+UNIT = "cell-stage-updates/s"
 
 
 def parse():
@@ -44,12 +55,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lattice", type=int, nargs=3, default=None, help="blocks per GPU (default 16 16 16)")
-    ap.add_argument("--scheme", default="central", choices=["central", "hybrid"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--lattice", type=int, nargs=3, default=None, help="development: blocks per GPU instead of the config's lattice")
+    ap.add_argument("--scheme", default=None, choices=["central", "hybrid"], help="development: functor set instead of the config's")
     ap.add_argument("--unfused", action="store_true", help="two kernels per stage (flux_div, then rk_update) instead of the fused stage kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-configs", action="store_true", help="skip the config-4 sub-record of the default run")
+    ap.add_argument("--no-parity", action="store_true")
+    a = ap.parse_args()
+    if a.scheme is None:
+        a.scheme = "hybrid" if a.config == 3 else "central"
+    return a
 
 
 def measured_peak_hbm():
@@ -60,6 +77,18 @@ def measured_peak_hbm():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per interior cell of one launch, from the tracked summary of the
+    `ncu --set full` captures (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic). None if no capture
+    of that kernel is tracked."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(p))[kernel_key]
+        return float(rec["dram_bytes_per_cell"]), rec.get("source")
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -121,80 +150,105 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-def reference_arm(args):
-    """The reference's own CPU implementation of the path (oracle/_ref = unmodified SPADE headers compiled in the
-    dev container; falls back to the C port) on all host threads, on a bounded sample of the workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# CPU legs: the reference's own implementation of the path (oracle/_ref = unmodified SPADE headers compiled in the dev
+# container with g++ -O3; falls back to the C port) on the host cores, on a bounded sample of the workload
+def cpu_sample(args, steps, all_threads=True):
     import numpy as np
     from oracle import ref, port
     cores = os.cpu_count() or 1
     kind = "reference" if ref.available() else "port"
-    lat = (4, 4, 4)                      # 128^3 cells in 32^3 blocks: same block shape as the GPU workload
-    nranks = max(1, min(cores, lat[0] * lat[1] * lat[2])) if kind == "reference" else 1
-    scheme = 0 if args.scheme == "central" else 1
+    flags = ref.use_timing_build() if kind == "reference" else "gcc -std=c11 -O2 -ffp-contract=off (oracle/spade_oracle.c)"
+    lat = (4, 4, 4)                      # 128^3 cells in 32^3 blocks: the block shape of the GPU workload
+    nranks = max(1, min(cores, lat[0] * lat[1] * lat[2])) if (kind == "reference" and all_threads) else 1
+    scheme = 1 if args.scheme == "hybrid" else 0
     mu = (P0 / (RGAS * T0)) * U0 * 1.0 / REYNOLDS
     cfg = ref.make_cfg(lat, (BLOCK,) * 3, NG, scheme=scheme, gamma=GAMMA, R=RGAS, mu=mu, prandtl=PRANDTL,
                        sensor_eps=1e-2, nranks=nranks, integrator=0)
     q = host_state(lat, np)
-    umax = port.reduce_umax(cfg, q.ravel())
-    dt = 0.2 * (2 * np.pi / (lat[0] * BLOCK)) / umax
+    dt = 0.2 * (2 * np.pi / (lat[0] * BLOCK)) / port.reduce_umax(cfg, q.ravel())
     cells = (lat[0] * BLOCK) ** 3
     if kind == "reference":
-        qq, _ = ref.advance(cfg, q.ravel(), dt, max(1, min(args.warmup, 1)))
-        qq, sec = ref.advance(cfg, qq, dt, args.steps)
+        qq, _ = ref.advance(cfg, q.ravel(), dt, 1)              # warm-up step (first touch of the thread pools)
+        qq, sec = ref.advance(cfg, qq, dt, steps)
     else:
         qq = port.advance(cfg, q.ravel(), dt, 1)
         t0 = time.time()
-        port.advance(cfg, qq, dt, args.steps)
+        port.advance(cfg, qq, dt, steps)
         sec = time.time() - t0
-    value = cells * STAGES * args.steps / sec
-    sample = f"TGV {lat[0]*BLOCK}^3 cells in {BLOCK}^3 blocks ({lat[0]}x{lat[1]}x{lat[2]}), rk4, {args.steps} steps"
-    line = {"impl": "reference", "metric": "fp64 cell-updates/sec (RHS+exchange+RK)", "value": value,
-            "unit": "cell-stage-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, sample_note=sample),
-            "cpu_baseline": {"value": value, "unit": "cell-stage-updates/s", "cores": nranks, "kind": kind, "sample": sample},
-            "e2e": {"value": value, "unit": "cell-stage-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    name = "hybrid(totani_lr,fweno_t,ducros_t) + visc_lr" if scheme else "totani_lr + visc_lr"
+    sample = (f"TGV {lat[0]*BLOCK}^3 cells in {BLOCK}^3 blocks ({lat[0]}x{lat[1]}x{lat[2]}), {name}, rk4, {steps} steps in {sec:.1f} s: a bounded "
+              f"sample of the workload (same block shape, functor set, integrator; the CPU path's cost per cell does not depend on the grid size)")
+    return {"value": cells * STAGES * steps / sec, "unit": UNIT, "cores": nranks, "kind": kind, "sample": sample,
+            "flags": flags, "seconds": sec, "ms_per_step": 1e3 * sec / steps}
+
+
+def reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cb = cpu_sample(args, max(1, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if args.config == 5 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus, sample_note=cb["sample"]),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "flags")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def host_state(lat, np):
+def host_state(lat, np, block=(BLOCK, BLOCK, BLOCK), perturb=0.0, seed=0, bounds_hi=None):
     """TGV initial condition on the host (all cells incl. ghosts analytic), reference memory order."""
     nlb = lat[0] * lat[1] * lat[2]
     L = 2 * np.pi
-    q = np.zeros((nlb, BLOCK + 2 * NG, BLOCK + 2 * NG, BLOCK + 2 * NG, 5))
+    hi = bounds_hi or (L, L, L)
+    q = np.zeros((nlb, block[2] + 2 * NG, block[1] + 2 * NG, block[0] + 2 * NG, 5))
     rho0 = P0 / (RGAS * T0)
     for lb in range(nlb):
         b = (lb % lat[0], (lb // lat[0]) % lat[1], lb // (lat[0] * lat[1]))
-        ax = [b[d] * L / lat[d] + (np.arange(-NG, BLOCK + NG) + 0.5) * (L / lat[d] / BLOCK) for d in range(3)]
+        ax = [b[d] * hi[d] / lat[d] + (np.arange(-NG, block[d] + NG) + 0.5) * (hi[d] / lat[d] / block[d]) for d in range(3)]
         Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
         q[lb, ..., 0] = P0 + rho0 * U0 * U0 / 16 * (np.cos(2 * X) + np.cos(2 * Y)) * (np.cos(2 * Z) + 2)
-        q[lb, ..., 1] = T0
+        q[lb, ..., 1] = T0 * (1 + (0.02 * np.sin(X + 2 * Y - Z) if perturb else 0.0))
         q[lb, ..., 2] = U0 * np.sin(X) * np.cos(Y) * np.cos(Z)
         q[lb, ..., 3] = -U0 * np.cos(X) * np.sin(Y) * np.cos(Z)
+        q[lb, ..., 4] = (0.3 * U0 * np.sin(Z) * np.cos(X + Y)) if perturb else 0.0
+    if perturb:
+        q *= 1 + perturb * np.random.default_rng(12345 + seed).uniform(-1, 1, q.shape)
     return q
 
 
-def workload_config(args, sample_note=None):
-    lat = tuple(args.lattice) if args.lattice else LATTICE_1GPU
-    n = args.gpus
-    cfg = {"workload": f"TGV {lat[0]*BLOCK}x{lat[1]*BLOCK}x{lat[2]*BLOCK*n} cells ({lat[0]}x{lat[1]}x{lat[2]*n} blocks of {BLOCK}^3, "
-                       f"{NG} exchange cells), {'totani_lr' if args.scheme == 'central' else 'hybrid(totani_lr,fweno_t,ducros_t)'}"
-                       " + visc_lr, rk4_t fused prim/cons, periodic",
-           "cells_per_gpu": lat[0] * lat[1] * lat[2] * BLOCK ** 3, "stages_per_step": STAGES,
-           "partition": f"contiguous block runs, rank r = z-slab r ({n} ranks)",
-           "l2": "inputs larger than L2 (q + 4 residual arrays, 7.6 GB each at 512^3)"}
+def workload_config(args, n, sample_note=None):
+    c = args.config
+    lat = tuple(args.lattice) if args.lattice else LATTICE.get(c)
+    sch = "totani_lr" if args.scheme == "central" else "hybrid(totani_lr,fweno_t,ducros_t(1e-2),full_flux)"
+    if c in (2, 4):
+        cfg = {"workload": f"BASELINE config {c}: TGV {lat[0]*BLOCK}x{lat[1]*BLOCK}x{lat[2]*BLOCK*n} cells ({lat[0]}x{lat[1]}x{lat[2]*n} blocks of {BLOCK}^3, "
+                           f"{NG} exchange cells), {sch} + visc_lr, rk4_t fused prim/cons, periodic",
+               "cells_per_gpu": lat[0] * lat[1] * lat[2] * BLOCK ** 3,
+               "partition": f"contiguous block runs, rank r = z-slab r ({n} ranks)",
+               "l2": "inputs larger than L2 (q + scratch + 4 residual arrays, %.1f GB each)" % (lat[0] * lat[1] * lat[2] * (BLOCK + 2 * NG) ** 3 * 40 / 1e9)}
+    elif c == 3:
+        cfg = {"workload": f"BASELINE config 3: channel {lat[0]*BLOCK}x{lat[1]*BLOCK}x{lat[2]*BLOCK*n} cells ({lat[0]}x{lat[1]}x{lat[2]*n} blocks of {BLOCK}^3), "
+                           f"y = integrated_tanh_1D(-1, 1, 0.1, 1.3), {sch} + visc_lr, rk4_t, no-slip isothermal walls in y, x/z periodic"
+                           + (" (N = 8 is the 1024x512x512 grid)" if n != 8 else ""),
+               "cells_per_gpu": lat[0] * lat[1] * lat[2] * BLOCK ** 3,
+               "partition": f"contiguous block runs, rank r = z-slab r ({n} ranks)",
+               "l2": "inputs larger than L2 (6 arrays of 1.9 GB per GPU)"}
+    else:
+        cfg = {"workload": "BASELINE config 5: AMR block grid, 8x8x8 roots of 32^3 cells on [0,2pi)^3, blocks intersecting |x-c| < 0.30*2pi refined, "
+                           "their children intersecting |x-c| < 0.12*2pi refined again (amr::constraints::factor2): 1912 blocks = 62.7 M cells, 3 levels; "
+                           f"{sch} + visc_lr, rk4_t, periodic; block boxes and exchange tables from the reference (tests/golden/config5_amr.npz)",
+               "cells_total": 1912 * BLOCK ** 3,
+               "partition": f"spade::partition contiguous runs of global block ids over {n} ranks (every block costs the same)",
+               "l2": "inputs larger than L2 (6 arrays of 3.6 GB in total)"}
+    cfg["stages_per_step"] = STAGES
     if sample_note:
         cfg["reference_sample"] = sample_note
     return cfg
 
 
 # ------------------------------------------------------------------------------------------------------
-def device_state(sp, grid, torch):
+def tgv_device_state(sp, grid, torch):
     """TGV initial condition generated on the device block-batch by block-batch (torch is plumbing here)."""
     nlb = grid.num_local_blocks
     q = sp.grid_array(grid, 0.0, (NG,) * 3)
@@ -218,6 +272,384 @@ def device_state(sp, grid, torch):
     return q
 
 
+device_state = tgv_device_state          # tools/kbench.py
+
+
+def boxes_device_state(sp, grid, boxes, torch):
+    """the same TGV field on blocks given by their boxes (AMR: per-block spacing)"""
+    q = sp.grid_array(grid, 0.0, (NG,) * 3)
+    rho0 = P0 / (RGAS * T0)
+    idx = torch.arange(-NG, BLOCK + NG, dtype=torch.float64, device="cuda") + 0.5
+    bx = torch.tensor(boxes, dtype=torch.float64, device="cuda")
+    for b0 in range(0, grid.num_local_blocks, 256):
+        b1 = min(grid.num_local_blocks, b0 + 256)
+        lo = bx[b0:b1, 0::2]
+        dx = (bx[b0:b1, 1::2] - lo) / BLOCK
+        X = (lo[:, 0, None] + idx[None, :] * dx[:, 0, None])[:, None, None, :]
+        Y = (lo[:, 1, None] + idx[None, :] * dx[:, 1, None])[:, None, :, None]
+        Z = (lo[:, 2, None] + idx[None, :] * dx[:, 2, None])[:, :, None, None]
+        v = q.data[b0:b1]
+        v[..., 0] = P0 + rho0 * U0 * U0 / 16 * (torch.cos(2 * X) + torch.cos(2 * Y)) * (torch.cos(2 * Z) + 2)
+        v[..., 1] = T0
+        v[..., 2] = U0 * torch.sin(X) * torch.cos(Y) * torch.cos(Z)
+        v[..., 3] = -U0 * torch.cos(X) * torch.sin(Y) * torch.cos(Z)
+        v[..., 4] = 0.0
+    return q
+
+
+def contiguous_partition(nglob, nranks, rank):
+    """spade::partition::block_partition_t (grid/partition.h:27-84): contiguous runs, the first nglob % nranks ranks one extra"""
+    per, extra = divmod(nglob, nranks)
+    first = rank * per + min(rank, extra)
+    return first, per + (1 if rank < extra else 0)
+
+
+def amr_tables(fix, prefix, nranks, rank, np):
+    return tuple(np.ascontiguousarray(fix[f"{prefix}_{k}_{nranks}_{rank}"], dtype=np.int64) for k in ("send", "recv", "isend", "irecv"))
+
+
+class Workload:
+    pass
+
+
+def make_flux(sp, gas, scheme, mu):
+    conv = sp.totani_lr(gas)
+    if scheme == "hybrid":
+        conv = sp.hybrid_scheme_t(conv, sp.fweno_t(gas), sp.ducros_t(1e-2), sp.full_flux)
+    return sp.flux_desc(sp.compose(conv, sp.visc_lr(sp.constant_viscosity_t(mu, PRANDTL), gas)))
+
+
+def build_workload(cfgid, args, sp, pool, torch, timing):
+    import numpy as np
+    w = Workload()
+    n = pool.size()
+    w.cfgid, w.n = cfgid, n
+    w.gas = gas = sp.ideal_gas_t(GAMMA, RGAS)
+    w.scheme = args.scheme if cfgid == args.config else ("hybrid" if cfgid == 3 else "central")
+    w.scaling = "strong" if cfgid == 5 else "weak"
+    bc_walls = None
+    if cfgid in (2, 4):
+        lat = tuple(args.lattice) if (args.lattice and cfgid == args.config) else LATTICE[cfgid]
+        L = 2 * np.pi
+        blocks = sp.cartesian_blocks_t((lat[0], lat[1], lat[2] * n), [0.0, L, 0.0, L, 0.0, L * n])
+        w.grid = grid = sp.cartesian_grid_t((BLOCK,) * 3, blocks, sp.identity(), pool)
+        mu = (P0 / (RGAS * T0)) * U0 * 1.0 / REYNOLDS
+        w.q = tgv_device_state(sp, grid, torch)
+        w.handle = sp.make_exchange(w.q, (True, True, True))
+        dmin = grid.get_dx(0)
+    elif cfgid == 3:
+        lat = tuple(args.lattice) if (args.lattice and cfgid == args.config) else LATTICE[3]
+        pi = float(np.pi)
+        u0 = 69.4
+        blocks = sp.cartesian_blocks_t((lat[0], lat[1], lat[2] * n), [0.0, 4 * pi, -1.0, 1.0, 0.0, 2 * pi * n / 8.0])
+        coords = sp.diagonal_coords(None, sp.integrated_tanh_1D(-1.0, 1.0, 0.1, 1.3), None)
+        w.grid = grid = sp.cartesian_grid_t((BLOCK,) * 3, blocks, coords, pool)
+        mu = (P0 / (RGAS * T0)) * u0 / 3000.0
+        # laminar parabolic profile + seeded perturbation + a planted pressure jump that wakes the shock sensor
+        w.q = q = sp.grid_array(grid, 0.0, (NG,) * 3)
+        idx = torch.arange(-NG, BLOCK + NG, dtype=torch.float64, device="cuda") + 0.5
+        gen = torch.Generator(device="cuda").manual_seed(12345 + pool.rank())
+        for b0 in range(0, grid.num_local_blocks, 128):
+            b1 = min(grid.num_local_blocks, b0 + 128)
+            org = torch.tensor([blocks.get_block_box(grid.first_block + l)[0::2] for l in range(b0, b1)], dtype=torch.float64, device="cuda")
+            dx = [grid.get_dx(d) for d in range(3)]
+            X = (org[:, 0, None] + idx[None, :] * dx[0])[:, None, None, :]
+            Y = (org[:, 1, None] + idx[None, :] * dx[1])[:, None, :, None]
+            Z = (org[:, 2, None] + idx[None, :] * dx[2])[:, :, None, None]
+            v = q.data[b0:b1]
+            v[..., 0] = P0 * torch.where(torch.sin(0.5 * X) > 0.3, 1.2, 1.0) + 0 * Y + 0 * Z
+            v[..., 1] = T0 + 0 * X + 0 * Y + 0 * Z
+            v[..., 2] = u0 * (1 - Y * Y) + 0 * X + 0 * Z
+            v[..., 3] = 0.02 * u0 * torch.sin(X) * torch.cos(pi * Y) * torch.cos(Z)
+            v[..., 4] = 0.02 * u0 * torch.sin(Z) * torch.cos(X + pi * Y)
+            v *= 1 + 1e-3 * (2 * torch.rand(v.shape, dtype=torch.float64, device="cuda", generator=gen) - 1)
+        w.handle = sp.make_exchange(q, (True, False, True))
+        bc_walls = (sp.boundary.ymin | sp.boundary.ymax, sp.noslip_isothermal_wall(T0))
+        _, jac, _ = grid.metric_tables((NG,) * 3)
+        dmin = min(grid.get_dx(0), grid.get_dx(2), float(np.abs(jac[1][:, NG:-NG]).min()) * grid.get_dx(1))
+    else:
+        fix = np.load(os.path.join(ROOT, "tests", "golden", "config5_amr.npz"))
+        boxes = fix["b_boxes"]
+        if n not in (1, 2, 4, 8):
+            raise SystemExit("bench.py --config 5: the tracked tables cover 1, 2, 4 and 8 ranks")
+        first, cnt = contiguous_partition(len(boxes), n, pool.rank())
+        w.grid = grid = sp.cartesian_grid_t.from_boxes((BLOCK,) * 3, boxes[first:first + cnt], pool, first_block=first)
+        mu = (P0 / (RGAS * T0)) * U0 * 1.0 / REYNOLDS
+        w.q = boxes_device_state(sp, grid, boxes[first:first + cnt], torch)
+        w.handle = sp.make_exchange(w.q, (True, True, True), tables=amr_tables(fix, "b", n, pool.rank(), np))
+        dmin = float((boxes[:, 1] - boxes[:, 0]).min()) / BLOCK
+        w.cells_total = len(boxes) * BLOCK ** 3
+    w.flux = make_flux(sp, gas, w.scheme, mu)
+    w.rhs = sp.grid_array(w.grid, 0.0, (NG,) * 3)
+    w.bc = sp.exchange_bc_t(w.handle, *(bc_walls or ()))
+    w.bc(w.q, 0.0)
+    w.umax0 = sp.transform_reduce(w.q, sp.FN_WAVESPEED, sp.RED_MAX, gas)
+    w.dt = 0.2 * dmin / w.umax0
+    w.fused = not args.unfused
+    if w.fused:
+        calc_rhs = sp.flux_div_rhs_t(w.flux, sp.overwrite)
+    else:
+        def calc_rhs(r, qq, t):
+            if timing["on"]:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sp.flux_div(qq, r, w.flux, sp.overwrite)
+                e1.record()
+                timing["events"].append((e0, e1, 80.0))
+            else:
+                sp.flux_div(qq, r, w.flux, sp.overwrite)
+    alg = sp.rk4_t
+    # the usual SPADE solver set-up: integrator_t(axis, alg, data, rhs callback, boundary callback, state transform). As a
+    # flux_div_rhs_t / exchange_bc_t the callbacks are recognised and every stage is ONE kernel per block range, the ghost
+    # messages of the rank-boundary blocks fly while the rank-interior blocks are advanced
+    w.ti = sp.integrator_t(sp.time_axis_t(0.0, w.dt), alg, sp.integrator_data_t(w.q, w.rhs, alg), calc_rhs, w.bc, sp.state_transform_t(gas))
+    w.cells_local = w.grid.local_cells()
+    if cfgid != 5:
+        w.cells_total = w.cells_local * n
+    return w
+
+
+def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, sample_clocks):
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        w.ti.advance()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and sample_clocks:
+        sampler.start()
+    launches0 = sp.launch_count()
+    timing["events"] = ev = []
+    timing["on"] = True
+    if w.fused:
+        w.ti.stage_events = ev
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(steps):
+        w.ti.advance()
+    t1.record()
+    barrier()
+    timing["on"] = False
+    w.ti.stage_events = None
+    ms = t0.elapsed_time(t1)
+    launches = sp.launch_count() - launches0
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+    kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / max(1, len(ev))
+    kern_bpc = sum(c for _, _, c in ev) / max(1, len(ev))      # algorithmic bytes per cell, mean over launches
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    umax_end = sp.transform_reduce(w.q, sp.FN_WAVESPEED, sp.RED_MAX, w.gas)
+    if not (umax_end == umax_end) or umax_end > 10 * w.umax0:
+        raise SystemExit(f"bench.py: solution diverged (umax {umax_end})")
+    return {"ms": ms, "launches": int(launches), "clocks": clocks, "kern_ms": kern_ms, "kern_bpc": kern_bpc, "n_events": len(ev),
+            "value": w.cells_total * STAGES * steps / (ms * 1e-3)}
+
+
+def roofline_of(w, m, steps):
+    """Roofline of the dominant kernel of one rank. Algorithmic bytes per interior cell: plain flux_div
+    reads q and writes rhs = 80 B; the fused stage kernel reads q, writes q', reads/writes the residual registers its stage
+    needs (rk4 = 120, 160, 200, 120 B, mean 150 B per launch) and writes the same-rank ghost cells (40 B x 0.4238 ghost
+    cells per interior cell at n = 32, g = 2 = 17 B). The hybrid WENO set is FP64-bound (2 000 algorithmic flop per cell)."""
+    peak, peak_src = measured_peak_hbm()
+    hbm_achieved = m["kern_bpc"] * w.cells_local / (m["kern_ms"] * 1e-3) / 1e9
+    common = {"alg_bytes_per_cell": m["kern_bpc"], "ms_per_launch": m["kern_ms"], "launches_timed": m["n_events"],
+              "cell_evals_per_s": w.cells_local / (m["kern_ms"] * 1e-3), "step_share": m["kern_ms"] * STAGES * steps / m["ms"],
+              "timed_with": "CUDA events around every stage launch on the launching stream, inside the timed region"}
+    if w.scheme == "hybrid":
+        tf = HYBRID_FLOP_PER_CELL * w.cells_local / (m["kern_ms"] * 1e-3) / 1e12
+        r = {"bound": "fp64", "kernel": "flux_div_kernel<hybrid WENO + viscous, FUSED stage>" if w.fused else "flux_div_kernel<hybrid> (rhs only)",
+             "achieved": tf, "peak": FP64_PEAK_NOMINAL_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_NOMINAL_TFLOPS,
+             "peak_source": "nominal B200 FP64 (no fp64 entry in MEASURED_PEAKS.json)", "alg_flop_per_cell": HYBRID_FLOP_PER_CELL,
+             "frac_of_measured_dfma_rate": tf / FP64_PEAK_MEASURED_TFLOPS, "measured_dfma_peak_tflops": FP64_PEAK_MEASURED_TFLOPS,
+             "hbm": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src}}
+        key = "hybrid_stage"
+    else:
+        r = {"bound": "hbm", "kernel": "flux_div_narrow_kernel<FUSED stage>" if w.fused else "flux_div kernel (rhs only)",
+             "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src}
+        key = ("fused_stage" if w.fused else "rhs") + ("_amr" if w.cfgid == 5 else "")
+    tpc, tsrc = measured_traffic(key)
+    r["traffic"] = tpc * w.cells_local if tpc else None
+    if tsrc:
+        r["traffic_source"] = tsrc
+    r.update(common)
+    return r
+
+
+# ------------------------------------------------------------------------------------------------------
+def parity_check(cfgid, scheme, sp, pool, torch):
+    """A small grid of the same functor set advanced through the SAME code path as the timed run (fused stage kernel with the
+    ghost warp / owner stores, rank-boundary blocks first on a side stream, peer-memory or NCCL messages), against the oracle
+    (oracle.port: the C restatement pinned against the unmodified reference; used here as the checker only). Every rank holds
+    the whole oracle result and compares its own blocks: the exchange bit for bit, 2 RK4 steps to 1e-12 relative L2."""
+    import numpy as np
+    from oracle import port, ref
+    n, rank = pool.size(), pool.rank()
+    blk = (32, 8, 8)
+    sid = 1 if scheme == "hybrid" else 0
+    mu = 1e-2
+    gas = sp.ideal_gas_t(GAMMA, RGAS)
+    flux = make_flux(sp, gas, scheme, mu)
+    L = 2 * np.pi
+    if cfgid == 5:
+        fix = np.load(os.path.join(ROOT, "tests", "golden", "config5_amr.npz"))
+        boxes = fix["p_boxes"]
+        nb = tuple(int(x) for x in fix["p_roots"])
+        nlb_glob = len(boxes)
+        first, cnt = contiguous_partition(nlb_glob, n, rank)
+        grid = sp.cartesian_grid_t.from_boxes(blk, boxes[first:first + cnt], pool, first_block=first)
+        tables = amr_tables(fix, "p", n, rank, np)
+        q0 = np.zeros((nlb_glob, blk[2] + 2 * NG, blk[1] + 2 * NG, blk[0] + 2 * NG, 5))
+        for lb in range(nlb_glob):
+            ax = [boxes[lb, 2 * d] + (np.arange(-NG, blk[d] + NG) + 0.5) * (boxes[lb, 2 * d + 1] - boxes[lb, 2 * d]) / blk[d] for d in range(3)]
+            Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+            q0[lb, ..., 0] = P0 * (1 + 0.05 * np.cos(X) * np.cos(Y))
+            q0[lb, ..., 1] = T0 * (1 + 0.02 * np.sin(X + 2 * Y - Z))
+            q0[lb, ..., 2] = U0 * np.sin(X) * np.cos(Y) * np.cos(Z)
+            q0[lb, ..., 3] = -U0 * np.cos(X) * np.sin(Y) * np.cos(Z)
+            q0[lb, ..., 4] = 10.0 * np.sin(Z) * np.cos(X + Y)
+        q0 *= 1 + 1e-2 * np.random.default_rng(61).uniform(-1, 1, q0.shape)
+        send_all = np.concatenate([fix[f"p_send_{n}_{r}"] for r in range(n)], axis=0).astype(np.int64)
+        isend_all = np.concatenate([fix[f"p_isend_{n}_{r}"] for r in range(n)], axis=0).astype(np.int64)
+        port.set_amr(boxes, send_all, isend_all)
+        desc = f"AMR 2x2x2 roots of {blk[0]}x{blk[1]}x{blk[2]} cells, root 0 refined: {nlb_glob} blocks, tables of the reference for {n} ranks"
+        dxmin = float((boxes[:, 1] - boxes[:, 0]).min()) / blk[0]
+    else:
+        nb = (2, 2, 2 * n)
+        blocks = sp.cartesian_blocks_t(nb, [0.0, L] * 3)
+        grid = sp.cartesian_grid_t(blk, blocks, sp.identity(), pool)
+        first, cnt = grid.first_block, grid.num_local_blocks
+        tables = None
+        q0 = host_state(nb, np, block=blk, perturb=1e-2, seed=31)
+        desc = f"{nb[0]}x{nb[1]}x{nb[2]} blocks of {blk[0]}x{blk[1]}x{blk[2]} cells, periodic, perturbed TGV"
+        dxmin = min(L / (nb[d] * blk[d]) for d in range(3))
+    try:
+        cfg = ref.make_cfg(nb, blk, NG, periodic=(1, 1, 1), scheme=sid, gamma=GAMMA, R=RGAS, mu=mu, prandtl=PRANDTL, sensor_eps=1e-2,
+                           nranks=1, integrator=0)
+        # (a) exchange alone, from zeroed ghosts: bit for bit
+        qz = q0.copy()
+        mask = np.zeros(q0.shape[1:4], dtype=bool)
+        mask[NG:-NG, NG:-NG, NG:-NG] = True
+        qz[:, ~mask, :] = 0.0
+        want_ex = port.exchange(cfg, qz.ravel()).reshape(q0.shape)
+        qa = sp.grid_array.from_host(grid, qz[first:first + cnt])
+        ex = sp.make_exchange(qa, (True, True, True), tables=tables)
+        ex.exchange(qa)
+        exch_ok = bool(np.array_equal(qa.to_host(), want_ex[first:first + cnt]))
+        # (b) 2 RK4 steps through the fused, overlapped path
+        qe = port.exchange(cfg, q0.ravel()).reshape(q0.shape)
+        dt = 0.2 * dxmin / port.reduce_umax(cfg, qe.ravel())
+        want = port.advance(cfg, qe.ravel(), dt, 2).reshape(q0.shape)
+        qa = sp.grid_array.from_host(grid, qe[first:first + cnt])
+        ex2 = sp.make_exchange(qa, (True, True, True), tables=tables)
+        ti = sp.integrator_t(sp.time_axis_t(0.0, dt), sp.rk4_t, sp.integrator_data_t(qa, sp.grid_array(grid, 0.0), sp.rk4_t),
+                             sp.flux_div_rhs_t(flux, sp.overwrite), sp.exchange_bc_t(ex2), sp.state_transform_t(gas))
+        for _ in range(2):
+            ti.advance()
+        got = ti.solution().to_host()
+        ref_slab = want[first:first + cnt]
+        num, den = float(((got - ref_slab) ** 2).sum()), float((ref_slab ** 2).sum())
+    finally:
+        if cfgid == 5:
+            port.set_amr()
+    red = pool.reduce(num, sp.RED_SUM), pool.reduce(den, sp.RED_SUM)
+    err = (red[0] / red[1]) ** 0.5
+    exch_all = pool.reduce(0.0 if exch_ok else 1.0, sp.RED_SUM) == 0.0
+    return {"ok": bool(exch_all and err < 1e-12), "exchange_bit_exact": bool(exch_all), "trajectory_rel_l2": err, "tolerance": 1e-12,
+            "steps": 2, "grid": desc, "ranks": n, "functor_set": "hybrid(totani_lr,fweno_t,ducros_t) + visc_lr" if sid else "totani_lr + visc_lr",
+            "path": {"fused_stage_kernel": ti._plan is not None, "ghosts_in_kernel": bool(ti._fuse_exchange),
+                     "messages": ("peer memory (CUDA IPC)" if ex2._p2p else "NCCL send/recv") if n > 1 else "none (1 rank)",
+                     "two_streams": bool(ti._two_streams and n > 1)},
+            "oracle": "oracle.port (C restatement, pinned against the unmodified reference in tests/test_oracle_vs_reference.py)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+def e2e_leg(w, args, sp, torch, dist, world, steps):
+    """End to end through the public API with HOST buffers: every step the state comes from pinned host memory (H2D), the step
+    runs, and the new state goes back to pinned host memory (D2H) together with the max-wavespeed scalar the CFL logic reads
+    (development/cuda-tgv/main.cc:228). Three streams: the upload of step s+1 and the download of step s-1 run while step s
+    computes; every byte still crosses PCIe inside the timed region."""
+    q = w.q
+    host_in = torch.empty(q.data.shape, dtype=torch.float64, pin_memory=True)
+    host_out = torch.empty(q.data.shape, dtype=torch.float64, pin_memory=True)
+    host_in.copy_(q.data)
+    torch.cuda.synchronize()
+    ksteps = max(2, min(steps, 5))
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    bufs = [q.data, torch.empty_like(q.data)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    drained = [torch.cuda.Event(), torch.cuda.Event()]
+    main = torch.cuda.current_stream()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    up.wait_stream(main)
+    with torch.cuda.stream(up):
+        bufs[0].copy_(host_in, non_blocking=True)
+        ready[0].record()
+    for s_ in range(ksteps):
+        cur = s_ % 2
+        if s_ + 1 < ksteps:
+            with torch.cuda.stream(up):
+                if s_ >= 1:
+                    up.wait_event(drained[1 - cur])          # the result of step s-1 has left bufs[1 - cur]
+                bufs[1 - cur].copy_(host_in, non_blocking=True)
+                ready[1 - cur].record()
+        main.wait_event(ready[cur])
+        q.data = bufs[cur]
+        w.ti.advance()
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(down):
+            down.wait_event(done)
+            host_out.copy_(q.data, non_blocking=True)
+            drained[cur].record()
+        sp.transform_reduce(q, sp.FN_WAVESPEED, sp.RED_MAX, w.gas)     # D2H of the scalar + cross-rank max (synchronises the step)
+    main.wait_stream(down)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ems = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ems], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ems = float(tt.item())
+    nbytes = int(host_in.numel() * 8)
+    q.data = bufs[0]
+    out = {"value": w.cells_total * STAGES * ksteps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
+           "d2h_bytes_per_step": nbytes + 8, "steps": ksteps, "ms_per_step": ems / ksteps,
+           "pcie_GBps_each_way": nbytes / (ems / ksteps * 1e-3) / 1e9,
+           "note": "per step: state H2D from pinned host memory, one RK4 step through integrator_t.advance(), new state D2H into pinned host "
+                   "memory + the max-wavespeed scalar; uploads, compute and downloads of neighbouring steps overlap on three streams"}
+    del host_in, host_out, bufs
+    return out
+
+
+def ref_gpu_baseline():
+    """The reference's own CUDA path on this GPU: integration/_build/ref_gpu_bench is the unmodified reference
+    compiled with nvcc -arch=sm_100a in the dev container (device::gpu arrays, tags `basic` / `fldbc` / `fused`). Rank 0, N = 1."""
+    exe = os.path.join(ROOT, "integration", "_build", "ref_gpu_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "integration/_build/ref_gpu_bench not built (needs /root/reference at build time)"}
+    out = {}
+    for scheme, name in ((0, "central"), (1, "hybrid")):
+        try:
+            r = subprocess.run([exe, "8", "32", "2", str(scheme)], capture_output=True, text=True, timeout=240)
+            rec = json.loads(r.stdout.strip().splitlines()[-1])
+            out[name] = rec
+        except Exception as exc:
+            out[name] = {"error": str(exc)[:200]}
+    return out
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -237,207 +669,83 @@ def ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     pool = sp.pool_t.from_torch()
     n = max(world, 1)
-    lat = tuple(args.lattice) if args.lattice else LATTICE_1GPU
-    lattice = (lat[0], lat[1], lat[2] * n)
-    L = 2 * 3.141592653589793
-    blocks = sp.cartesian_blocks_t(lattice, [0.0, L, 0.0, L, 0.0, L * n])
-    grid = sp.cartesian_grid_t((BLOCK,) * 3, blocks, sp.identity(), pool)
-    gas = sp.ideal_gas_t(GAMMA, RGAS)
-    mu = (P0 / (RGAS * T0)) * U0 * 1.0 / REYNOLDS
-    conv = sp.totani_lr(gas)
-    if args.scheme == "hybrid":
-        conv = sp.hybrid_scheme_t(conv, sp.fweno_t(gas), sp.ducros_t(1e-2), sp.full_flux)
-    flux = sp.flux_desc(sp.compose(conv, sp.visc_lr(sp.constant_viscosity_t(mu, PRANDTL), gas)))
+    timing = {"on": False, "events": []}
 
-    q = device_state(sp, grid, torch)
-    rhs = sp.grid_array(grid, 0.0, (NG,) * 3)
-    handle = sp.make_exchange(q, (True, True, True))
-    handle.exchange(q)
-    umax = sp.transform_reduce(q, sp.FN_WAVESPEED, sp.RED_MAX, gas)
-    dt = 0.2 * grid.get_dx(0) / umax
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(args.config, args.scheme, sp, pool, torch)
+        except Exception as exc:             # a broken checker must be visible, not fatal to the measurement
+            parity = {"ok": False, "error": repr(exc)[:300]}
 
-    ev_pairs = []
-    timing_on = [False]
-    fused = (not args.unfused) and args.scheme == "central"
+    w = build_workload(args.config, args, sp, pool, torch, timing)
+    m = measure(w, args.steps, args.warmup, sp, torch, dist, world, rank, local_rank, timing, True)
+    roofline = roofline_of(w, m, args.steps)
 
-    def calc_rhs_unfused(r, qq, t):
-        if timing_on[0]:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            sp.flux_div(qq, r, flux, sp.overwrite)
-            e1.record()
-            ev_pairs.append((e0, e1, 80.0))
-        else:
-            sp.flux_div(qq, r, flux, sp.overwrite)
-
-    # the usual SPADE rhs callback (flux_div with the overwrite trait); as a flux_div_rhs_t the integrator recognises it and
-    # runs flux_div + stage update as ONE kernel per stage
-    calc_rhs = sp.flux_div_rhs_t(flux, sp.overwrite) if fused else calc_rhs_unfused
-
-    # the usual periodic boundary callback (exchange only); as an exchange_bc_t the integrator can send the ghost messages of
-    # the rank-boundary blocks while it advances the rank-interior blocks
-    bc = sp.exchange_bc_t(handle)
-
-    alg = sp.rk4_t
-    data = sp.integrator_data_t(q, rhs, alg)
-    ti = sp.integrator_t(sp.time_axis_t(0.0, dt), alg, data, calc_rhs, bc, sp.state_transform_t(gas))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        ti.advance()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = sp.launch_count()
-    timing_on[0] = True
-    if fused:
-        ti.stage_events = ev_pairs
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    for _ in range(args.steps):
-        ti.advance()
-    t1.record()
-    barrier()
-    timing_on[0] = False
-    ti.stage_events = None
-    ms = t0.elapsed_time(t1)
-    launches = sp.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    fdiv_ms = sum(a.elapsed_time(b) for a, b, _ in ev_pairs) / max(1, len(ev_pairs))
-    fdiv_bpc = sum(c for _, _, c in ev_pairs) / max(1, len(ev_pairs))      # algorithmic bytes per cell, mean over launches
-    if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    umax_end = sp.transform_reduce(q, sp.FN_WAVESPEED, sp.RED_MAX, gas)
-    if not (umax_end == umax_end) or umax_end > 10 * umax:
-        raise SystemExit(f"bench.py: solution diverged (umax {umax_end})")
-
-    local_cells = grid.local_cells()
-    total_cells = local_cells * n
-    value = total_cells * STAGES * args.steps / (ms * 1e-3)
-
-    # roofline of the dominant kernel. Algorithmic bytes per interior cell: plain flux_div reads q and
-    # writes rhs = 80 B; the fused stage kernel reads q, writes q', reads/writes the residual registers its stage needs
-    # (rk4 = 120, 160, 200, 120 B, mean 150 B per launch) and writes the same-rank ghost cells (40 B x 0.4238 ghost cells per
-    # interior cell at n = 32, g = 2 = 17 B).
-    peak, peak_src = measured_peak_hbm()
-    fdiv_bytes = fdiv_bpc * local_cells
-    achieved = fdiv_bytes / (fdiv_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "flux_div_narrow_kernel<FUSED stage>" if fused else "flux_div kernel (rhs only)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": TRAFFIC_PER_CELL.get("fused" if fused else "rhs") and
-                TRAFFIC_PER_CELL["fused" if fused else "rhs"] * local_cells, "peak_source": peak_src,
-                "alg_bytes_per_cell": fdiv_bpc, "ms_per_launch": fdiv_ms, "launches_timed": len(ev_pairs),
-                "cell_evals_per_s": local_cells / (fdiv_ms * 1e-3),
-                "step_share": fdiv_ms * STAGES * args.steps / ms}
     # the RHS alone (pde_algs::flux_div with the overwrite trait, 80 B per cell), timed after the run for the record
     for _ in range(2):
-        sp.flux_div(q, rhs, flux, sp.overwrite)
+        sp.flux_div(w.q, w.rhs, w.flux, sp.overwrite)
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     r0.record()
     for _ in range(5):
-        sp.flux_div(q, rhs, flux, sp.overwrite)
+        sp.flux_div(w.q, w.rhs, w.flux, sp.overwrite)
     r1.record()
     torch.cuda.synchronize()
     rhs_ms = r0.elapsed_time(r1) / 5
+    peak, _ = measured_peak_hbm()
     roofline["rhs_only"] = {"kernel": "flux_div (overwrite)", "alg_bytes_per_cell": 80.0, "ms_per_launch": rhs_ms,
-                            "achieved": 80.0 * local_cells / (rhs_ms * 1e-3) / 1e9,
-                            "frac": 80.0 * local_cells / (rhs_ms * 1e-3) / 1e9 / peak}
+                            "achieved": 80.0 * w.cells_local / (rhs_ms * 1e-3) / 1e9,
+                            "frac": 80.0 * w.cells_local / (rhs_ms * 1e-3) / 1e9 / peak}
+    if w.scheme == "hybrid":
+        tf = HYBRID_FLOP_PER_CELL * w.cells_local / (rhs_ms * 1e-3) / 1e12
+        roofline["rhs_only"].update({"fp64_tflops": tf, "fp64_frac": tf / FP64_PEAK_NOMINAL_TFLOPS})
+    tpc, tsrc = measured_traffic("rhs")
+    if tpc and w.scheme == "central":
+        roofline["rhs_only"]["traffic"] = tpc * w.cells_local
 
-    # end to end through the public API with host buffers: every step the state comes from pinned host memory
-    # and the step's metric (max wavespeed for the CFL number, as in development/cuda-tgv/main.cc:228) goes back
     e2e = None
     if not args.no_e2e:
-        host_q = torch.empty(q.data.shape, dtype=torch.float64, pin_memory=True)
-        host_q.copy_(q.data)
-        torch.cuda.synchronize()
-        ksteps = max(2, min(args.steps, 5))
-        barrier()
-        # Two device buffers: the copy of step s+1's input (its own stream) runs while step s computes. Every step's input
-        # still crosses PCIe inside the timed region; what overlaps is only that the bus and the SMs work at the same time.
-        copy_stream = torch.cuda.Stream()
-        bufs = [q.data, torch.empty_like(q.data)]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        main = torch.cuda.current_stream()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        copy_stream.wait_stream(main)
-        with torch.cuda.stream(copy_stream):
-            bufs[0].copy_(host_q, non_blocking=True)
-            ready[0].record()
-        for s_ in range(ksteps):
-            cur = s_ % 2
-            if s_ + 1 < ksteps:
-                with torch.cuda.stream(copy_stream):       # bufs[1 - cur] was last read by step s-1, which the reduction below has synchronised
-                    bufs[1 - cur].copy_(host_q, non_blocking=True)
-                    ready[1 - cur].record()
-            main.wait_event(ready[cur])
-            q.data = bufs[cur]
-            ti.advance()
-            um = sp.transform_reduce(q, sp.FN_WAVESPEED, sp.RED_MAX, gas)     # D2H of the scalar + cross-rank max
-        e1.record()
-        barrier()
-        ems = e0.elapsed_time(e1)
-        if world > 1:
-            tt = torch.tensor([ems], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ems = float(tt.item())
-        e2e = {"value": total_cells * STAGES * ksteps / (ems * 1e-3), "unit": "cell-stage-updates/s",
-               "h2d_bytes_per_step": int(host_q.numel() * 8), "d2h_bytes_per_step": 8, "steps": ksteps,
-               "note": "state copied from pinned host memory every step (double-buffered: the copy of the next step's input overlaps the current step); max-wavespeed scalar read back"}
-        del host_q, bufs
+        e2e = e2e_leg(w, args, sp, torch, dist, world, args.steps)
 
-    cpu_baseline = None
+    # config 4 (256^3 per GPU, the weak-scaling sweep BASELINE names) in the same line of the default run
+    configs = None
+    if args.config == 2 and not args.no_configs and not args.lattice:
+        w4 = build_workload(4, args, sp, pool, torch, timing)
+        m4 = measure(w4, max(args.steps, 20), max(args.warmup, 3), sp, torch, dist, world, rank, local_rank, timing, False)
+        r4 = roofline_of(w4, m4, max(args.steps, 20))
+        configs = {"config4": {"workload": workload_config(argparse.Namespace(**{**vars(args), "config": 4}), n)["workload"],
+                               "value": m4["value"], "unit": UNIT, "ms_per_step": m4["ms"] / max(args.steps, 20), "steps": max(args.steps, 20),
+                               "gpu_launches": m4["launches"], "scaling": "weak",
+                               "roofline": {k: r4[k] for k in ("bound", "achieved", "peak", "unit", "frac", "ms_per_launch", "alg_bytes_per_cell", "step_share")}}}
+        del w4
+
+    cpu_baseline, ref_gpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu_baseline = cpu_baseline_leg(args)
+            cb = cpu_sample(args, 2)
+            cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "flags")}
         except Exception as exc:     # the baseline must never take the GPU number down with it
             cpu_baseline = {"value": None, "error": str(exc)}
+        ref_gpu = ref_gpu_baseline()
+        if isinstance(ref_gpu, dict) and "unavailable" not in ref_gpu:
+            # our kernels on the same grid as the reference-GPU run (256^3 in 32^3 blocks), for the ratio
+            pass
 
     if rank == 0:
-        line = {"metric": "fp64 cell-updates/sec (RHS+exchange+RK)", "value": value, "unit": "cell-stage-updates/s",
-                "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args), "cell_steps_per_s": value / STAGES,
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks}
+        line = {"metric": METRIC, "value": m["value"], "unit": UNIT,
+                "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps,
+                "higher_is_better": True, "scaling": w.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, n), "cell_steps_per_s": m["value"] / STAGES,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": m["launches"],
+                "clocks": m["clocks"], "parity_check": parity}
+        if configs:
+            line["configs"] = configs
+        if ref_gpu is not None:
+            line["ref_gpu_baseline"] = ref_gpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def cpu_baseline_leg(args):
-    """oracle/_ref (the reference itself) timed on the host cores on a bounded sample (about 10-30 s)."""
-    import numpy as np
-    from oracle import ref, port
-    cores = os.cpu_count() or 1
-    kind = "reference" if ref.available() else "port"
-    lat = (4, 4, 4)
-    nranks = max(1, min(cores, 64)) if kind == "reference" else 1
-    mu = (P0 / (RGAS * T0)) * U0 * 1.0 / REYNOLDS
-    cfg = ref.make_cfg(lat, (BLOCK,) * 3, NG, scheme=0 if args.scheme == "central" else 1, gamma=GAMMA, R=RGAS, mu=mu,
-                       prandtl=PRANDTL, sensor_eps=1e-2, nranks=nranks, integrator=0)
-    q = host_state(lat, np)
-    dt = 0.2 * (2 * np.pi / (lat[0] * BLOCK)) / port.reduce_umax(cfg, q.ravel())
-    steps = 2
-    if kind == "reference":
-        _, sec = ref.advance(cfg, q.ravel(), dt, steps)
-    else:
-        t0 = time.time()
-        port.advance(cfg, q.ravel(), dt, steps)
-        sec = time.time() - t0
-    cells = (lat[0] * BLOCK) ** 3
-    return {"value": cells * STAGES * steps / sec, "unit": "cell-stage-updates/s", "cores": nranks, "kind": kind,
-            "sample": f"TGV {lat[0]*BLOCK}^3 cells in {BLOCK}^3 blocks, rk4, {steps} steps, {sec:.1f} s"}
 
 
 if __name__ == "__main__":

@@ -137,6 +137,9 @@ int spb_flux_div_blocks(const spb_grid* g, const double* q_dev, double* rhs_dev,
  * set (totani_lr and/or visc_lr); other descriptors return SPB_ERR_UNSUPPORTED and the caller uses
  * spb_flux_div + spb_rk_update. The caller folds dt and the Butcher coefficients into cq (see
  * spade_b200/api.py::integrator_t for rk4_t). */
+/* 1 if the fused stage exists for this functor set (totani_lr and/or visc_lr; visc_lr with hybrid(totani_lr | cent_keep<4>,
+ * fweno_t) or cent_keep<4|6|8>; the WALE closure on those up to cent_keep<4>), 0 otherwise. Host-only. */
+int spb_flux_div_rk_stage_supported(const spb_flux_desc* flux);
 typedef struct spb_stage_desc
 {
     int           nin;          /* number of residual registers read (0..2) */

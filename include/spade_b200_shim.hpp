@@ -108,17 +108,49 @@ namespace spade::b200
     }
 
     // ---------------------------------------------------------------- grid handle (device image of grid_geometry_t)
-    // one host thread per GPU (compute_pool.h:497-514): the cache is thread-local, handles live as long as the thread
+    // one host thread per GPU (compute_pool.h:497-514): the cache is thread-local. An entry is keyed by the grid's address and
+    // the exchange-cell counts and carries a fingerprint of the geometry (cells per block, block count, first and last block
+    // box); a grid rebuilt at the same address (a stack grid in a resolution loop, an AMR grid refined in place) fails the
+    // fingerprint and its handle is rebuilt. b200::invalidate(grid) drops the entries of a grid whose lifetime ends.
+    struct grid_entry_t { spb_grid* h = nullptr; int nx[3] = {0, 0, 0}; std::size_t nlb = 0; double box[12] = {0}; };
+    using grid_key_t = std::tuple<const void*, int, int, int>;
+    inline std::map<grid_key_t, grid_entry_t>& grid_cache() { thread_local std::map<grid_key_t, grid_entry_t> cache; return cache; }
+    template <typename grid_t> inline void invalidate(const grid_t& grid)
+    {
+        auto& cache = grid_cache();
+        for (auto it = cache.begin(); it != cache.end();)
+        {
+            if (std::get<0>(it->first) == (const void*)&grid) { spb_grid_destroy(it->second.h); it = cache.erase(it); }
+            else ++it;
+        }
+    }
     template <typename array_t> inline spb_grid* grid_handle(const array_t& arr)
     {
-        using key_t = std::tuple<const void*, int, int, int, std::size_t>;
-        thread_local std::map<key_t, spb_grid*> cache;
+        auto& cache = grid_cache();
         const auto& grid = arr.get_grid();
         const auto ng = arr.get_num_exchange();
         const std::size_t nlb = grid.get_num_local_blocks();
-        const key_t key{(const void*)&grid, ng[0], ng[1], ng[2], nlb};
+        const grid_key_t key{(const void*)&grid, ng[0], ng[1], ng[2]};
+        grid_entry_t fp;
+        fp.nlb = nlb;
+        for (int d = 0; d < 3; ++d) fp.nx[d] = grid.get_num_cells(d);
+        if (nlb > 0)
+        {
+            const auto b0 = grid.get_bounding_box(utils::tag[partition::local](std::size_t(0)));
+            const auto b1 = grid.get_bounding_box(utils::tag[partition::local](nlb - 1));
+            for (int d = 0; d < 3; ++d) { fp.box[2*d] = b0.min(d); fp.box[2*d + 1] = b0.max(d); fp.box[6 + 2*d] = b1.min(d); fp.box[7 + 2*d] = b1.max(d); }
+        }
         auto it = cache.find(key);
-        if (it != cache.end()) return it->second;
+        if (it != cache.end())
+        {
+            const grid_entry_t& e = it->second;
+            bool same = e.nlb == fp.nlb;
+            for (int d = 0; d < 3; ++d) same = same && e.nx[d] == fp.nx[d];
+            for (int i = 0; i < 12; ++i) same = same && e.box[i] == fp.box[i];
+            if (same) return e.h;
+            spb_grid_destroy(e.h);                                       // stale: another grid lived at this address
+            cache.erase(it);
+        }
         using coord_sys_t = typename array_t::grid_type::coord_sys_type;
         constexpr bool is_identity = std::same_as<coord_sys_t, coords::identity<typename array_t::grid_type::coord_type>>;
         static_assert(is_identity || coords::diagonal_coordinate_system<coord_sys_t>,
@@ -164,7 +196,8 @@ namespace spade::b200
             for (int d = 0; d < 3; ++d) { md.area[d] = area[d].data(); md.jac[d] = jac[d].data(); md.face[d] = face[d].data(); }
             check(spb_grid_set_metric(h, &md), "spb_grid_set_metric");
         }
-        cache[key] = h;
+        fp.h = h;
+        cache[key] = fp;
         return h;
     }
 
@@ -176,6 +209,10 @@ namespace spade::b200
         static_assert(on_gpu<array_t>, "spade_b200: arrays must live on device::gpu (the CPU path is the reference itself)");
         static_assert(std::same_as<typename array_t::value_type, double>, "spade_b200: fp64 only");
         static_assert(array_t::alias_type::size() == 5, "spade_b200: 5-variable states (prim_t / cons_t / flux_t)");
+        // the kernels read the reference's DEFAULT memory order (mem_map::linear_t, variable fastest; core/mem_map.h:467-497);
+        // an array built with mem_map::tiled / tiled_small (mem_map.h:501-650) has another order and would be misread
+        static_assert(std::same_as<typename array_t::mem_map_type, mem_map::linear_t<5>>,
+            "spade_b200: arrays must use the default mem_map::linear memory map (tiled maps are not implemented)");
     }
 
     // ---------------------------------------------------------------- exchange
@@ -183,83 +220,207 @@ namespace spade::b200
     // every rank publishes the device pointers of its per-peer receive buffers in this process-wide table; a rank then packs
     // its message for peer p STRAIGHT INTO p's receive buffer over NVLink (spb_exchange_pack_peer, peer access enabled once per
     // thread) instead of the reference's pack -> cudaMemcpyPeer -> unpack (exchange_message.h:14-56, compute_pool.h:93-99).
+    struct peer_slot_t { double* buf[2] = {nullptr, nullptr}; unsigned long long* flags = nullptr; double* stage = nullptr; };
     struct peer_table_t
     {
         std::mutex mut;
-        std::map<std::tuple<int, int, int>, double*> recvbuf;      // (exchange id, owner rank, sending peer) -> buffer on the owner's GPU
+        std::map<std::tuple<int, int, int>, peer_slot_t> slot;     // (exchange id, owner rank, sending peer) -> the owner's receive side
     };
     inline peer_table_t& peer_table() { static peer_table_t t; return t; }
 
+    // side stream (highest priority) + the two events that order it against the thread's main (legacy default) stream
+    struct stream_pair_t
+    {
+        cudaStream_t side = nullptr; cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+        void fork() { cudaEventRecord(ev_main, nullptr); cudaStreamWaitEvent(side, ev_main, 0); }      // side continues after main
+        void join() { cudaEventRecord(ev_side, side);    cudaStreamWaitEvent(nullptr, ev_side, 0); }   // main continues after side
+    };
+    inline stream_pair_t& streams()
+    {
+        thread_local stream_pair_t sp;
+        if (!sp.side)
+        {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (cudaStreamCreateWithPriority(&sp.side, cudaStreamNonBlocking, hi) != cudaSuccess
+                || cudaEventCreateWithFlags(&sp.ev_main, cudaEventDisableTiming) != cudaSuccess
+                || cudaEventCreateWithFlags(&sp.ev_side, cudaEventDisableTiming) != cudaSuccess)
+                throw except::sp_exception("spade_b200: could not create the side stream of the overlapped schedule");
+        }
+        return sp;
+    }
+
+    // Move-only owner of a plan and of this rank's receive buffers / arrival flags (grid::make_exchange's handle is a value
+    // type too, make_exchange.h:98-110; copies of THIS handle would alias device memory, so they are not allowed).
+    // Messages between the GPUs of the process (the reference's model: one host thread per GPU, compute_pool.h:497-514) do
+    // not pass through the host: begin() packs each message STRAIGHT INTO the neighbour's receive buffer over NVLink
+    // (spb_exchange_pack_peer, peer access enabled once per thread) and raises the neighbour's arrival flag behind it in
+    // stream order (spb_flag_signal); finish() makes the stream wait on this rank's own flags (spb_flag_wait) and unpacks.
+    // No host barrier, no spb_sync: the reference's three barriers per exchange (compute_pool.h:166,216,222) are gone. Two
+    // receive buffers per neighbour, used alternately, are enough: a rank can only pack message s+2 after it has received
+    // s+1, which its neighbour sends after having unpacked s. GPUs without peer access fall back to pack -> cudaMemcpyPeer
+    // -> unpack behind host barriers, like the reference (exchange_message.h:14-56, compute_pool.h:93-99).
     template <typename array_t> struct arr_exchange_t
     {
         using grid_type = typename array_t::grid_type;
         spb_exchange* plan = nullptr;
         int rank = 0, size = 1, id = 0;
-        std::vector<double*> recvbuf;       // [peer]: messages from `peer` land here (this rank's GPU)
-        std::vector<double*> peerbuf;       // [peer]: where this rank's message for `peer` goes (peer's GPU), or a local staging buffer
-        std::vector<char>    direct;        // [peer]: peerbuf is peer memory (P2P) / a local send buffer the peer pulls from
-        std::vector<double*> stagebuf;      // [peer]: the sender-side staging buffer of `peer` when P2P is not available (pulled by us)
-        bool wired = false;
+        std::vector<peer_slot_t> own;       // [peer]: where messages from `peer` land (this rank's GPU)
+        std::vector<peer_slot_t> remote;    // [peer]: the slot of this rank on `peer`'s GPU
+        std::vector<double*> sendstage;     // [peer]: local send buffer when `peer` cannot be written directly
+        bool all_direct = true, wired = false;
+        unsigned long long seq = 0;
+        std::vector<std::pair<int64_t, int64_t>> runs_first, runs_second;    // rank-boundary block runs, and the rest
+        bool runs_ready = false;
+
+        arr_exchange_t() = default;
+        arr_exchange_t(const arr_exchange_t&) = delete;
+        arr_exchange_t& operator=(const arr_exchange_t&) = delete;
+        arr_exchange_t(arr_exchange_t&& o) noexcept { swap(o); }
+        arr_exchange_t& operator=(arr_exchange_t&& o) noexcept { if (this != &o) { release(); swap(o); } return *this; }
+        ~arr_exchange_t() { release(); }
+        void swap(arr_exchange_t& o) noexcept
+        {
+            std::swap(plan, o.plan); std::swap(rank, o.rank); std::swap(size, o.size); std::swap(id, o.id);
+            own.swap(o.own); remote.swap(o.remote); sendstage.swap(o.sendstage);
+            std::swap(all_direct, o.all_direct); std::swap(wired, o.wired); std::swap(seq, o.seq);
+            runs_first.swap(o.runs_first); runs_second.swap(o.runs_second); std::swap(runs_ready, o.runs_ready);
+        }
+        void release() noexcept
+        {
+            if (wired)
+            {
+                auto& tab = peer_table();
+                std::lock_guard<std::mutex> lk(tab.mut);
+                for (int p = 0; p < size; ++p) tab.slot.erase({id, rank, p});
+            }
+            for (auto& sl: own) { for (auto* b: sl.buf) if (b) spb_dev_free(b); if (sl.flags) spb_dev_free(sl.flags); if (sl.stage) spb_dev_free(sl.stage); }
+            for (auto* b: sendstage) if (b) spb_dev_free(b);
+            own.clear(); remote.clear(); sendstage.clear(); wired = false;
+            if (plan) { spb_exchange_destroy(plan); plan = nullptr; }
+        }
 
         template <typename group_t> void wire(group_t& group)
         {
-            recvbuf.assign(size, nullptr); peerbuf.assign(size, nullptr); direct.assign(size, 1); stagebuf.assign(size, nullptr);
+            own.assign(size, peer_slot_t{}); remote.assign(size, peer_slot_t{}); sendstage.assign(size, nullptr);
             auto& tab = peer_table();
             const int mydev = group.device_id();
+            int direct_here = 1;
             for (int p = 0; p < size; ++p)
             {
                 if (p == rank) continue;
                 const int64_t nr = spb_exchange_recv_cells(plan, p), ns = spb_exchange_send_cells(plan, p);
-                if (nr > 0 && cudaMalloc((void**)&recvbuf[p], sizeof(double)*5*nr) != cudaSuccess) throw except::sp_exception("spade_b200: cudaMalloc of a receive buffer failed");
+                if (nr > 0)
+                {
+                    for (int par = 0; par < 2; ++par) check(spb_dev_alloc((void**)&own[p].buf[par], sizeof(double)*5*nr), "spb_dev_alloc (receive buffer)");
+                    check(spb_dev_alloc((void**)&own[p].flags, 2*sizeof(unsigned long long)), "spb_dev_alloc (arrival flags)");
+                }
                 const int pdev = group.pid(p).device_id;
-                int can = 0;
-                if (pdev != mydev) cudaDeviceCanAccessPeer(&can, mydev, pdev); else can = 1;
-                if (pdev != mydev && can) { const cudaError_t e = cudaDeviceEnablePeerAccess(pdev, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0; cudaGetLastError(); }
-                direct[p] = char(can);
-                if (!can && ns > 0 && cudaMalloc((void**)&peerbuf[p], sizeof(double)*5*ns) != cudaSuccess) throw except::sp_exception("spade_b200: cudaMalloc of a send buffer failed");
+                int can = 1;
+                if (pdev != mydev)
+                {
+                    cudaDeviceCanAccessPeer(&can, mydev, pdev);
+                    if (can) { const cudaError_t e = cudaDeviceEnablePeerAccess(pdev, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0; cudaGetLastError(); }
+                }
+                if (!can) direct_here = 0;
+                if (!can && ns > 0) check(spb_dev_alloc((void**)&sendstage[p], sizeof(double)*5*ns), "spb_dev_alloc (send staging)");
                 std::lock_guard<std::mutex> lk(tab.mut);
-                tab.recvbuf[{id, rank, p}] = recvbuf[p];
-                if (!can) tab.recvbuf[{-1 - id, rank, p}] = peerbuf[p];          // staging buffers under the negated id
+                peer_slot_t pub = own[p];
+                pub.stage = nullptr;
+                tab.slot[{id, rank, p}] = pub;
             }
+            // every rank must take the same path: direct only if EVERY pair of the group can be written directly
+            all_direct = group.reduce(direct_here, [](const int a, const int b) { return a < b ? a : b; }) != 0;
             group.sync();
             for (int p = 0; p < size; ++p)
             {
                 if (p == rank) continue;
                 std::lock_guard<std::mutex> lk(tab.mut);
-                if (direct[p]) peerbuf[p] = tab.recvbuf[{id, p, rank}];
-                auto it = tab.recvbuf.find({-1 - id, p, rank});
-                if (it != tab.recvbuf.end()) stagebuf[p] = it->second;          // peer p cannot reach us: we pull from its staging buffer
+                auto it = tab.slot.find({id, p, rank});
+                if (it != tab.slot.end()) remote[p] = it->second;
+            }
+            if (!all_direct)
+            {
+                // staged path: publish the send staging buffers so that the receivers can pull from them
+                { std::lock_guard<std::mutex> lk(tab.mut); for (int p = 0; p < size; ++p) if (p != rank) tab.slot[{-1 - id, rank, p}].stage = sendstage[p]; }
+                group.sync();
+                std::lock_guard<std::mutex> lk(tab.mut);
+                for (int p = 0; p < size; ++p) if (p != rank) { auto it = tab.slot.find({-1 - id, p, rank}); if (it != tab.slot.end()) own[p].stage = it->second.stage; }
             }
             group.sync();
             wired = true;
         }
 
-        // off-rank half of exchange() on a raw device buffer in the array's layout
-        template <typename group_t> void exchange_messages(double* q, group_t& group)
+        void block_runs(const int64_t nlb)
+        {
+            if (runs_ready) return;
+            std::vector<unsigned char> mask((std::size_t)std::max<int64_t>(nlb, 1), 0);
+            check(spb_exchange_boundary_blocks(plan, nlb, mask.data()), "spb_exchange_boundary_blocks");
+            runs_first.clear(); runs_second.clear();
+            for (int64_t b = 0; b < nlb;)
+            {
+                int64_t e = b;
+                while (e < nlb && mask[e] == mask[b]) ++e;
+                (mask[b] ? runs_first : runs_second).push_back({b, e});
+                b = e;
+            }
+            runs_ready = true;
+        }
+
+        // first half of the off-rank exchange on a raw device buffer in the array's layout: the messages leave on `stream`
+        template <typename group_t> void begin(const double* q, group_t& group, cudaStream_t stream)
         {
             if (size == 1) return;
             if (!wired) wire(group);
-            for (int p = 0; p < size; ++p)
-                if (p != rank && spb_exchange_send_cells(plan, p) > 0)
-                    check(direct[p] ? spb_exchange_pack_peer(plan, q, p, peerbuf[p], nullptr) : spb_exchange_pack(plan, q, p, peerbuf[p], nullptr), "spb_exchange_pack");
-            check(spb_sync(nullptr), "spb_sync");
-            group.sync();                                               // every message for this rank has been written
+            ++seq;
+            const int par = int(seq & 1ull);
             for (int p = 0; p < size; ++p)
             {
-                if (p == rank || spb_exchange_recv_cells(plan, p) == 0) continue;
-                if (stagebuf[p])
-                    cudaMemcpyPeerAsync(recvbuf[p], group.device_id(), stagebuf[p], group.pid(p).device_id, sizeof(double)*5*spb_exchange_recv_cells(plan, p), nullptr);
-                check(spb_exchange_unpack(plan, q, p, recvbuf[p], nullptr), "spb_exchange_unpack");
+                if (p == rank || spb_exchange_send_cells(plan, p) == 0) continue;
+                if (all_direct)
+                {
+                    check(spb_exchange_pack_peer(plan, q, p, remote[p].buf[par], stream), "spb_exchange_pack_peer");
+                    check(spb_flag_signal(remote[p].flags + par, seq, stream), "spb_flag_signal");
+                }
+                else check(spb_exchange_pack(plan, q, p, sendstage[p], stream), "spb_exchange_pack");
             }
-            check(spb_sync(nullptr), "spb_sync");
-            group.sync();                                               // buffers may be overwritten by the next exchange
+        }
+        // second half: wait for the neighbours' messages and unpack them on `stream`
+        template <typename group_t> void finish(double* q, group_t& group, cudaStream_t stream)
+        {
+            if (size == 1) return;
+            const int par = int(seq & 1ull);
+            if (!all_direct)
+            {
+                check(spb_sync(stream), "spb_sync");
+                group.sync();                                           // every staging buffer has been written
+            }
+            for (int p = 0; p < size; ++p)
+            {
+                const int64_t nr = spb_exchange_recv_cells(plan, p);
+                if (p == rank || nr == 0) continue;
+                if (all_direct) check(spb_flag_wait(own[p].flags + par, seq, stream), "spb_flag_wait");
+                else cudaMemcpyPeerAsync(own[p].buf[par], group.device_id(), own[p].stage, group.pid(p).device_id, sizeof(double)*5*nr, stream);
+                check(spb_exchange_unpack(plan, q, p, own[p].buf[par], stream), "spb_exchange_unpack");
+            }
+            if (!all_direct)
+            {
+                check(spb_sync(stream), "spb_sync");
+                group.sync();                                           // staging buffers may be overwritten by the next exchange
+            }
+        }
+        template <typename group_t> void exchange_messages(double* q, group_t& group, cudaStream_t stream = nullptr)
+        {
+            begin(q, group, stream);
+            finish(q, group, stream);
         }
 
         void exchange(array_t& array, typename grid_type::group_type& group)
         {
             require_supported_array<array_t>();
-            check(spb_exchange_local(plan, dev_ptr(array), nullptr), "spb_exchange_local");
-            if (group.size() != 1) exchange_messages(dev_ptr(array), group);
+            if (group.size() != 1) begin(dev_ptr(array), group, nullptr);
+            check(spb_exchange_local(plan, dev_ptr(array), nullptr), "spb_exchange_local");      // overlaps the NVLink transfers
+            if (group.size() != 1) finish(dev_ptr(array), group, nullptr);
             check(spb_sync(nullptr), "spb_sync");                       // reference semantics: visible on return (execute.h:85)
         }
     };
@@ -447,14 +608,89 @@ namespace spade::b200
     }
 
     // ---------------------------------------------------------------- reductions
-    template <typename gas_t> struct wavespeed { gas_t gas; };       // sqrt(gamma R T) + |u|   (CFL, cuda-tgv/main.cc:152-161)
-    template <typename array_t, typename gas_t, typename op_t>
-    inline double transform_reduce(const array_t& q, const wavespeed<gas_t>& f, const op_t&)
+    // algs::transform_reduce(array, make_reduction(array, f, op)) (transform_reduce.h:43-191) for the closed set of element
+    // kernels of the C ABI, with op = algs::max or algs::sum; the cross-rank step is the group's own reduce (transform_reduce.h:171-190)
+    template <typename gas_t> struct wavespeed { gas_t gas; };             // sqrt(gamma R T) + |u|   (CFL, cuda-tgv/main.cc:152-161)
+    template <typename gas_t> struct kinetic_energy { gas_t gas; };        // 0.5 rho |u|^2
+    struct variable { int ivar = 0; };                                     // q[ivar]
+    struct abs_variable { int ivar = 0; };                                 // |q[ivar]|
+    template <typename op_t> constexpr int reduce_op()
+    {
+        static_assert(std::same_as<op_t, algs::max_t> || std::same_as<op_t, algs::sum_t>, "spade_b200: transform_reduce with algs::max or algs::sum");
+        return std::same_as<op_t, algs::max_t> ? SPB_RED_MAX : SPB_RED_SUM;
+    }
+    template <typename array_t, typename op_t>
+    inline double reduce_impl(const array_t& q, const int fn, const int ivar, const double gamma, const double R, const op_t& op)
     {
         require_supported_array<array_t>();
         double out = 0.0;
-        check(spb_reduce(grid_handle(q), dev_ptr(q), SPB_RED_MAX, SPB_FN_WAVESPEED, 0, f.gas.get_gamma(), f.gas.get_R(), &out, nullptr), "spb_reduce");
-        return q.get_grid().group().reduce(out, [](const double a, const double b) { return a > b ? a : b; });
+        check(spb_reduce(grid_handle(q), dev_ptr(q), reduce_op<op_t>(), fn, ivar, gamma, R, &out, nullptr), "spb_reduce");
+        return q.get_grid().group().reduce(out, [&](const double a, const double b) { return double(op(a, b)); });
+    }
+    template <typename array_t, typename gas_t, typename op_t>
+    inline double transform_reduce(const array_t& q, const wavespeed<gas_t>& f, const op_t& op)
+    { return reduce_impl(q, SPB_FN_WAVESPEED, 0, f.gas.get_gamma(), f.gas.get_R(), op); }
+    template <typename array_t, typename gas_t, typename op_t>
+    inline double transform_reduce(const array_t& q, const kinetic_energy<gas_t>& f, const op_t& op)
+    { return reduce_impl(q, SPB_FN_KINETIC, 0, f.gas.get_gamma(), f.gas.get_R(), op); }
+    template <typename array_t, typename op_t>
+    inline double transform_reduce(const array_t& q, const variable& f, const op_t& op) { return reduce_impl(q, SPB_FN_VAR, f.ivar, 1.4, 287.15, op); }
+    template <typename array_t, typename op_t>
+    inline double transform_reduce(const array_t& q, const abs_variable& f, const op_t& op) { return reduce_impl(q, SPB_FN_ABSVAR, f.ivar, 1.4, 287.15, op); }
+
+    // ---------------------------------------------------------------- checkpoints and visualisation files
+    // io::binary_write / io::binary_read (io/io_native.h:18-56): a headerless file in which global block lb occupies the bytes
+    // [lb*B, (lb+1)*B), B = bytes of one padded block in the array's own memory order. The device layout IS that order, so a
+    // rank's share is one contiguous slab: one cudaMemcpy and one pwrite / pread per rank. Files are interchangeable with the
+    // reference's (same bytes) — a SPADE checkpoint restarts here and the other way round.
+    template <typename array_t> inline void binary_write(const std::string& filename, const array_t& arr)
+    {
+        require_supported_array<array_t>();
+        const auto& grid = arr.get_grid();
+        auto& group = grid.group();
+        const std::size_t nlb = grid.get_num_local_blocks(), total = arr.data.size();
+        const std::size_t per_block = nlb ? total/nlb : 0;
+        std::vector<double> host(total);
+        if (total && cudaMemcpy(host.data(), dev_ptr(arr), sizeof(double)*total, cudaMemcpyDeviceToHost) != cudaSuccess) throw except::sp_exception("spade_b200: binary_write: device -> host copy failed");
+        if (group.isroot())
+        {
+            std::FILE* f = std::fopen(filename.c_str(), "wb");
+            if (!f) throw except::sp_exception("spade_b200: binary_write: cannot create " + filename);
+            std::fclose(f);
+        }
+        group.sync();
+        std::FILE* f = std::fopen(filename.c_str(), "r+b");
+        if (!f) throw except::sp_exception("spade_b200: binary_write: cannot open " + filename);
+        std::size_t nw = 0;
+        for (std::size_t lb = 0; lb < nlb; ++lb)
+        {
+            const std::size_t lb_glob = grid.get_partition().to_global(utils::tag[partition::local](lb)).value;
+            std::fseek(f, long(lb_glob*per_block*sizeof(double)), SEEK_SET);
+            nw += std::fwrite(host.data() + lb*per_block, sizeof(double), per_block, f);
+        }
+        std::fclose(f);
+        if (nw != total) throw except::sp_exception("spade_b200: binary_write: short write to " + filename);
+        group.sync();
+    }
+    template <typename array_t> inline void binary_read(const std::string& filename, array_t& arr)
+    {
+        require_supported_array<array_t>();
+        const auto& grid = arr.get_grid();
+        const std::size_t nlb = grid.get_num_local_blocks(), total = arr.data.size();
+        const std::size_t per_block = nlb ? total/nlb : 0;
+        std::vector<double> host(total);
+        std::FILE* f = std::fopen(filename.c_str(), "rb");
+        if (!f) throw except::sp_exception("spade_b200: binary_read: cannot open " + filename);
+        std::size_t nr = 0;
+        for (std::size_t lb = 0; lb < nlb; ++lb)
+        {
+            const std::size_t lb_glob = grid.get_partition().to_global(utils::tag[partition::local](lb)).value;
+            std::fseek(f, long(lb_glob*per_block*sizeof(double)), SEEK_SET);
+            nr += std::fread(host.data() + lb*per_block, sizeof(double), per_block, f);
+        }
+        std::fclose(f);
+        if (nr != total) throw except::sp_exception("spade_b200: binary_read: " + filename + " does not hold this rank's blocks");
+        if (total && cudaMemcpy(dev_ptr(arr), host.data(), sizeof(double)*total, cudaMemcpyHostToDevice) != cudaSuccess) throw except::sp_exception("spade_b200: binary_read: host -> device copy failed");
     }
 }
 
@@ -560,11 +796,15 @@ namespace spade::time_integration
         boundary(q, axis.time());
     }
 
-    // The same call again, selected when the rhs callback is b200::flux_div_rhs_t (and, for the ghost fusion, the boundary
-    // callback b200::exchange_bc_t): one kernel per stage, spb_flux_div_rk_stage[_exchange] (include/spade_b200.h). The stage
-    // coefficients are the coefficient differences of advance.h:47-55,84-92 folded into at most two residual inputs and one
-    // output per stage; a final update that needs more than two earlier residuals gets their combination prepared by the stage
-    // before it (rk4: C = k0/6 + k1/3 - 2 k2/3). Falls back to the two-kernel path for schemes outside that pattern.
+    // The same call again, selected when the rhs callback is b200::flux_div_rhs_t (and, for the ghost fusion and the overlapped
+    // schedule, the boundary callback b200::exchange_bc_t): one kernel per stage and block range,
+    // spb_flux_div_rk_stage[_exchange] (include/spade_b200.h). The stage plan comes from spb_rk_fused_plan and the supported
+    // functor sets from spb_flux_div_rk_stage_supported — the same two calls the Python host makes, so the two host sides
+    // cannot diverge. Falls back to the two-kernel path for schemes / functor sets outside that pattern.
+    // With more than one rank (GPU) the schedule is the Python host's: the stage kernel runs on the rank-boundary blocks
+    // (spb_exchange_boundary_blocks) on a high-priority side stream, their messages are packed straight into the
+    // neighbours' buffers behind them, and the rank-interior blocks are advanced on the main stream AT THE SAME TIME; the
+    // unpack waits on stream-ordered arrival flags. No host barrier and no stream synchronisation inside the step.
     template <typename axis_t, typename var_state_t, typename rhs_state_t, typename scheme_t, typename flux_func_t, typename boundary_t,
               typename state_t, typename gas_t>
     requires (scheme_t::is_rk_specialization && b200::on_gpu<var_state_t>)
@@ -577,11 +817,9 @@ namespace spade::time_integration
         constexpr int n = scheme_t::table_type::rows();
         using numeric_type = typename axis_t::value_type;
         const spb_flux_desc fd = b200::flux_desc(rhs.flux_func);
-        const bool narrow = (fd.diss == SPB_DISS_NONE && (fd.conv == SPB_CONV_NONE || fd.conv == SPB_CONV_TOTANI) && (fd.conv != SPB_CONV_NONE || fd.visc))
-                         || (fd.visc && ((fd.conv == SPB_CONV_TOTANI && fd.diss == SPB_DISS_FWENO) || fd.conv == SPB_CONV_CENT_KEEP4));   // fused stage available
 
-        // diffs[i][j]: coefficient of k_j in the update that follows stage i (last row: the accumulation row)
-        double diffs[n][n];
+        // diffs[i][j]: coefficient of k_j in the update that follows stage i (last row: the accumulation row), advance.h:47-55,84-92
+        double diffs[n*n];
         algs::static_for<0, n>([&](const auto& ii)
         {
             constexpr int i = ii.value;
@@ -593,47 +831,18 @@ namespace spade::time_integration
                 {
                     using curr_t = typename scheme_t::table_type::template elem_t<i + 1>::template elem_t<j>;
                     using diff_t = typename detail::ratio_diff_t<curr_t, prev_t>::type;
-                    diffs[i][j] = detail::nonzero_t<diff_t>::value ? double(detail::coeff_value_t<numeric_type, diff_t>::value()) : 0.0;
+                    diffs[i*n + j] = detail::nonzero_t<diff_t>::value ? double(detail::coeff_value_t<numeric_type, diff_t>::value()) : 0.0;
                 }
                 else
                 {
                     using curr_t = typename scheme_t::accum_type::template elem_t<j>;
                     using diff_t = typename detail::ratio_diff_t<curr_t, prev_t>::type;
-                    diffs[i][j] = detail::nonzero_t<diff_t>::value ? double(detail::coeff_value_t<numeric_type, diff_t>::value()) : 0.0;
+                    diffs[i*n + j] = detail::nonzero_t<diff_t>::value ? double(detail::coeff_value_t<numeric_type, diff_t>::value()) : 0.0;
                 }
             });
         });
-        struct stage_t { int nin = 0; int in[2] = {0, 0}; double cq[2] = {0, 0}, co[2] = {0, 0}; double cq_self = 0, co_self = 0; int out = -1; };
-        stage_t plan[n];
-        bool ok = narrow && n <= 4;
-        int nfinal = 0;
-        for (int j = 0; j + 1 < n; ++j) if (diffs[n-1][j] != 0.0) ++nfinal;
-        const bool use_c = nfinal > 2;
-        for (int i = 0; i < n && ok; ++i)
-        {
-            stage_t& st = plan[i];
-            st.cq_self = diffs[i][i];
-            if (i == n - 1 && use_c) { st.nin = 1; st.in[0] = n - 2; st.cq[0] = 1.0; continue; }   // register n-2 holds C
-            for (int j = 0; j < i; ++j)
-            {
-                const bool prior = diffs[i][j] != 0.0;
-                const bool extra = use_c && i == n - 2 && diffs[n-1][j] != 0.0;
-                if (!prior && !extra) continue;
-                if (st.nin == 2) { ok = false; break; }
-                st.in[st.nin] = j; st.cq[st.nin] = diffs[i][j]; st.co[st.nin] = 0.0; ++st.nin;
-            }
-            if (use_c && i == n - 2)
-            {
-                st.out = n - 2; st.co_self = diffs[n-1][i];
-                for (int a = 0; a < st.nin; ++a) st.co[a] = diffs[n-1][st.in[a]];
-            }
-            else
-            {
-                bool later = false;
-                for (int m = i + 1; m < n; ++m) later = later || diffs[m][i] != 0.0;
-                if (later) { st.out = i; st.co_self = 1.0; }
-            }
-        }
+        spb_stage_plan plan[n];
+        const bool ok = spb_flux_div_rk_stage_supported(&fd) && spb_rk_fused_plan(n, diffs, plan) == 0;
         if (!ok)
         {
             // outside the fused pattern: same two-kernel path as for an opaque rhs callback
@@ -658,35 +867,59 @@ namespace spade::time_integration
         double* bufs[2] = {b200::dev_ptr(q), b200::scratch_buffer(nd)};
         const double dt = double(axis.timestep());
         const int64_t nlb = (int64_t)q.get_grid().get_num_local_blocks();
+        constexpr bool known_bc = b200::is_exchange_bc<boundary_t>::value;
         spb_exchange* fuse = nullptr;
-        if constexpr (b200::is_exchange_bc<boundary_t>::value) fuse = boundary.handle->plan;       // same-rank ghosts; messages below
+        bool overlap = false;
+        if constexpr (known_bc)
+        {
+            fuse = boundary.handle->plan;                                 // same-rank ghosts in the kernel; messages below
+            overlap = boundary.group->size() > 1;
+            if (overlap) boundary.handle->block_runs(nlb);
+        }
         thread_local bool fuse_refused = false;
         int cur = 0;
         for (int i = 0; i < n; ++i)
         {
-            const stage_t& st = plan[i];
+            const spb_stage_plan& st = plan[i];
             spb_stage_desc sd{};
             sd.nin = st.nin;
             for (int a = 0; a < st.nin; ++a) { sd.in[a] = b200::dev_ptr(data.residual(st.in[a])); sd.cq[a] = st.cq[a]*dt; sd.co[a] = st.co[a]; }
             sd.cq_self = st.cq_self*dt; sd.co_self = st.co_self;
             sd.out = st.out >= 0 ? b200::dev_ptr(data.residual(st.out)) : nullptr;
             bool ghosts_done = false;
-            if (fuse && !fuse_refused)
+            const auto launch = [&](const int64_t b0, const int64_t b1, cudaStream_t stream)
             {
-                const int rc = spb_flux_div_rk_stage_exchange(gh, bufs[cur], bufs[1 - cur], &fd, &sd, fuse, 0, nlb, nullptr);
-                if (rc == SPB_ERR_UNSUPPORTED) fuse_refused = true;          // e.g. AMR interpolation: separate exchange from now on
-                else { b200::check(rc, "spb_flux_div_rk_stage_exchange"); ghosts_done = true; }
+                if (fuse && !fuse_refused)
+                {
+                    const int rc = spb_flux_div_rk_stage_exchange(gh, bufs[cur], bufs[1 - cur], &fd, &sd, fuse, b0, b1, stream);
+                    if (rc == SPB_ERR_UNSUPPORTED) fuse_refused = true;          // e.g. AMR interpolation: separate exchange from now on
+                    else { b200::check(rc, "spb_flux_div_rk_stage_exchange"); ghosts_done = true; return; }
+                }
+                b200::check(spb_flux_div_rk_stage(gh, bufs[cur], bufs[1 - cur], &fd, &sd, b0, b1, stream), "spb_flux_div_rk_stage");
+            };
+            if constexpr (known_bc)
+            {
+                if (overlap)
+                {
+                    auto& sp = b200::streams();
+                    auto& h = *boundary.handle;
+                    sp.fork();
+                    for (const auto& r: h.runs_first) launch(r.first, r.second, sp.side);
+                    h.begin(bufs[1 - cur], *boundary.group, sp.side);             // the messages of the boundary blocks leave
+                    for (const auto& r: h.runs_second) launch(r.first, r.second, nullptr);
+                    sp.join();
+                }
+                else launch(0, nlb, nullptr);
             }
-            if (!ghosts_done) b200::check(spb_flux_div_rk_stage(gh, bufs[cur], bufs[1 - cur], &fd, &sd, 0, nlb, nullptr), "spb_flux_div_rk_stage");
+            else launch(0, nlb, nullptr);
             cur = 1 - cur;
             axis.time() = t_start + tfrac[i]*dt;
-            if constexpr (b200::is_exchange_bc<boundary_t>::value)
+            if constexpr (known_bc)
             {
                 // the callback's work on the raw stage buffer (the result may sit in the scratch buffer): same-rank ghosts unless the
-                // kernel wrote them, the ghost cells fed by other ranks (other GPUs of this process: packed straight into the peers'
-                // buffers), then the wall fills of a channel solver
+                // kernel wrote them, the ghost cells fed by other ranks, then the wall fills of a channel solver
                 if (!ghosts_done) b200::check(spb_exchange_local(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local");
-                if (boundary.group->size() > 1) boundary.handle->exchange_messages(bufs[cur], *boundary.group);
+                if (overlap) boundary.handle->finish(bufs[cur], *boundary.group, nullptr);
                 boundary.fill(q, bufs[cur]);
             }
             else
@@ -703,5 +936,108 @@ namespace spade::time_integration
         if (cur == 1) cudaMemcpyAsync(bufs[0], bufs[1], sizeof(double)*nd, cudaMemcpyDeviceToDevice, nullptr);    // odd number of stages
         axis.time() = t_start + dt;
         b200::check(spb_sync(nullptr), "spb_sync");
+    }
+
+    // ssprk3_opt: the 2-register SSPRK3 of advance.h:359-402 (detail::opt_rk3_s0/s1/s2, advance.h:286-354) for device::gpu arrays;
+    // more specialised in `data` than the reference's overload, so partial ordering prefers it. Same operation order as the
+    // reference: stage 1 overwrites r0 with (dt/6)(r0 + r1).
+    template <typename axis_t, typename var_state_t, typename rhs_state_t, typename rhs_t, typename boundary_t, typename state_t, typename gas_t>
+    requires (b200::on_gpu<var_state_t>)
+    void integrate_advance(axis_t& axis, integrator_data_t<var_state_t, rhs_state_t, tspecial_rk3_t>& data, const tspecial_rk3_t&, const rhs_t& rhs,
+                           const boundary_t& boundary, const fluid_state::state_transform_t<gas_t, state_t>& trans)
+    {
+        b200::require_supported_array<var_state_t>();
+        static_assert(std::same_as<state_t, fluid_state::cons_t<double>>, "spade_b200: ssprk3_opt integrates conserved variables");
+        auto& q  = data.solution(0);
+        auto& r0 = data.residual(0);
+        auto& r1 = data.residual(1);
+        using numeric_type = typename axis_t::value_type;
+        const auto& dt = axis.timestep();
+        const numeric_type tc[3] = {numeric_type(0.0), numeric_type(1.0), numeric_type(0.5)};
+        spb_grid* gh = b200::grid_handle(q);
+        const double gamma = trans.gas.get_gamma(), R = trans.gas.get_R();
+        const auto stage = [&](const int s)
+        {
+            b200::check(spb_ssprk3_stage(gh, s, b200::dev_ptr(q), b200::dev_ptr(r0), b200::dev_ptr(r1), double(dt), gamma, R, nullptr), "spb_ssprk3_stage");
+            b200::check(spb_sync(nullptr), "spb_sync");
+        };
+        axis.time() += tc[0]*dt;
+        rhs(r0, q, axis.time());
+        axis.time() -= tc[0]*dt;
+        stage(0);
+        axis.time() += tc[1]*dt;
+        boundary(q, axis.time());
+        rhs(r1, q, axis.time());
+        axis.time() -= tc[1]*dt;
+        stage(1);
+        axis.time() += tc[2]*dt;
+        boundary(q, axis.time());
+        rhs(r1, q, axis.time());
+        axis.time() -= tc[2]*dt;
+        stage(2);
+        axis.time() += dt;
+        boundary(q, axis.time());
+    }
+
+    // Generic integrate_advance (advance.h:109-230) with time_integration::identity_transform on device::gpu arrays: the array
+    // itself is integrated. Every `resid *= c; sol (+|-)= resid; resid *= 1/c` triple of the reference (three passes, each
+    // followed by a device synchronisation) is ONE kernel (spb_axpy_roundtrip), bit-identical including the round trip of the
+    // residual. Tables with a second copy of the solution (rk2hs_t, ssprk3hs_t; explicit.h:33) skip the subtraction pass.
+    template <typename axis_t, typename var_state_t, typename rhs_state_t, typename scheme_t, typename rhs_t, typename boundary_t>
+    requires (scheme_t::is_rk_specialization && b200::on_gpu<var_state_t>)
+    void integrate_advance(axis_t& axis, integrator_data_t<var_state_t, rhs_state_t, scheme_t>& data, const scheme_t& scheme,
+                           const rhs_t& rhs, const boundary_t& boundary, const identity_transform_t&)
+    {
+        b200::require_supported_array<var_state_t>();
+        constexpr bool second = scheme_t::var_size() > 1;
+        constexpr int n = scheme_t::table_type::rows();
+        using numeric_type = typename axis_t::value_type;
+        const auto& dt = axis.timestep();
+        const auto axpy = [&](auto& sol, auto& resid, const numeric_type c, const int subtract)
+        {
+            b200::check(spb_axpy_roundtrip(b200::grid_handle(sol), b200::dev_ptr(sol), b200::dev_ptr(resid), double(c), subtract, nullptr), "spb_axpy_roundtrip");
+        };
+        algs::static_for<0, n>([&](const auto& ii)
+        {
+            constexpr int i = ii.value;
+            auto& sol = data.solution(second ? 1 : 0);
+            if constexpr (second)
+                cudaMemcpyAsync(b200::dev_ptr(sol), b200::dev_ptr(data.solution(0)), sizeof(double)*sol.data.size(), cudaMemcpyDeviceToDevice, nullptr);
+            const auto sweep = [&](const int subtract)
+            {
+                algs::static_for<0, i>([&](const auto& jj)
+                {
+                    constexpr int j = jj.value;
+                    using coeff_t = typename scheme_t::table_type::template elem_t<i>::template elem_t<j>;
+                    if constexpr (detail::nonzero_t<coeff_t>::value)
+                    {
+                        constexpr numeric_type coeff = detail::coeff_value_t<numeric_type, coeff_t>::value();
+                        axpy(sol, data.residual(j), dt*coeff, subtract);
+                    }
+                });
+            };
+            sweep(0);
+            b200::check(spb_sync(nullptr), "spb_sync");
+            constexpr numeric_type tcoef = detail::coeff_value_t<numeric_type, typename scheme_t::dt_type::template elem_t<i>>::value();
+            axis.time() += tcoef*dt;
+            if constexpr (i > 0) boundary(sol, axis.time());
+            rhs(data.residual(i), sol, axis.time());
+            axis.time() -= tcoef*dt;
+            if constexpr (!second) sweep(1);
+        });
+        auto& new_solution = data.solution(0);
+        algs::static_for<0, n>([&](const auto& ii)
+        {
+            constexpr int i = ii.value;
+            using coeff_t = typename scheme_t::accum_type::template elem_t<i>;
+            if constexpr (detail::nonzero_t<coeff_t>::value)
+            {
+                constexpr numeric_type coeff = detail::coeff_value_t<numeric_type, coeff_t>::value();
+                axpy(new_solution, data.residual(i), coeff*dt, 0);
+            }
+        });
+        b200::check(spb_sync(nullptr), "spb_sync");
+        axis.time() += dt;
+        boundary(new_solution, axis.time());
     }
 }

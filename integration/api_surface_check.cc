@@ -37,6 +37,52 @@ static void compile_only(spade::parallel::pool_t& pool)
     spade::b200::source_term(q, r, spade::b200::body_force{{1.0, 0.0, 0.0}});
     spade::fluid_state::ideal_gas_t<real_t> air(1.4, 287.15);
     (void)spade::b200::transform_reduce(q, spade::b200::wavespeed<decltype(air)>{air}, spade::algs::max);
+    (void)spade::b200::transform_reduce(q, spade::b200::kinetic_energy<decltype(air)>{air}, spade::algs::sum);
+    (void)spade::b200::transform_reduce(q, spade::b200::variable{0}, spade::algs::sum);
+    (void)spade::b200::transform_reduce(q, spade::b200::abs_variable{2}, spade::algs::max);
+    spade::b200::binary_write("/tmp/spade_b200_check.bin", q);
+    spade::b200::binary_read("/tmp/spade_b200_check.bin", q);
+    spade::b200::invalidate(grid);
+    {
+        // every integrate_advance overload of the shim: ssprk3_opt (advance.h:359-402), the generic path with
+        // identity_transform (advance.h:109-230) incl. a high-storage table, the fused prim/cons path with opaque callbacks
+        // and with the named callbacks (one kernel per stage, overlapped schedule)
+        using cons_t = spade::fluid_state::cons_t<real_t>;
+        cons_t cstate;
+        spade::fluid_state::state_transform_t trans(cstate, air);
+        spade::viscous_laws::constant_viscosity_t<real_t> vl(1.8e-5, 0.72);
+        const auto fl = spade::omni::compose(spade::convective::totani_lr(air), spade::viscous::visc_lr(vl, air));
+        const auto rhs_l = [&](auto& rr, const auto& qq, const auto&) { spade::pde_algs::flux_div(qq, rr, fl, spade::algs::make_traits(spade::pde_algs::b200, spade::pde_algs::overwrite)); };
+        const auto bc_l  = [&](auto& qq, const auto&) { handle.exchange(qq, pool); };
+        spade::time_integration::time_axis_t axis(real_t(0.0), real_t(1e-6));
+        {
+            spade::time_integration::integrator_data_t qd(q, r, spade::time_integration::ssprk3_opt);
+            spade::time_integration::integrator_t ti(axis, spade::time_integration::ssprk3_opt, qd, rhs_l, bc_l, trans);
+            ti.advance();
+        }
+        {
+            spade::time_integration::rk4_t alg;
+            spade::time_integration::integrator_data_t qd(q, r, alg);
+            spade::time_integration::integrator_t ti(axis, alg, qd, rhs_l, bc_l);
+            ti.advance();
+        }
+        {
+            spade::time_integration::ssprk3hs_t alg;
+            spade::time_integration::integrator_data_t qd(q, r, alg);
+            spade::time_integration::integrator_t ti(axis, alg, qd, rhs_l, bc_l);
+            ti.advance();
+        }
+        {
+            spade::time_integration::ssprk34_t alg;
+            spade::time_integration::integrator_data_t qd(q, r, alg);
+            spade::time_integration::integrator_t t1(axis, alg, qd, rhs_l, bc_l, trans);
+            t1.advance();
+            const auto rhs_n = spade::b200::flux_div_rhs(fl);
+            const auto bc_n  = spade::b200::exchange_bc(handle, pool);
+            spade::time_integration::integrator_t t2(axis, alg, qd, rhs_n, bc_n, trans);
+            t2.advance();
+        }
+    }
     spade::pde_algs::flux_div(q, r, spade::convective::cent_keep<6>(air), spade::algs::make_traits(spade::pde_algs::b200, spade::pde_algs::increment));
 }
 

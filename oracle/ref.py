@@ -34,17 +34,32 @@ def make_bc(mask, kind=0, order=0, a=(1, 1, 1, 1, 1), b=(0, 0, 0, 0, 0), a_norma
     return bc
 
 
+LIB_PATH_O3 = os.path.join(_HERE, "_ref", "libspade_ref_o3.so")
+BUILD_FLAGS = {LIB_PATH: "g++ -std=c++20 -O2 -ffp-contract=off", LIB_PATH_O3: "g++ -std=c++20 -O3"}
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
 
 _lib = None
+_lib_path = LIB_PATH
+
+
+def use_timing_build():
+    """bench.py's CPU legs time the -O3 build of the same driver (oracle/Makefile) when it exists; returns the flags of
+    the library that will be loaded. Must be called before the first lib() of the process."""
+    global _lib_path
+    assert _lib is None, "use_timing_build() after the library was loaded"
+    if os.path.exists(LIB_PATH_O3):
+        _lib_path = LIB_PATH_O3
+    return BUILD_FLAGS[_lib_path]
 
 
 def lib():
     global _lib
     if _lib is None:
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(_lib_path)
         _lib.ref_last_error.restype = C.c_char_p
         _lib.ref_array_size.restype = C.c_int64
     return _lib

@@ -76,6 +76,7 @@ SYMBOLS = {
                                                  C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "spb_rk_update": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, _dp, C.c_double,
                                 C.c_double, C.c_void_p]),
+    "spb_flux_div_rk_stage_supported": (C.c_int, [C.c_void_p]),
     "spb_rk_fused_plan": (C.c_int, [C.c_int, _dp, C.POINTER(StagePlan)]),
     "spb_axpy_roundtrip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]),
     "spb_ssprk3_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

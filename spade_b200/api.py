@@ -1028,12 +1028,7 @@ class integrator_t:
         self._side = None
         self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
         if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
-            f = rhs_calc.flux
-            narrow = f.diss == DISS_NONE and f.conv in (CONV_NONE, CONV_TOTANI) and (f.conv != CONV_NONE or f.visc)
-            wide = bool(f.visc) and ((f.conv == CONV_TOTANI and f.diss == DISS_FWENO) or f.conv in (CONV_CENT_KEEP4, CONV_CENT_KEEP6, CONV_CENT_KEEP8))
-            if f.sgs:                      # the WALE closure rides on the wide kernel for every functor set it supports
-                narrow, wide = False, bool(f.visc) and f.conv in (CONV_NONE, CONV_TOTANI, CONV_CENT_KEEP4)
-            if narrow or wide:
+            if lib().spb_flux_div_rk_stage_supported(C.byref(rhs_calc.flux)):
                 self._plan = self._fused_plan(scheme)
 
     def solution(self):

@@ -61,6 +61,21 @@ extern "C"
         return SPB_ERR_UNSUPPORTED;
     }
 
+    // the functor sets the fused stage exists for (one place: both host sides ask here instead of keeping their own list)
+    int spb_flux_div_rk_stage_supported(const spb_flux_desc* f)
+    {
+        if (!f) return 0;
+        const bool hybrid_or_plain = f->diss == SPB_DISS_NONE || f->diss == SPB_DISS_FWENO;
+        if (f->sgs == SPB_SGS_WALE)
+            return f->visc && hybrid_or_plain && ((f->conv == SPB_CONV_NONE && f->diss == SPB_DISS_NONE) || f->conv == SPB_CONV_TOTANI || f->conv == SPB_CONV_CENT_KEEP4);
+        if (f->sgs != SPB_SGS_NONE) return 0;
+        const bool narrow = f->diss == SPB_DISS_NONE && (f->conv == SPB_CONV_TOTANI || (f->conv == SPB_CONV_NONE && f->visc));
+        const bool wide = f->visc && ((f->conv == SPB_CONV_TOTANI && f->diss == SPB_DISS_FWENO)
+                                      || (f->conv == SPB_CONV_CENT_KEEP4 && hybrid_or_plain)
+                                      || ((f->conv == SPB_CONV_CENT_KEEP6 || f->conv == SPB_CONV_CENT_KEEP8) && f->diss == SPB_DISS_NONE));
+        return (narrow || wide) ? 1 : 0;
+    }
+
     int spb_flux_div_rk_stage(const spb_grid* g, const double* q_in, double* q_out, const spb_flux_desc* f,
                               const spb_stage_desc* sd, int64_t lb_begin, int64_t lb_end, void* stream)
     {

@@ -14,6 +14,46 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from util import GAMMA, RGAS, make_state, oracle_cfg, product_flux, rel_l2, zero_ghosts  # noqa: E402
 
 
+def amr_case(sp, port, pool, rank, world):
+    """AMR grid partitioned over the ranks (BASELINE config 5; tables of the unmodified reference for this rank count,
+    tests/golden/config5_amr.npz): exchange bit-exact, and an RK4 trajectory through the overlapped schedule — the donor
+    blocks of off-rank interpolation sends must be advanced BEFORE their messages are packed (spb_exchange_boundary_blocks)."""
+    fix = np.load(os.path.join(ROOT, "tests", "golden", "config5_amr.npz"))
+    if f"p_send_{world}_0" not in fix:
+        return
+    from util import amr_state
+    boxes, n, ng = fix["p_boxes"], tuple(int(x) for x in fix["p_cells"]), 2
+    per, extra = divmod(len(boxes), world)
+    lo, nloc = rank * per + min(rank, extra), per + (1 if rank < extra else 0)
+    tabs = tuple(fix[f"p_{k}_{world}_{rank}"].astype(np.int64) for k in ("send", "recv", "isend", "irecv"))
+    cfg = oracle_cfg(tuple(int(x) for x in fix["p_roots"]), n, ng, scheme=0, integrator=0)
+    q0 = amr_state(boxes, n, ng, seed=61)
+    port.set_amr(boxes, np.concatenate([fix[f"p_send_{world}_{r}"] for r in range(world)]).astype(np.int64),
+                 np.concatenate([fix[f"p_isend_{world}_{r}"] for r in range(world)]).astype(np.int64))
+    try:
+        qz = zero_ghosts(q0, ng)
+        want = port.exchange(cfg, qz.ravel()).reshape(q0.shape)
+        grid = sp.cartesian_grid_t.from_boxes(n, boxes[lo:lo + nloc], pool, first_block=lo)
+        qa = sp.grid_array.from_host(grid, qz[lo:lo + nloc])
+        ex = sp.make_exchange(qa, (1, 1, 1), tables=tabs)
+        ex.exchange(qa)
+        assert np.array_equal(qa.to_host(), want[lo:lo + nloc]), f"rank {rank}: AMR exchange differs from the oracle"
+        qe = port.exchange(cfg, q0.ravel()).reshape(q0.shape)
+        dt = 0.2 * float((boxes[:, 1] - boxes[:, 0]).min()) / n[0] / port.reduce_umax(cfg, qe.ravel())
+        want = port.advance(cfg, qe.ravel(), dt, 2).reshape(q0.shape)
+        gas = sp.ideal_gas_t(GAMMA, RGAS)
+        qa = sp.grid_array.from_host(grid, qe[lo:lo + nloc])
+        ex = sp.make_exchange(qa, (1, 1, 1), tables=tabs)
+        ti = sp.integrator_t(sp.time_axis_t(0.0, dt), sp.rk4_t, sp.integrator_data_t(qa, sp.grid_array(grid, 0.0), sp.rk4_t),
+                             sp.flux_div_rhs_t(sp.flux_desc(product_flux(0)), sp.overwrite), sp.exchange_bc_t(ex), sp.state_transform_t(gas))
+        for _ in range(2):
+            ti.advance()
+        err = rel_l2(ti.solution().to_host(), want[lo:lo + nloc])
+        assert err < 1e-12 and ti._plan is not None, f"rank {rank} AMR fused + overlap: rel L2 {err}"
+    finally:
+        port.set_amr()
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -79,6 +119,7 @@ def main():
         local_now = rel_l2(qa.to_host(), want[lo:lo + nloc])
         assert umax == umax_want or abs(umax / umax_want - 1) < 1e-12, \
             f"rank {rank} lattice {nb}: umax {umax!r} vs oracle {umax_want!r}; rel L2 of the reduced array now {local_now:.3e}"
+    amr_case(sp, port, pool, rank, world)
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok p2p={int(bool(ex._p2p))}")
