@@ -157,8 +157,9 @@ int spb_flux_div_rk_stage(const spb_grid* g, const double* q_in_dev, double* q_o
  * to a separate exchange of q_out. With lb_begin/lb_end the ghost cells fed by blocks outside the range are not
  * written. The one-ghost-cell functor set sends the ghosts from a dedicated warp (TMA stores of the staged plane; 2 exchange
  * cells along i), every other functor set stores them from the threads that own the cells (any number of exchange cells).
- * SPB_ERR_UNSUPPORTED if the plan holds same-rank transactions other than the 26 canonical injection boxes (AMR
- * interpolation); the caller then uses spb_flux_div_rk_stage + spb_exchange_local. exch == NULL is spb_flux_div_rk_stage. */
+ * SPB_ERR_UNSUPPORTED if the plan holds same-rank INJECTION transactions other than the 26 canonical boxes; the caller then
+ * uses spb_flux_div_rk_stage + spb_exchange_local. Interpolation transactions (AMR) are never done by the kernel: after
+ * a fused call the caller runs spb_exchange_local_interp. exch == NULL is spb_flux_div_rk_stage. */
 typedef struct spb_exchange spb_exchange;
 int spb_flux_div_rk_stage_exchange(const spb_grid* g, const double* q_in_dev, double* q_out_dev, const spb_flux_desc* flux,
                                    const spb_stage_desc* stage, spb_exchange* exch, int64_t lb_begin, int64_t lb_end,
@@ -184,6 +185,16 @@ typedef struct spb_stage_plan
     int    out;            /* register written, -1 = none */
 } spb_stage_plan;
 int spb_rk_fused_plan(int n, const double* diffs, spb_stage_plan* plan);
+
+/* The fused stage on ONE PART of the local blocks in ONE launch, whatever their order in memory: part SPB_PART_BOUNDARY = the
+ * blocks spb_exchange_boundary_blocks marks (sources of off-rank sends), SPB_PART_INTERIOR = the rest, SPB_PART_ALL = every
+ * block. The overlapped schedule runs BOUNDARY on a side stream, sends the messages behind it and runs INTERIOR at the
+ * same time on the main stream. On AMR grids the rank-boundary blocks are scattered in local order, so contiguous ranges
+ * (lb_begin, lb_end) would mean one launch per run. fuse_ghosts != 0 also stores the same-rank injection ghosts from the
+ * kernel (SPB_ERR_UNSUPPORTED if the plan cannot be fused: retry with fuse_ghosts = 0 and spb_exchange_local). */
+enum { SPB_PART_ALL = 0, SPB_PART_BOUNDARY = 1, SPB_PART_INTERIOR = 2 };
+int spb_flux_div_rk_stage_part(const spb_grid* g, const double* q_in_dev, double* q_out_dev, const spb_flux_desc* flux,
+                               const spb_stage_desc* stage, spb_exchange* exch, int fuse_ghosts, int part, void* stream);
 
 /* ---- RK stage update: replaces detail::transform_advance_to -----------------------------------
  * reference src/time-integration/advance.h:57-102: per interior cell
@@ -253,6 +264,10 @@ int64_t spb_exchange_recv_cells(const spb_exchange* e, int peer);
 int spb_exchange_boundary_blocks(const spb_exchange* e, int64_t nlb, unsigned char* mask);
 /* same-rank transactions: q(dst) = q(src) on the device (make_exchange.h:166-203). */
 int spb_exchange_local(spb_exchange* e, double* q_dev, void* stream);
+/* only the same-rank INTERPOLATION transactions (AMR): what remains after spb_flux_div_rk_stage_exchange has stored the
+ * same-level (injection) ghosts from inside the stage kernel. Every source cell of a transaction is an interior cell, so
+ * the split gives the same ghost values as spb_exchange_local. No-op on plans without interpolation lists. */
+int spb_exchange_local_interp(spb_exchange* e, double* q_dev, void* stream);
 /* pack q into the contiguous message for `peer` (make_exchange.h:136-164) / unpack (340-369). */
 int spb_exchange_pack(spb_exchange* e, const double* q_dev, int peer, double* sendbuf_dev, void* stream);
 int spb_exchange_unpack(spb_exchange* e, double* q_dev, int peer, const double* recvbuf_dev, void* stream);

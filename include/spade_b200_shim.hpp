@@ -874,7 +874,6 @@ namespace spade::time_integration
         {
             fuse = boundary.handle->plan;                                 // same-rank ghosts in the kernel; messages below
             overlap = boundary.group->size() > 1;
-            if (overlap) boundary.handle->block_runs(nlb);
         }
         thread_local bool fuse_refused = false;
         int cur = 0;
@@ -887,15 +886,16 @@ namespace spade::time_integration
             sd.cq_self = st.cq_self*dt; sd.co_self = st.co_self;
             sd.out = st.out >= 0 ? b200::dev_ptr(data.residual(st.out)) : nullptr;
             bool ghosts_done = false;
-            const auto launch = [&](const int64_t b0, const int64_t b1, cudaStream_t stream)
+            // one launch per part of the local blocks (boundary / interior / all), whatever their order in memory
+            const auto launch = [&](const int part, cudaStream_t stream)
             {
                 if (fuse && !fuse_refused)
                 {
-                    const int rc = spb_flux_div_rk_stage_exchange(gh, bufs[cur], bufs[1 - cur], &fd, &sd, fuse, b0, b1, stream);
-                    if (rc == SPB_ERR_UNSUPPORTED) fuse_refused = true;          // e.g. AMR interpolation: separate exchange from now on
-                    else { b200::check(rc, "spb_flux_div_rk_stage_exchange"); ghosts_done = true; return; }
+                    const int rc = spb_flux_div_rk_stage_part(gh, bufs[cur], bufs[1 - cur], &fd, &sd, fuse, 1, part, stream);
+                    if (rc == SPB_ERR_UNSUPPORTED) fuse_refused = true;          // same-rank injections not canonical: separate exchange from now on
+                    else { b200::check(rc, "spb_flux_div_rk_stage_part"); ghosts_done = true; return; }
                 }
-                b200::check(spb_flux_div_rk_stage(gh, bufs[cur], bufs[1 - cur], &fd, &sd, b0, b1, stream), "spb_flux_div_rk_stage");
+                b200::check(spb_flux_div_rk_stage_part(gh, bufs[cur], bufs[1 - cur], &fd, &sd, fuse, 0, part, stream), "spb_flux_div_rk_stage_part");
             };
             if constexpr (known_bc)
             {
@@ -904,14 +904,14 @@ namespace spade::time_integration
                     auto& sp = b200::streams();
                     auto& h = *boundary.handle;
                     sp.fork();
-                    for (const auto& r: h.runs_first) launch(r.first, r.second, sp.side);
+                    launch(SPB_PART_BOUNDARY, sp.side);
                     h.begin(bufs[1 - cur], *boundary.group, sp.side);             // the messages of the boundary blocks leave
-                    for (const auto& r: h.runs_second) launch(r.first, r.second, nullptr);
+                    launch(SPB_PART_INTERIOR, nullptr);
                     sp.join();
                 }
-                else launch(0, nlb, nullptr);
+                else launch(SPB_PART_ALL, nullptr);
             }
-            else launch(0, nlb, nullptr);
+            else launch(SPB_PART_ALL, nullptr);
             cur = 1 - cur;
             axis.time() = t_start + tfrac[i]*dt;
             if constexpr (known_bc)
@@ -919,6 +919,7 @@ namespace spade::time_integration
                 // the callback's work on the raw stage buffer (the result may sit in the scratch buffer): same-rank ghosts unless the
                 // kernel wrote them, the ghost cells fed by other ranks, then the wall fills of a channel solver
                 if (!ghosts_done) b200::check(spb_exchange_local(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local");
+                else b200::check(spb_exchange_local_interp(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local_interp");   // AMR: what the kernel left
                 if (overlap) boundary.handle->finish(bufs[cur], *boundary.group, nullptr);
                 boundary.fill(q, bufs[cur]);
             }

@@ -123,6 +123,12 @@ def advance(cfg, q, dt, nsteps):
     return out, sec.value
 
 
+def output_vtk(cfg, q, out_dir, basename):
+    """the reference's io::output_vtk of the array holding q (io/io_vtk.h:276-288)"""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    _check(lib().ref_output_vtk(C.byref(cfg), _ptr(q), str(out_dir).encode(), str(basename).encode()))
+
+
 def advance_generic(cfg, q, dt, nsteps, high_storage=False):
     out = np.array(q, dtype=np.float64, copy=True)
     _check(lib().ref_advance_generic(C.byref(cfg), _ptr(out), C.c_double(dt), int(nsteps), int(bool(high_storage))))

@@ -407,6 +407,20 @@ extern "C"
         });
     }
 
+    // io::output_vtk(out_dir, basename, prim) (io/io_vtk.h:276-288) and io::binary_write (io/io_native.h:40-47) of the array
+    // holding q: the reference's own files, for the byte-for-byte check of the drop-in's writers (tests/test_io.py)
+    int ref_output_vtk(const ref_cfg* c, const double* q, const char* out_dir, const char* basename)
+    {
+        return guarded([&]
+        {
+            with_setup(*c, [&](auto& pool, auto& grid, auto& prim, auto& rhs, auto& handle, std::size_t off, std::size_t cnt)
+            {
+                std::copy(q + off, q + off + cnt, prim.data.begin());
+                spade::io::output_vtk(std::string(out_dir), std::string(basename), prim);
+            });
+        });
+    }
+
     // nsteps of integrator_t::advance() with bc = exchange, rhs = flux_div(basic, overwrite).
     // q must enter with ghosts filled. If seconds != nullptr it receives the wall time of the
     // advance() loop (max over ranks, barriers on both sides).
@@ -458,6 +472,8 @@ extern "C"
                         case 1: { run(spade::time_integration::ssprk3_opt); break; }
                         case 2: { run(spade::time_integration::ssprk3_t()); break; }
                         case 3: { run(spade::time_integration::rk2_t());   break; }
+                        case 4: { run(spade::time_integration::ssprk34_t()); break; }
+                        case 5: { run(spade::time_integration::rk38r_t());   break; }
                         default: throw std::runtime_error("ref_driver: unknown integrator id");
                     }
                 });

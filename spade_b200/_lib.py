@@ -32,6 +32,7 @@ class StagePlan(C.Structure):
 
 
 SPB_ERR_BAD_ARG, SPB_ERR_UNSUPPORTED, SPB_ERR_NO_DEVICE, SPB_ERR_DRIVER = 10001, 10002, 10003, 10004
+SPB_PART_ALL, SPB_PART_BOUNDARY, SPB_PART_INTERIOR = 0, 1, 2
 
 
 class BcDesc(C.Structure):
@@ -77,6 +78,7 @@ SYMBOLS = {
     "spb_rk_update": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, _dp, C.c_double,
                                 C.c_double, C.c_void_p]),
     "spb_flux_div_rk_stage_supported": (C.c_int, [C.c_void_p]),
+    "spb_flux_div_rk_stage_part": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "spb_rk_fused_plan": (C.c_int, [C.c_int, _dp, C.POINTER(StagePlan)]),
     "spb_axpy_roundtrip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p]),
     "spb_ssprk3_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
@@ -92,6 +94,7 @@ SYMBOLS = {
     "spb_exchange_destroy": (None, [C.c_void_p]),
     "spb_exchange_num_send": (C.c_int64, [C.c_void_p]),
     "spb_exchange_num_recv": (C.c_int64, [C.c_void_p]),
+    "spb_exchange_local_interp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "spb_exchange_boundary_blocks": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_ubyte)]),
     "spb_exchange_tables": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p]),
     "spb_exchange_local_blocks": (C.c_int64, [C.c_void_p]),

@@ -612,6 +612,14 @@ class arr_exchange_t:
         check(lib().spb_exchange_tables(self._h, send.ctypes.data_as(i64), recv.ctypes.data_as(i64), offs.ctypes.data_as(i64)))
         return send, recv, offs
 
+    def local_injection_cells(self):
+        """cells of the same-rank injection transactions (the ghost cells the fused stage kernel writes itself)"""
+        if getattr(self, "_linj", None) is None:
+            send, _, _ = self.tables()
+            mine = send[send[:, 2] == self.pool.rank()]
+            self._linj = int((mine[:, 9] * mine[:, 10] * mine[:, 11]).sum())
+        return self._linj
+
     def _buffers(self):
         me = self.pool.rank()
         for p in range(self.pool.size()):
@@ -738,6 +746,8 @@ class arr_exchange_t:
         st = _stream_ptr()
         if local:
             check(lib().spb_exchange_local(self._h, _dptr(array.data), st))
+        else:
+            check(lib().spb_exchange_local_interp(self._h, _dptr(array.data), st))    # AMR: what the stage kernel left (no-op otherwise)
         if self.pool.size() > 1 and self._p2p:
             par = self._seq & 1
             for p, (bufs, flags) in self._own.items():
@@ -1076,18 +1086,17 @@ class integrator_t:
             sd.co_self = st["co_self"]
             ex = self.boundary_cond.handle if isinstance(self.boundary_cond, exchange_bc_t) else None
             overlap = ex is not None and ex.pool.size() > 1
-            runs_first, runs_second = ex.boundary_block_runs() if overlap else ([(0, cur.grid.num_local_blocks)], [])
 
-            def launch(b0, b1):
-                # with a recognised exchange handle the kernel also fills the same-rank ghost cells of q_out
+            def launch(part):
+                # one launch per part of the local blocks (spb_flux_div_rk_stage_part: boundary / interior / all), whatever their
+                # order in memory; with a recognised exchange handle the kernel also fills the same-rank injection ghosts of q_out
+                exh = ex._h if ex is not None else None
                 if ex is not None and self._fuse_exchange:
-                    rc = lib().spb_flux_div_rk_stage_exchange(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd),
-                                                              ex._h, b0, b1, _stream_ptr())
+                    rc = lib().spb_flux_div_rk_stage_part(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd), exh, 1, part, _stream_ptr())
                     if rc != _lib.SPB_ERR_UNSUPPORTED:
                         return check(rc)
                     self._fuse_exchange = False                  # plan not canonical: separate same-rank copy from now on
-                check(lib().spb_flux_div_rk_stage(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd),
-                                                  b0, b1, _stream_ptr()))
+                check(lib().spb_flux_div_rk_stage_part(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd), exh, 0, part, _stream_ptr()))
 
             if self.stage_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1095,32 +1104,29 @@ class integrator_t:
             if overlap and self._two_streams:
                 # rank-boundary blocks on a high-priority side stream, their messages packed and posted from it; the rank-interior
                 # blocks run on the main stream AT THE SAME TIME (both read q_in only and write disjoint cells), so the small
-                # boundary launches leave no partial waves behind and the messages fly under the interior kernel
+                # boundary launch leaves no partial wave behind and the messages fly under the interior kernel
                 if self._side is None:
                     self._side = torch.cuda.Stream(priority=-1)
                 main, side = torch.cuda.current_stream(), self._side
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    for b0, b1 in runs_first:
-                        launch(b0, b1)
+                    launch(_lib.SPB_PART_BOUNDARY)
                     ex.begin(nxt)
-                for b0, b1 in runs_second:
-                    launch(b0, b1)
+                launch(_lib.SPB_PART_INTERIOR)
                 main.wait_stream(side)
+            elif overlap:
+                launch(_lib.SPB_PART_BOUNDARY)
+                ex.begin(nxt)
+                launch(_lib.SPB_PART_INTERIOR)
             else:
-                for b0, b1 in runs_first:
-                    launch(b0, b1)
-                if overlap:
-                    ex.begin(nxt)
-                    for b0, b1 in runs_second:
-                        launch(b0, b1)
+                launch(_lib.SPB_PART_ALL)
             if self.stage_events is not None:
                 e1.record()
                 # algorithmic bytes per interior cell of this launch: q in, q out, residual registers read / written, and one
-                # 40-byte write per same-rank ghost cell when the ghost exchange is fused into the kernel
+                # 40-byte write per same-rank injection ghost cell when the ghost exchange is fused into the kernel
                 ghost = 0.0
                 if ex is not None and self._fuse_exchange:
-                    ghost = 40.0 * ex.send_cells[ex.pool.rank()] / max(1, cur.grid.local_cells())
+                    ghost = 40.0 * ex.local_injection_cells() / max(1, cur.grid.local_cells())
                 self.stage_events.append((e0, e1, 80.0 + 40.0 * sd.nin + (40.0 if st["out"] else 0.0) + ghost))
             cur, nxt = nxt, cur
             tnext = ax.t + (float(s.dt[i + 1]) * dt if i + 1 < s.rows() else dt)

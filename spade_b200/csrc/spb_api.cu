@@ -6,6 +6,8 @@
 
 namespace spb
 {
+    BlockList& current_block_list() { thread_local BlockList b; return b; }
+
     static thread_local std::string t_error;
     std::atomic<int64_t> g_launches{0};
     void set_error(const std::string& msg) { t_error = msg; }

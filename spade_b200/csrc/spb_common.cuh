@@ -35,6 +35,14 @@ namespace spb
     // (ex,ey,ez) through a same-rank transaction, -1 if there is none (off-rank, domain boundary, e = 13).
     // SPB_ERR_UNSUPPORTED if a same-rank transaction is not one of the 26 canonical injection boxes.
     int exchange_fuse_table(spb_exchange* e, const int nx[3], const int ng[3], int64_t nlb, const int** d_nbr);
+    // Device list of the local blocks of one part of the overlapped schedule (spb_exchange.cu): part 1 = the source blocks of
+    // off-rank sends (injection and interpolation), part 2 = the rest. Built once per plan.
+    int exchange_block_list(spb_exchange* e, int64_t nlb, int part, const int** d_list, int64_t* count);
+    // Block list the RHS launchers use instead of the contiguous range [lb_begin, lb_end) when set (one launch for a scattered
+    // set of blocks: AMR grids, whose rank-boundary blocks are not contiguous in local order). Set and cleared by the C entry
+    // point around the launch; thread-local like the rest of the per-thread (= per-GPU) state.
+    struct BlockList { const int* dev = nullptr; int64_t count = 0; };
+    BlockList& current_block_list();
 }
 
 #define SPB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return spb::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)

@@ -55,6 +55,13 @@ struct spb_exchange
     int fuse_state = 0;
     int* d_nbr = nullptr;
     int64_t nbr_blocks = 0;
+    // same-rank interpolation work items only (what is left to do after the stage kernel stored the injection ghosts)
+    std::vector<spb::WorkItem> items_local_itp;
+    spb::WorkItem* d_items_local_itp = nullptr;
+    // device block lists of the overlapped schedule: [0] rank-boundary blocks, [1] the rest
+    int* d_blist[2] = {nullptr, nullptr};
+    int64_t blist_count[2] = {0, 0};
+    int64_t blist_nlb = -1;
 };
 
 namespace spb
@@ -112,6 +119,7 @@ namespace spb
         if (e->d_recv) cudaFree(e->d_recv);
         for (auto p: e->d_items_send) if (p) cudaFree(p);
         for (auto p: e->d_items_recv) if (p) cudaFree(p);
+        if (e->d_items_local_itp) { cudaFree(e->d_items_local_itp); e->d_items_local_itp = nullptr; }
         e->d_send = nullptr; e->d_recv = nullptr; e->d_items_send.clear(); e->d_items_recv.clear();
     }
 
@@ -164,6 +172,14 @@ namespace spb
         };
         int rc = build(e->send, e->isend, true, e->inj_send_cells, &e->d_send, e->items_send, e->d_items_send);
         if (rc) return rc;
+        // the same-rank interpolation items alone: device transaction ids continue after the injection list
+        e->items_local_itp.clear();
+        for (const auto& it: e->items_send[e->rank]) if (it.trans >= (int)e->send.size()) e->items_local_itp.push_back(it);
+        if (!e->items_local_itp.empty())
+        {
+            SPB_CUDA(cudaMalloc((void**)&e->d_items_local_itp, sizeof(WorkItem)*e->items_local_itp.size()));
+            SPB_CUDA(cudaMemcpy(e->d_items_local_itp, e->items_local_itp.data(), sizeof(WorkItem)*e->items_local_itp.size(), cudaMemcpyHostToDevice));
+        }
         rc = build(e->recv, e->irecv, false, e->inj_recv_cells, &e->d_recv, e->items_recv, e->d_items_recv);
         if (rc) return rc;
         e->dev_ready = true;
@@ -175,7 +191,6 @@ namespace spb
         if (!e || !d_nbr) { set_error("exchange_fuse_table: null argument"); return SPB_ERR_BAD_ARG; }
         for (int d = 0; d < 3; ++d)
             if (e->nx[d] != nx[d] || e->ng[d] != ng[d]) { set_error("fused exchange: the plan was made for another block shape"); return SPB_ERR_BAD_ARG; }
-        if (!e->isend.empty() || !e->irecv.empty()) e->fuse_state = -1;          // AMR interpolation: separate exchange kernels
         if (e->fuse_state == 0 || (e->fuse_state == 1 && e->nbr_blocks != nlb))
         {
             if (e->d_nbr) { cudaFree(e->d_nbr); e->d_nbr = nullptr; }
@@ -214,6 +229,30 @@ namespace spb
             return SPB_ERR_UNSUPPORTED;
         }
         *d_nbr = e->d_nbr;
+        return 0;
+    }
+
+    int exchange_block_list(spb_exchange* e, int64_t nlb, int part, const int** d_list, int64_t* count)
+    {
+        if (!e || !d_list || !count || (part != 1 && part != 2) || nlb < 0) { set_error("exchange_block_list: bad argument"); return SPB_ERR_BAD_ARG; }
+        if (e->blist_nlb != nlb)
+        {
+            std::vector<unsigned char> mask((size_t)std::max<int64_t>(nlb, 1), 0);
+            int rc = spb_exchange_boundary_blocks(e, nlb, mask.data()); if (rc) return rc;
+            std::vector<int> lists[2];
+            for (int64_t b = 0; b < nlb; ++b) lists[mask[b] ? 0 : 1].push_back((int)b);
+            for (int k = 0; k < 2; ++k)
+            {
+                if (e->d_blist[k]) { cudaFree(e->d_blist[k]); e->d_blist[k] = nullptr; }
+                e->blist_count[k] = (int64_t)lists[k].size();
+                if (lists[k].empty()) continue;
+                SPB_CUDA(cudaMalloc((void**)&e->d_blist[k], sizeof(int)*lists[k].size()));
+                SPB_CUDA(cudaMemcpy(e->d_blist[k], lists[k].data(), sizeof(int)*lists[k].size(), cudaMemcpyHostToDevice));
+            }
+            e->blist_nlb = nlb;
+        }
+        *d_list = e->d_blist[part - 1];
+        *count = e->blist_count[part - 1];
         return 0;
     }
 
@@ -401,6 +440,7 @@ extern "C"
         if (!e) return;
         spb::free_device(e);
         if (e->d_nbr) cudaFree(e->d_nbr);
+        for (int k = 0; k < 2; ++k) if (e->d_blist[k]) cudaFree(e->d_blist[k]);
         delete e;
     }
 
@@ -447,6 +487,17 @@ extern "C"
         const auto& items = e->items_send[e->rank];
         if (items.empty()) return 0;
         exchange_kernel<0><<<(unsigned)items.size(), 256, 0, (cudaStream_t)stream>>>(q_dev, q_dev, nullptr, nullptr, e->d_send, e->d_items_send[e->rank], e->np[0], e->np[1]);
+        SPB_LAUNCH_CHECK();
+        return 0;
+    }
+
+    int spb_exchange_local_interp(spb_exchange* e, double* q_dev, void* stream)
+    {
+        using namespace spb;
+        if (!e || !q_dev) { set_error("spb_exchange_local_interp: bad argument"); return SPB_ERR_BAD_ARG; }
+        int rc = build_device(e); if (rc) return rc;
+        if (e->items_local_itp.empty()) return 0;
+        exchange_kernel<0><<<(unsigned)e->items_local_itp.size(), 256, 0, (cudaStream_t)stream>>>(q_dev, q_dev, nullptr, nullptr, e->d_send, e->d_items_local_itp, e->np[0], e->np[1]);
         SPB_LAUNCH_CHECK();
         return 0;
     }

@@ -131,6 +131,23 @@ extern "C"
         return SPB_ERR_UNSUPPORTED;
     }
 
+    int spb_flux_div_rk_stage_part(const spb_grid* g, const double* q_in, double* q_out, const spb_flux_desc* f,
+                                   const spb_stage_desc* sd, spb_exchange* exch, int fuse_ghosts, int part, void* stream)
+    {
+        using namespace spb;
+        if (!g) { set_error("spb_flux_div_rk_stage_part: null grid"); return SPB_ERR_BAD_ARG; }
+        if (part == SPB_PART_ALL) return spb_flux_div_rk_stage_exchange(g, q_in, q_out, f, sd, fuse_ghosts ? exch : nullptr, 0, g->nlb, stream);
+        if (!exch) { set_error("spb_flux_div_rk_stage_part: a part needs the exchange plan"); return SPB_ERR_BAD_ARG; }
+        const int* list = nullptr; int64_t count = 0;
+        int rc = exchange_block_list(exch, g->nlb, part, &list, &count); if (rc) return rc;
+        if (count == 0) return 0;
+        BlockList& bl = current_block_list();
+        bl.dev = list; bl.count = count;
+        rc = spb_flux_div_rk_stage_exchange(g, q_in, q_out, f, sd, fuse_ghosts ? exch : nullptr, 0, g->nlb, stream);
+        bl.dev = nullptr; bl.count = 0;
+        return rc;
+    }
+
     int spb_flux_div(const spb_grid* g, const double* q_dev, double* rhs_dev, const spb_flux_desc* f, int increment, void* stream)
     {
         if (!g) { spb::set_error("spb_flux_div: null grid"); return SPB_ERR_BAD_ARG; }

@@ -80,6 +80,7 @@ namespace spb
             int ghost;                      // fused stage: also store the finished q planes into the same-rank neighbours' ghost cells
             double idx[3], cdx[3];          // uniform lattice: 1/dx and 0.25/dx
             int lm;                         // general coordinates: row length of the metric tables (spb_grid::metric_lm)
+            const int* blist;               // local block of CTA group t (a scattered block set in one launch), or null: lb0 + t
         };
 
         // One tensor map per neighbour direction e = (ex+1) + 3*(ey+1) + 9*(ez+1): a view of q_out whose extents are exactly
@@ -216,7 +217,7 @@ namespace spb
             int t = blockIdx.x;
             const int ti = t % G.tiles_i; t /= G.tiles_i;
             const int tj = t % G.tiles_j; t /= G.tiles_j;
-            const long long lb = G.lb0 + t;
+            const long long lb = G.blist ? (long long)G.blist[t] : G.lb0 + t;
             const int i0 = ti*TI, j0 = tj*TJ;
             const int nz = G.nx[2];
             const int ni_t = min(TI, G.nx[0] - i0);
@@ -892,7 +893,10 @@ namespace spb
         G.increment = increment;
         G.lm = g->metric_lm;
         G.tma_store = tma_store;
-        const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
+        const BlockList& bl = current_block_list();
+        G.blist = bl.dev;
+        if (bl.dev) { lb_begin = 0; lb_end = g->nlb; }                  // the spacing check below then covers every block
+        const int64_t nblk = (bl.dev ? bl.count : lb_end - lb_begin)*G.tiles_i*G.tiles_j;
         if (nblk <= 0) return 0;
         // A lattice counts as uniform when the per-block spacings agree to 8 ulp: box.size/num_cell formed block by block
         // (cartesian_grid.h:134-135) wobbles in the last bit with the block origin, which is 1e-16 relative in the rhs.

@@ -26,6 +26,7 @@ namespace spb
         long long lb0;
         int increment;
         int lm;                     // general coordinates: length of one metric table row (spb_grid::metric_lm)
+        const int* blist;           // local block of CTA group t (a scattered block set in one launch), or null: lb0 + t
     };
 
     template <int H> struct FdivSmem
@@ -90,7 +91,7 @@ namespace spb
         int t = blockIdx.x;
         const int ti = t % G.tiles_i; t /= G.tiles_i;
         const int tj = t % G.tiles_j; t /= G.tiles_j;
-        const long long lb = G.lb0 + t;
+        const long long lb = G.blist ? (long long)G.blist[t] : G.lb0 + t;
         const int i0 = ti*TI, j0 = tj*TJ;
         const int nz = G.nx[2];
         const int ni_t = min(TI, G.nx[0] - i0);     // interior cells of this tile along i / j
@@ -378,7 +379,9 @@ namespace spb
         const int* nbr_tab = nullptr;
         if (FUSED && exch) { int rc = exchange_fuse_table(exch, g->nx, g->ng, g->nlb, &nbr_tab); if (rc) return rc; }
         if (CURV && !g->metric_dev) { set_error("spb_flux_div: general-coordinate kernel without a metric (spb_grid_set_metric)"); return SPB_ERR_BAD_ARG; }
-        const int64_t nblk = (lb_end - lb_begin)*G.tiles_i*G.tiles_j;
+        const BlockList& bl = current_block_list();
+        G.blist = bl.dev;
+        const int64_t nblk = (bl.dev ? bl.count : lb_end - lb_begin)*G.tiles_i*G.tiles_j;
         if (nblk <= 0) return 0;
         auto kern = flux_div_kernel<CONV, DISS, VISC, FUSED, CURV, SGS>;
         StageParams SP{};

@@ -137,7 +137,8 @@ def test_gpu_amr_exchange_three_simulated_ranks_bit_exact(gold, case):
 @pytest.mark.parametrize("fused", [False, True])
 def test_gpu_amr_flux_div_and_rk4_trajectory(gold, fused):
     """per-block spacing (fine blocks next to coarse ones) in the RHS kernel, and two RK4 steps with the AMR exchange;
-    the fused stage kernel refuses to fuse an interpolating plan and the integrator falls back to the separate exchange"""
+    the fused stage kernel stores the same-level (injection) ghosts itself and leaves only the interpolation transactions
+    to a separate kernel (spb_exchange_local_interp)"""
     import spade_b200.api as sp
     roots, n = CASES["a"]
     grid = sp.cartesian_grid_t.from_boxes(n, gold["a_boxes"])
@@ -156,5 +157,5 @@ def test_gpu_amr_flux_div_and_rk4_trajectory(gold, fused):
         ti.advance()
     assert (ti._plan is not None) == fused
     if fused:
-        assert not ti._fuse_exchange
+        assert ti._fuse_exchange
     assert rel_l2(ti.solution().to_host(), gold["a_q_adv"]) < 1e-12

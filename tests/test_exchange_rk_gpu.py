@@ -84,7 +84,7 @@ def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1)
     ra = sp.grid_array(grid, 0.0)
     ex = sp.make_exchange(qa, periodic)
     flux = sp.flux_desc(product_flux(scheme))
-    alg = {0: sp.rk4_t, 1: sp.ssprk3_opt, 2: sp.ssprk3_t, 3: sp.rk2_t}[integ]
+    alg = {0: sp.rk4_t, 1: sp.ssprk3_opt, 2: sp.ssprk3_t, 3: sp.rk2_t, 4: sp.ssprk34_t, 5: sp.rk38r_t}[integ]
     data = sp.integrator_data_t(qa, ra, alg)
     rhs_calc = sp.flux_div_rhs_t(flux, sp.overwrite) if fused else (lambda r, qq, t: sp.flux_div(qq, r, flux, sp.overwrite))
     ti = sp.integrator_t(sp.time_axis_t(0.0, dt), alg, data, rhs_calc,
@@ -99,7 +99,7 @@ def _advance_product(nb, n, ng, q, scheme, integ, dt, nsteps, periodic=(1, 1, 1)
     return ti.solution().to_host()
 
 
-@pytest.mark.parametrize("integ", [0, 1, 2, 3])
+@pytest.mark.parametrize("integ", [0, 1, 2, 3, 4, 5])
 def test_rk_trajectory_matches_oracle(integ):
     from oracle import port
     nb, n, ng = (2, 2, 1), (16, 8, 8), 2
@@ -114,8 +114,7 @@ def test_rk_trajectory_matches_oracle(integ):
     assert rel_l2(got - q0, want - q0) < 1e-9      # the increment itself, not just the state
 
 
-@pytest.mark.parametrize("integ", [0, 2, 3])
-@pytest.mark.parametrize("scheme", [0, 3, 4, 1, 2, 6, 11, 12])
+@pytest.mark.parametrize("integ,scheme", [(i, s) for i in (0, 2, 3) for s in (0, 3, 4, 1, 2, 6, 11, 12)] + [(4, 0), (5, 0), (4, 1), (5, 1)])
 def test_fused_stage_kernel_trajectory_matches_oracle(integ, scheme):
     """flux_div + RK stage update in one kernel (spb_flux_div_rk_stage), rk4 (with the pre-combined final update),
     ssprk3 (odd number of stages: result ends in the second buffer) and rk2; blocks that are not multiples of the tile."""

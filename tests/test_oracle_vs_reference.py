@@ -72,7 +72,7 @@ def test_exchange_tables_sanity_anchors(ref_lib):
     assert o[0, 0] == 6656 and o[1, 0] == 5760 and o[0, 3] == 20 and o[1, 3] == 48
 
 
-@pytest.mark.parametrize("integ", [0, 1, 2, 3])
+@pytest.mark.parametrize("integ", [0, 1, 2, 3, 4, 5])       # rk4, ssprk3_opt, ssprk3, rk2, ssprk34, rk38r (explicit.h:48-116)
 def test_rk_trajectory(ref_lib, integ):
     from oracle import port
     nb, n, ng = (2, 2, 1), (8, 4, 4), 2
