@@ -71,6 +71,8 @@ typedef struct spb_flux_desc
     double sensor_eps;  /* state_sensor::ducros_t::epsilon, reference state_sensor.h:21-43 */
     int    sgs;         /* SPB_SGS_* (needs visc) */
     double sgs_cw, sgs_delta, sgs_prt;   /* wale_t::cw, delta, prt */
+    int    weno_linear; /* 1: fweno_t / weno_t<.., disable_smooth> (convective.h:248-252): the linear weights 1/3, 2/3, 2/3, 1/3 instead of the
+                           nonlinear ones; 0 (enable_smooth) is the default of the reference */
 } spb_flux_desc;
 
 /* ---- grid ------------------------------------------------------------------------------------

@@ -48,7 +48,7 @@ namespace spade::b200
     template <typename F> inline void fill(spb_flux_desc&, const F&)
     {
         static_assert(always_false<F>::value, "spade_b200: this flux functor type is not in the implemented set "
-            "(totani_lr, cent_keep<2|4|6|8>, fweno_t, weno_t<rusanov_t>, hybrid_scheme_t<central, fweno_t | weno_t<rusanov_t>, ducros_t>, visc_lr<constant_viscosity_t | sgs_visc_t<constant_viscosity_t, wale_t>>, omni::compose of those); "
+            "(totani_lr, cent_keep<2|4|6|8>, fweno_t / weno_t<rusanov_t> with enable_smooth or disable_smooth, hybrid_scheme_t<central, fweno_t | weno_t<rusanov_t>, ducros_t>, visc_lr<constant_viscosity_t | sgs_visc_t<constant_viscosity_t, wale_t>>, omni::compose of those); "
             "there is no CPU fallback");
     }
     template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::totani_lr<gas_t>& f)
@@ -59,24 +59,27 @@ namespace spade::b200
         d.conv = (order == 2) ? SPB_CONV_TOTANI : (order == 4) ? SPB_CONV_CENT_KEEP4 : (order == 6) ? SPB_CONV_CENT_KEEP6 : SPB_CONV_CENT_KEEP8;
         fill_gas(d, f.gas);
     }
-    template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::fweno_t<gas_t, convective::enable_smooth>& f)
-    { d.conv = SPB_CONV_FWENO; fill_gas(d, f.gas); }
+    // fweno_t / weno_t with enable_smooth (nonlinear weights) or disable_smooth (the linear weights, convective.h:301-305,397-401)
+    template <typename gas_t, convective::weno_smooth_indicator sm> inline void fill(spb_flux_desc& d, const convective::fweno_t<gas_t, sm>& f)
+    { d.conv = SPB_CONV_FWENO; d.weno_linear = (sm == convective::disable_smooth) ? 1 : 0; fill_gas(d, f.gas); }
     // weno_t<rusanov_t> (convective.h:256-333, flux_funcs.h:9-53): the same reconstruction as fweno_t on precomputed split
     // fluxes (the nonlinear weights are algebraically identical); runs on the fweno_t kernel, agrees to round-off
-    template <typename gas_t> inline void fill(spb_flux_desc& d, const convective::weno_t<convective::rusanov_t<gas_t>, convective::enable_smooth>& f)
-    { d.conv = SPB_CONV_FWENO; fill_gas(d, f.flux_func.gas); }
-    template <typename s0_t, typename gas_t, typename float_t, typename tag_t>
-    inline void fill(spb_flux_desc& d, const convective::hybrid_scheme_t<s0_t, convective::weno_t<convective::rusanov_t<gas_t>, convective::enable_smooth>, state_sensor::ducros_t<float_t>, tag_t>& f)
+    template <typename gas_t, convective::weno_smooth_indicator sm> inline void fill(spb_flux_desc& d, const convective::weno_t<convective::rusanov_t<gas_t>, sm>& f)
+    { d.conv = SPB_CONV_FWENO; d.weno_linear = (sm == convective::disable_smooth) ? 1 : 0; fill_gas(d, f.flux_func.gas); }
+    template <typename s0_t, typename gas_t, convective::weno_smooth_indicator sm, typename float_t, typename tag_t>
+    inline void fill(spb_flux_desc& d, const convective::hybrid_scheme_t<s0_t, convective::weno_t<convective::rusanov_t<gas_t>, sm>, state_sensor::ducros_t<float_t>, tag_t>& f)
     {
         fill(d, f.scheme0);
+        d.weno_linear = (sm == convective::disable_smooth) ? 1 : 0;
         d.diss = SPB_DISS_FWENO;
         d.blend = tag_t::value ? SPB_BLEND_FULL_FLUX : SPB_BLEND_DISS_FLUX;
         d.sensor_eps = f.blender.epsilon;
     }
-    template <typename s0_t, typename gas_t, typename float_t, typename tag_t>
-    inline void fill(spb_flux_desc& d, const convective::hybrid_scheme_t<s0_t, convective::fweno_t<gas_t, convective::enable_smooth>, state_sensor::ducros_t<float_t>, tag_t>& f)
+    template <typename s0_t, typename gas_t, convective::weno_smooth_indicator sm, typename float_t, typename tag_t>
+    inline void fill(spb_flux_desc& d, const convective::hybrid_scheme_t<s0_t, convective::fweno_t<gas_t, sm>, state_sensor::ducros_t<float_t>, tag_t>& f)
     {
         fill(d, f.scheme0);
+        d.weno_linear = (sm == convective::disable_smooth) ? 1 : 0;
         d.diss = SPB_DISS_FWENO;
         d.blend = tag_t::value ? SPB_BLEND_FULL_FLUX : SPB_BLEND_DISS_FLUX;
         d.sensor_eps = f.blender.epsilon;

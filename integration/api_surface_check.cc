@@ -9,8 +9,8 @@ using real_t = double;
 
 static void show(const char* name, const spb_flux_desc& d)
 {
-    std::printf("%-44s conv=%d diss=%d blend=%d visc=%d sgs=%d gamma=%g R=%g mu=%g beta=%g prinv=%g eps=%g cw=%g delta=%g prt=%g\n", name, d.conv, d.diss,
-                d.blend, d.visc, d.sgs, d.gamma, d.R, d.mu, d.beta, d.prandtl_inv, d.sensor_eps, d.sgs_cw, d.sgs_delta, d.sgs_prt);
+    std::printf("%-44s conv=%d diss=%d blend=%d visc=%d sgs=%d linear=%d gamma=%g R=%g mu=%g beta=%g prinv=%g eps=%g cw=%g delta=%g prt=%g\n", name, d.conv, d.diss,
+                d.blend, d.visc, d.sgs, d.weno_linear, d.gamma, d.R, d.mu, d.beta, d.prandtl_inv, d.sensor_eps, d.sgs_cw, d.sgs_delta, d.sgs_prt);
 }
 
 // Instantiated but never executed without a GPU: the rest of the shim's entry points on a device::gpu array
@@ -114,6 +114,8 @@ int main(int argc, char** argv)
     show("cent_keep<8>", flux_desc(spade::convective::cent_keep<8>(air)));
     show("fweno_t", flux_desc(fweno));
     show("weno_t<rusanov_t>", flux_desc(wrus));
+    show("fweno_t<disable_smooth>", flux_desc(spade::convective::fweno_t<decltype(air), spade::convective::disable_smooth>(air)));
+    show("weno_t<rusanov_t, disable_smooth>", flux_desc(spade::convective::weno_t<decltype(rus), spade::convective::disable_smooth>(rus)));
     show("visc_lr", flux_desc(vscheme));
     show("totani_lr + visc_lr<sgs_visc_t<wale_t>>", flux_desc(compose(tscheme, sscheme)));
     {

@@ -196,6 +196,20 @@ namespace
                 func(spade::omni::compose(hyb, vscheme));
                 break;
             }
+            case 17: { func(spade::convective::fweno_t<decltype(air), spade::convective::disable_smooth>(air)); break; }
+            case 18:
+            {
+                spade::convective::rusanov_t rus(air);
+                func(spade::convective::weno_t<decltype(rus), spade::convective::disable_smooth>(rus));
+                break;
+            }
+            case 19:
+            {
+                spade::convective::fweno_t<decltype(air), spade::convective::disable_smooth> wlin(air);
+                spade::convective::hybrid_scheme_t hyb(tscheme, wlin, ducr, spade::convective::full_flux);
+                func(spade::omni::compose(hyb, vscheme));
+                break;
+            }
             default: throw std::runtime_error("ref_driver: unknown scheme id");
         }
     }

@@ -16,7 +16,8 @@ class FluxDesc(C.Structure):
     _fields_ = [("conv", C.c_int), ("diss", C.c_int), ("blend", C.c_int), ("visc", C.c_int),
                 ("gamma", C.c_double), ("R", C.c_double), ("mu", C.c_double), ("beta", C.c_double),
                 ("prandtl_inv", C.c_double), ("sensor_eps", C.c_double),
-                ("sgs", C.c_int), ("sgs_cw", C.c_double), ("sgs_delta", C.c_double), ("sgs_prt", C.c_double)]
+                ("sgs", C.c_int), ("sgs_cw", C.c_double), ("sgs_delta", C.c_double), ("sgs_prt", C.c_double),
+                ("weno_linear", C.c_int)]
 
 
 class StageDesc(C.Structure):

@@ -413,15 +413,22 @@ class cent_keep(_functor):
         d.gamma, d.R = self.gas.gamma, self.gas.R
 
 
-class fweno_t(_functor):
-    """convective::fweno_t<gas, enable_smooth>, convective.h:336-497"""
+enable_smooth, disable_smooth = "enable_smooth", "disable_smooth"      # convective::weno_smooth_indicator, convective.h:248-252
 
-    def __init__(self, gas):
-        self.gas = gas
+
+class fweno_t(_functor):
+    """convective::fweno_t<gas, use_smooth>, convective.h:336-497; disable_smooth = the linear weights 1/3, 2/3, 2/3, 1/3
+    (convective.h:397-401, "use this for MMS")"""
+
+    def __init__(self, gas, use_smooth=enable_smooth):
+        if use_smooth not in (enable_smooth, disable_smooth):
+            raise SpbError("fweno_t: use_smooth is enable_smooth or disable_smooth")
+        self.gas, self.use_smooth = gas, use_smooth
 
     def _fill(self, d):
         d.conv = CONV_FWENO
         d.gamma, d.R = self.gas.gamma, self.gas.R
+        d.weno_linear = 1 if self.use_smooth == disable_smooth else 0
 
 
 class rusanov_t:
@@ -436,10 +443,10 @@ class weno_t(fweno_t):
     (the nonlinear weights a0/(a0+a1) and be1^2/(2 be0^2 + be1^2) are the same number), applied to precomputed split
     fluxes; it runs on the fweno_t kernel and agrees with the reference's weno_t to round-off."""
 
-    def __init__(self, flux_func):
+    def __init__(self, flux_func, use_smooth=enable_smooth):
         if not isinstance(flux_func, rusanov_t):
             raise SpbError("weno_t: implemented for the rusanov_t flux function")
-        super().__init__(flux_func.gas)
+        super().__init__(flux_func.gas, use_smooth)
 
 
 class ducros_t:
@@ -1251,6 +1258,77 @@ class io:
         host = torch.from_numpy(np.frombuffer(raw, dtype=np.float64).reshape(array.shape).copy())
         array.data.copy_(host.pin_memory(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
+
+
+    # ---- visualisation files (reference src/io/io_vtk.h:276-288) -----------------------------------------------------
+    VAR_NAMES = {"prim": ("P", "T", "U", "V", "W"), "cons": ("rho", "rhoH", "rhoU", "rhoV", "rhoW"),
+                 "flux": ("continuity", "energy", "x_momentum", "y_momentum", "z_momentum")}       # fluid_state.h:28-77
+
+    @staticmethod
+    def _b64(raw):
+        """spade::detail::stream_base_64 of a vector (core/base_64.h:68-75): the uint32 byte count and the payload are
+        encoded separately, each with its own '=' padding."""
+        import base64
+        import struct
+        return base64.b64encode(struct.pack("<I", len(raw))) + base64.b64encode(raw)
+
+    @staticmethod
+    def write_vtk_files(out_dir, basename, host, num_cell, num_exch, boxes, global_ids, num_global_blocks, coords=None,
+                        names=("P", "T", "U", "V", "W"), write_base=True):
+        """The files of io::output_vtk for blocks held on the host: `<basename>.pvts` (written if write_base: the root rank's
+        job) and one `data_<basename>/b<9-digit global id>.vts` per block — StructuredGrid pieces with the interior cells
+        of every variable as base-64 "binary" CellData in i-fastest order and the (ni+1)(nj+1)(nk+1) node positions
+        coords.map(box.min + index*dx) (grid_geometry.h:52-70), byte for byte the reference's files
+        (tests/golden/vtk_small, written by the unmodified reference)."""
+        ni, nj, nk = (int(x) for x in num_cell)
+        g = [int(x) for x in num_exch]
+        os.makedirs(os.path.join(out_dir, "data_" + basename), exist_ok=True)
+        if write_base:
+            with open(os.path.join(out_dir, basename + ".pvts"), "w") as f:
+                f.write('<?xml version="1.0"?>\n<VTKFile type="PStructuredGrid" version="0.1" byte_order="LittleEndian">\n')
+                f.write(f'<PStructuredGrid WholeExtent="0 {ni} 0 {nj} 0 {nk * num_global_blocks}" GhostLevel="0">\n')
+                f.write(f'<PCellData Scalars = "{",".join(names)}">\n')
+                for nm in names:
+                    f.write(f'<PDataArray type="Float64" Name="{nm}"/>\n')
+                f.write('</PCellData>\n<PPoints>\n<PDataArray type="Float64" NumberOfComponents="3"/>\n</PPoints>\n')
+                for lb in range(num_global_blocks):
+                    f.write(f'<Piece Extent="0 {ni} 0 {nj} {lb * nk} {(lb + 1) * nk}" Source="data_{basename}/b{lb:09d}.vts"/>\n')
+                f.write('</PStructuredGrid>\n</VTKFile>\n')
+        for l, lb_glob in enumerate(global_ids):
+            blk = host[l, g[2]:g[2] + nk, g[1]:g[1] + nj, g[0]:g[0] + ni, :]
+            bx = boxes[l]
+            dx = [(bx[2 * d + 1] - bx[2 * d]) / n for d, n in enumerate((ni, nj, nk))]      # bbx.size(d)/num_cell[d]
+            ax = [bx[2 * d] + np.arange(n + 1, dtype=np.float64) * dx[d] for d, n in enumerate((ni, nj, nk))]
+            if coords is not None and not isinstance(coords, identity):
+                ax = [np.array([c.map(float(x)) for x in a]) for c, a in zip((coords.xcoord, coords.ycoord, coords.zcoord), ax)]
+            pts = np.empty((nk + 1, nj + 1, ni + 1, 3))
+            pts[..., 0], pts[..., 1], pts[..., 2] = ax[0][None, None, :], ax[1][None, :, None], ax[2][:, None, None]
+            with open(os.path.join(out_dir, "data_" + basename, f"b{int(lb_glob):09d}.vts"), "wb") as f:
+                f.write(b'<?xml version="1.0"?>\n<VTKFile type="StructuredGrid" version="0.1" byte_order="LittleEndian">\n')
+                f.write(f'<StructuredGrid WholeExtent="0 {ni} 0 {nj} 0 {nk}">\n<Piece Extent="0 {ni} 0 {nj} 0 {nk}">\n'.encode())
+                f.write(f'<CellData Scalars="{",".join(names)}">\n'.encode())
+                for v, nm in enumerate(names):
+                    f.write(f'<DataArray type="Float64" Name="{nm}" format="binary">\n'.encode())
+                    f.write(io._b64(np.ascontiguousarray(blk[..., v]).tobytes()))
+                    f.write(b'\n</DataArray>\n')
+                f.write(b'</CellData>\n<Points>\n<DataArray type="Float64" NumberOfComponents="3" format="binary">\n')
+                f.write(io._b64(pts.tobytes()))
+                f.write(b'\n</DataArray>\n</Points>\n</Piece>\n</StructuredGrid>\n</VTKFile>\n')
+
+    @staticmethod
+    def output_vtk(out_dir, basename, array, names=None):
+        """io::output_vtk(out_dir, basename, array): every rank writes the pieces of its own blocks, the root the .pvts."""
+        grid, pool = array.grid, array.grid.group()
+        nglob = grid.get_num_global_blocks() if grid.blocks is not None else int(pool.reduce(float(grid.num_local_blocks), RED_SUM))
+        boxes = (np.array([grid.blocks.get_block_box(grid.first_block + l) for l in range(grid.num_local_blocks)])
+                 if grid.blocks is not None else grid._boxes)
+        if pool.isroot():
+            os.makedirs(out_dir, exist_ok=True)
+        pool.sync()
+        io.write_vtk_files(out_dir, basename, array.to_host(), grid.num_cell, array.num_exch, boxes,
+                           range(grid.first_block, grid.first_block + grid.num_local_blocks), nglob, grid.coords,
+                           names or io.VAR_NAMES["prim"], write_base=pool.isroot())
+        pool.sync()
 
 
 def launch_count():

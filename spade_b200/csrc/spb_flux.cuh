@@ -23,6 +23,7 @@ namespace spb
         double mu, beta, two_mu, kappa;
         double eps;
         int    blend;                 // SPB_BLEND_*
+        int    weno_linear;           // weno_smooth_indicator disable_smooth: the linear weights 1/3, 2/3, 2/3, 1/3 (convective.h:301-305,397-401)
         double sgs_c, sgs_cp_prt;     // wale_t: cw^2 delta^2; (gamma R/(gamma-1))/Pr_t
     };
 
@@ -181,7 +182,7 @@ namespace spb
     }
 
     // ---- convective::fweno_t ---------------------------------------------------------------------
-    __device__ __forceinline__ double fweno_apply(const double (&f)[4], const double (&d)[4])
+    __device__ __forceinline__ double fweno_apply(const double (&f)[4], const double (&d)[4], const int linear)
     {
         const double f0u = f[0] + d[0];
         const double f1u = f[1] + d[1], f1d = f[1] - d[1];
@@ -191,6 +192,7 @@ namespace spb
         const double r1 = 0.5*(f1u + f2u);
         const double r2 = 0.5*(f1d + f2d);
         const double r3 = fma(1.5, f2d, -0.5*f3d);
+        if (linear) return (1.0/3.0)*(r0 + r3) + (2.0/3.0)*(r1 + r2);      // uniform over the launch
         const double eps = 1e-16;
         double a0 = f0u - f1u, a1 = f1u - f2u, a2 = f1d - f2d, a3 = f2d - f3d;
         a0 = fma(a0, a0, eps); a0 *= a0;
@@ -224,7 +226,7 @@ namespace spb
         }
         const double hA = CURV ? 0.5*A : 0.5;
         // continuity
-        F[0] = fweno_apply(fm, hsr);
+        F[0] = fweno_apply(fm, hsr, P.weno_linear);
         // energy
         #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -233,7 +235,7 @@ namespace spb
             fl[i] = fm[i]*(engy + a[i]);
             ds[i] = hsr[i]*engy;
         }
-        F[1] = fweno_apply(fl, ds);
+        F[1] = fweno_apply(fl, ds, P.weno_linear);
         // momentum
         #pragma unroll
         for (int dr = 0; dr < 3; ++dr)
@@ -245,7 +247,7 @@ namespace spb
                 if (dr == D) fl[i] = fma(hA, q[i][0], fl[i]);
                 ds[i] = hsr[i]*q[i][2+dr];
             }
-            F[2+dr] = fweno_apply(fl, ds);
+            F[2+dr] = fweno_apply(fl, ds, P.weno_linear);
         }
     }
 

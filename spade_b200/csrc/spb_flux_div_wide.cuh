@@ -399,7 +399,7 @@ namespace spb
         P.mu = f->mu; P.beta = f->beta; P.two_mu = 2.0*f->mu;
         // reference viscous.h:64-68: cond = (gamma R/(gamma-1)) * (mu * prandtl_inv)
         P.kappa = (f->gamma*f->R/(f->gamma - 1.0))*(f->mu*f->prandtl_inv);
-        P.eps = f->sensor_eps; P.blend = f->blend;
+        P.eps = f->sensor_eps; P.blend = f->blend; P.weno_linear = f->weno_linear ? 1 : 0;
         // wale_t (subgrid_scale.h:86-89): mu_t = rho cw cw delta delta (...); sgs_visc_t: alpha += mu_t/Pr_t (viscous_laws.h:192-195)
         P.sgs_c = f->sgs_cw*f->sgs_cw*f->sgs_delta*f->sgs_delta;
         P.sgs_cp_prt = f->sgs ? (f->gamma*f->R/(f->gamma - 1.0))/f->sgs_prt : 0.0;

@@ -90,7 +90,9 @@ def test_shim_recognises_every_functor_type_of_the_implemented_set():
     for line in out.stdout.strip().splitlines():
         name, rest = line[:44].strip(), line[44:].split()
         rows[name] = dict(kv.split("=") for kv in rest)
-    assert len(rows) == 13
+    assert len(rows) == 15
+    assert rows["fweno_t"]["linear"] == "0" and rows["fweno_t<disable_smooth>"]["linear"] == "1"
+    assert rows["weno_t<rusanov_t, disable_smooth>"]["linear"] == "1" and rows["weno_t<rusanov_t, disable_smooth>"]["conv"] == "3"
     assert rows["totani_lr"]["conv"] == "1" and rows["cent_keep<2>"]["conv"] == "1"
     assert rows["cent_keep<6> + visc_lr"]["conv"] == "4" and rows["cent_keep<8>"]["conv"] == "5"
     assert rows["fweno_t"]["conv"] == "3" and rows["weno_t<rusanov_t>"]["conv"] == "3"

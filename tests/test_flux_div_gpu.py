@@ -18,11 +18,11 @@ def run_product(nb, n, ng, q, scheme, increment=False, rhs0=None, bounds=None, *
     return ra.to_host()
 
 
-@pytest.mark.parametrize("scheme", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
+@pytest.mark.parametrize("scheme", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 17, 18, 19])
 def test_schemes_match_oracle(scheme):
     from oracle import port
     nb, n, ng = (2, 1, 2), (32, 16, 8), 2
-    q = make_state(nb, n, ng, seed=scheme, jump=scheme in (1, 6, 8, 10, 12))
+    q = make_state(nb, n, ng, seed=scheme, jump=scheme in (1, 6, 8, 10, 12, 19))
     cfg = oracle_cfg(nb, n, ng, scheme=scheme)
     want = port.flux_div(cfg, q.ravel()).reshape(q.shape)
     got = run_product(nb, n, ng, q, scheme)

@@ -13,11 +13,11 @@ import pytest
 from util import GAMMA, RGAS, make_state, oracle_cfg, rel_l2, zero_ghosts
 
 
-@pytest.mark.parametrize("scheme", range(17))
+@pytest.mark.parametrize("scheme", range(20))          # 17-19: fweno_t / weno_t / hybrid with disable_smooth
 def test_flux_div_all_schemes(ref_lib, scheme):
     from oracle import port
     nb, n, ng = (2, 1, 2), (8, 6, 4), {13: 3, 14: 4, 15: 3, 16: 4}.get(scheme, 2)
-    q = make_state(nb, n, ng, seed=scheme, jump=scheme in (1, 6, 8, 10, 12))
+    q = make_state(nb, n, ng, seed=scheme, jump=scheme in (1, 6, 8, 10, 12, 19))
     cfg = oracle_cfg(nb, n, ng, scheme=scheme)
     want = ref_lib.flux_div(cfg, q.ravel())
     got = port.flux_div(cfg, q.ravel())

@@ -97,6 +97,9 @@ def product_flux(scheme, gamma=GAMMA, R=RGAS, mu=1e-2, prandtl=0.72, eps=1e-2):
             14: lambda: sp.compose(sp.cent_keep(8, gas), v),
             15: lambda: sp.cent_keep(6, gas),
             16: lambda: sp.cent_keep(8, gas),
+            17: lambda: sp.fweno_t(gas, sp.disable_smooth),
+            18: lambda: sp.weno_t(sp.rusanov_t(gas), sp.disable_smooth),
+            19: lambda: sp.compose(sp.hybrid_scheme_t(t, sp.fweno_t(gas, sp.disable_smooth), du, sp.full_flux), v),
             9: lambda: sp.weno_t(sp.rusanov_t(gas)),
             10: lambda: sp.compose(sp.hybrid_scheme_t(t, sp.weno_t(sp.rusanov_t(gas)), du, sp.full_flux), v)}[scheme]()
 
