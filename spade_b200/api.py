@@ -471,6 +471,7 @@ class hybrid_scheme_t(_functor):
     def _fill(self, d):
         self.scheme0._fill(d)
         d.diss = DISS_FWENO
+        d.weno_linear = 1 if self.scheme1.use_smooth == disable_smooth else 0
         d.blend = self.tag
         d.sensor_eps = self.blender.epsilon
 

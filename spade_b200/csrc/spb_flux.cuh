@@ -192,17 +192,69 @@ namespace spb
         const double r1 = 0.5*(f1u + f2u);
         const double r2 = 0.5*(f1d + f2d);
         const double r3 = fma(1.5, f2d, -0.5*f3d);
-        if (linear) return (1.0/3.0)*(r0 + r3) + (2.0/3.0)*(r1 + r2);      // uniform over the launch
         const double eps = 1e-16;
         double a0 = f0u - f1u, a1 = f1u - f2u, a2 = f1d - f2d, a3 = f2d - f3d;
         a0 = fma(a0, a0, eps); a0 *= a0;
         a1 = fma(a1, a1, eps); a1 *= a1;
         a2 = fma(a2, a2, eps); a2 *= a2;
         a3 = fma(a3, a3, eps); a3 *= a3;
-        const double w0 = a1*rcp_nr(a0 + a0 + a1);
-        const double w3 = a2*rcp_nr(a3 + a3 + a2);
+        double w0 = a1*rcp_nr(a0 + a0 + a1);
+        double w3 = a2*rcp_nr(a3 + a3 + a2);
+        if (linear) { w0 = 1.0/3.0; w3 = 1.0/3.0; }      // disable_smooth: the linear weights (two selects, no control flow)
         // w0 r0 + (1-w0) r1 + (1-w3) r2 + w3 r3
         return fma(w0, r0 - r1, r1) + fma(w3, r3 - r2, r2);
+    }
+
+    // The direction-independent per-cell part of fweno_t (convective.h:355-378): hr = rho/2 and hs = (rho/2)(|u| + c). One
+    // reciprocal and two square roots per CELL: the wide kernel evaluates it once per cell and plane and hands it to the
+    // faces (flux_fweno_pre) instead of once per stencil cell of every face (12 times per cell).
+    __device__ __forceinline__ void weno_cell(const FluxParams& P, const double p, const double T, const double u, const double v,
+                                              const double w, double& hr, double& hs)
+    {
+        const double a = P.R*T;
+        const double u2 = fma(u, u, fma(v, v, w*w));
+        hr = 0.5*(p*rcp_nr(a));
+        hs = hr*(sqrt_nr(fmax(u2, 1e-300)) + sqrt_nr(a*P.gamma));      // |u| = 0 becomes 1e-150
+    }
+
+    // fweno_t on prepared cells: the same arithmetic as flux_fweno below with rho/2 and the half spectral radius given
+    template <int D, bool CURV = false>
+    __device__ __forceinline__ void flux_fweno_pre(const FluxParams& P, const double (&c0)[5], const double (&c1)[5],
+                                                   const double (&c2)[5], const double (&c3)[5], const double (&hr)[4],
+                                                   const double (&hsr)[4], double (&F)[5], const double A = 1.0)
+    {
+        const double* q[4] = {c0, c1, c2, c3};
+        double a[4], ke[4], fm[4], fl[4], ds[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            a[i]  = P.R*q[i][1];
+            ke[i] = 0.5*fma(q[i][2], q[i][2], fma(q[i][3], q[i][3], q[i][4]*q[i][4]));
+            fm[i] = hr[i]*q[i][2+D];
+            if (CURV) fm[i] *= A;
+        }
+        const double hA = CURV ? 0.5*A : 0.5;
+        F[0] = fweno_apply(fm, hsr, P.weno_linear);
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const double engy = fma(a[i], P.inv_gm1, ke[i]);
+            fl[i] = fm[i]*(engy + a[i]);
+            ds[i] = hsr[i]*engy;
+        }
+        F[1] = fweno_apply(fl, ds, P.weno_linear);
+        #pragma unroll
+        for (int dr = 0; dr < 3; ++dr)
+        {
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                fl[i] = fm[i]*q[i][2+dr];
+                if (dr == D) fl[i] = fma(hA, q[i][0], fl[i]);
+                ds[i] = hsr[i]*q[i][2+dr];
+            }
+            F[2+dr] = fweno_apply(fl, ds, P.weno_linear);
+        }
     }
 
     // general coordinates: the metric scales the flux part (u.n, p n) but not the Rusanov dissipation, exactly like the
@@ -280,9 +332,10 @@ namespace spb
         return rho*P.sgs_c*ssd*sqrt0*rcp_nr(1e-8 + fma(ss*ss, sqrt2, ssd*sqrt1));
     }
 
-    template <int CONV, int DISS, int VISC, int D, bool CURV = false, bool SGS = false, class A>
+    // PRE: hr4 / hs4 hold weno_cell of the four stencil cells (LL, L, R, RR) of the face
+    template <int CONV, int DISS, int VISC, int D, bool CURV = false, bool SGS = false, bool PRE = false, class A>
     __device__ __forceinline__ void face_flux(const A& a, const FluxParams& P, const double (&invdx)[3], double (&F)[5],
-                                              const double area = 1.0)
+                                              const double area = 1.0, const double* hr4 = nullptr, const double* hs4 = nullptr)
     {
         constexpr int T1 = (D + 1) % 3, T2 = (D + 2) % 3;
         constexpr bool WIDE = (CONV == SPB_CONV_CENT_KEEP4) || (CONV == SPB_CONV_FWENO) || (DISS != SPB_DISS_NONE);
@@ -299,7 +352,17 @@ namespace spb
 
         if (CONV == SPB_CONV_TOTANI)     flux_totani<D>(P, qL, qR, F);
         if (CONV == SPB_CONV_CENT_KEEP4) flux_cent_keep4<D>(P, qLL, qL, qR, qRR, F);
-        if (CONV == SPB_CONV_FWENO)      flux_fweno<D, CURV>(P, qLL, qL, qR, qRR, F, area);
+        double hrv[4] = {0.0, 0.0, 0.0, 0.0}, hsv[4] = {0.0, 0.0, 0.0, 0.0};
+        if (PRE)
+        {
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) { hrv[i] = hr4[i]; hsv[i] = hs4[i]; }
+        }
+        if (CONV == SPB_CONV_FWENO)
+        {
+            if (PRE) flux_fweno_pre<D, CURV>(P, qLL, qL, qR, qRR, hrv, hsv, F, area);
+            else     flux_fweno<D, CURV>(P, qLL, qL, qR, qRR, F, area);
+        }
         if (CONV == SPB_CONV_CENT_KEEP6 || CONV == SPB_CONV_CENT_KEEP8)
         {
             constexpr int ORDER = (CONV == SPB_CONV_CENT_KEEP6) ? 6 : 8;
@@ -348,7 +411,8 @@ namespace spb
                 const double vort = fma(w0, w0, fma(w1, w1, w2*w2));
                 const double alpha = th2*rcp_nr(th2 + vort + P.eps);
                 double F1[5];
-                flux_fweno<D, CURV>(P, qLL, qL, qR, qRR, F1, area);
+                if (PRE) flux_fweno_pre<D, CURV>(P, qLL, qL, qR, qRR, hrv, hsv, F1, area);
+                else     flux_fweno<D, CURV>(P, qLL, qL, qR, qRR, F1, area);
                 const double coeff0 = (P.blend == SPB_BLEND_FULL_FLUX) ? (1.0 - alpha) : 1.0;
                 #pragma unroll
                 for (int v = 0; v < 5; ++v) F[v] = fma(alpha, F1[v], coeff0*F[v]);

@@ -47,6 +47,11 @@ namespace spb
         static constexpr int FX_DOUBLES = TJ*(TI + 1)*5;
         static constexpr int FY_DOUBLES = (TJ + 1)*TI*5;
         static constexpr int BYTES = NP*PLANE_STRIDE_BYTES + (FX_DOUBLES + FY_DOUBLES)*8 + NP*8 + 128;
+        // WENO kernels (PRE): the x-fluxes travel by warp shuffle (only the tile's upper-edge column goes through shared memory) and
+        // the freed space holds the per-cell WENO preparation of ONE plane, two values per cell of the tile + 2 halo cells
+        static constexpr int PW = TI + 4, PH = TJ + 4, PUB_CELLS = PW*PH;
+        static constexpr int FXE_DOUBLES = TJ*5;
+        static constexpr int BYTES_PRE = NP*PLANE_STRIDE_BYTES + (FXE_DOUBLES + FY_DOUBLES + 2*PUB_CELLS)*8 + NP*8 + 128;
     };
 
     // accessor of the staged planes, centred on tile-local cell (il, jl) of the current plane
@@ -81,9 +86,13 @@ namespace spb
         // pointer arithmetic on the __shared__ symbol (no integer round trip) keeps the address space known
         // to the compiler: LDS/STS instead of generic LD/ST
         double*   ring = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u)/8u;
-        double*   Fx   = ring + S::NP*S::PLANE_STRIDE;
-        double*   Fy   = Fx + S::FX_DOUBLES;
-        uint64_t* bars = (uint64_t*)(Fy + S::FY_DOUBLES);
+        // PRE: per-cell WENO preparation published once per plane (see FdivSmem), x-fluxes by shuffle
+        constexpr bool PRE = (CONV == SPB_CONV_FWENO) || (DISS == SPB_DISS_FWENO);
+        double*   Fx   = ring + S::NP*S::PLANE_STRIDE;                           // PRE: only the upper-edge column [TJ][5]
+        double*   Fy   = Fx + (PRE ? S::FXE_DOUBLES : S::FX_DOUBLES);
+        double*   pubh = Fy + S::FY_DOUBLES;                                     // PRE: rho/2 of the published plane
+        double*   pubs = pubh + S::PUB_CELLS;                                    // PRE: (rho/2)(|u| + c)
+        uint64_t* bars = (uint64_t*)(PRE ? pubs + S::PUB_CELLS : Fy + S::FY_DOUBLES);
 
         const int tid = threadIdx.x;
         const int il = tid & 31, jl = tid >> 5;
@@ -159,6 +168,39 @@ namespace spb
         #pragma unroll
         for (int d = 0; d < AH; ++d) acc.pl[d] = d*S::PLANE_STRIDE;
 
+        // PRE: weno_cell of the own column for the cells k-2 .. k+1 (the stencil of the z-face k-1/2) rolls through registers; the
+        // plane the x / y faces of a step read is published in shared memory: the interior cells from these registers, the
+        // 2-cell halo ring (176 cells) evaluated by the first 176 threads
+        double zh[4] = {0.0, 0.0, 0.0, 0.0}, zs[4] = {0.0, 0.0, 0.0, 0.0};
+        const int pown = (jl + 2)*S::PW + (il + 2);
+        int phalo = -1, chalo = 0;                   // published index and ring offset of this thread's halo cell
+        if (PRE && tid < S::PUB_CELLS - TI*TJ)
+        {
+            int pi, pj;
+            if (tid < 4*S::PW) { pj = tid / S::PW; pi = tid - pj*S::PW; if (pj >= 2) pj += TJ; }
+            else { const int r = tid - 4*S::PW; pj = 2 + r/4; const int c = r & 3; pi = (c < 2) ? c : TI + c; }
+            phalo = pj*S::PW + pi;
+            chalo = (pj*S::TIp + (pi + ash))*5;      // H = 2: tile-local cell (pi - 2, pj - 2) sits at box column pi - 2 + H + ash
+        }
+        auto publish = [&](const int dk, const double hr_own, const double hs_own)
+        {
+            pubh[pown] = hr_own; pubs[pown] = hs_own;
+            if (phalo >= 0)
+            {
+                const double* c = ring + acc.pl[dk + H] + chalo;
+                double hr, hs;
+                weno_cell(P, c[0], c[1], c[2], c[3], c[4], hr, hs);
+                pubh[phalo] = hr; pubs[phalo] = hs;
+            }
+        };
+        if (PRE)
+        {
+            #pragma unroll
+            for (int d = 0; d < 3; ++d)
+                weno_cell(P, acc(0, 0, 0, d - 2), acc(1, 0, 0, d - 2), acc(2, 0, 0, d - 2), acc(3, 0, 0, d - 2), acc(4, 0, 0, d - 2), zh[d], zs[d]);
+            publish(0, zh[2], zs[2]);
+            __syncthreads();
+        }
         double rprev[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // partial rhs of cell k-1 (x, y and lower-z parts)
         const long long col0 = lb*G.block_stride
             + 5ll*((i0 + il + G.ng[0]) + (long long)G.np[0]*((j0 + jl + G.ng[1]) + (long long)G.np[1]*G.ng[2]));
@@ -177,16 +219,18 @@ namespace spb
 
             double Fz[5];
             double jac_prev = 1.0;                   // Jacobian of cell k-1
+            if (PRE && k + AH < nplanes)             // the cell entering the z-stencil (plane k+1)
+                weno_cell(P, acc(0, 0, 0, 1), acc(1, 0, 0, 1), acc(2, 0, 0, 1), acc(3, 0, 0, 1), acc(4, 0, 0, 1), zh[3], zs[3]);
             if (active)
             {
                 if (CURV)
                 {
                     double gs[3], area;
                     face_metric(DZ, ipc, jpc, k + G.ng[2], gs, area);
-                    face_flux<CONV, DISS, VISC, 2, true, SGS>(acc, P, gs, Fz, area);
+                    face_flux<CONV, DISS, VISC, 2, true, SGS, PRE>(acc, P, gs, Fz, area, zh, zs);
                     if (k >= 1) jac_prev = M(0, 1, ipc)*M(1, 1, jpc)*M(2, 1, k - 1 + G.ng[2]);
                 }
-                else face_flux<CONV, DISS, VISC, 2, false, SGS>(acc, P, invdx, Fz);
+                else face_flux<CONV, DISS, VISC, 2, false, SGS, PRE>(acc, P, invdx, Fz, 1.0, zh, zs);
             }
 
             if (k >= 1 && active)
@@ -279,19 +323,51 @@ namespace spb
                 }
             }
 
+            double dFxy[5] = {0.0, 0.0, 0.0, 0.0, 0.0};          // PRE: F_x(own) - F_x(il+1) for all but the tile's last column
             if (k < nz)
             {
+                double Fxo[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
                 if (active)
                 {
                     double F[5], gs[3], area;
-                    if (CURV) { face_metric(DX, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true, SGS>(acc, P, gs, F, area); }
-                    else face_flux<CONV, DISS, VISC, 0, false, SGS>(acc, P, invdx, F);
-                    #pragma unroll
-                    for (int v = 0; v < 5; ++v) Fx[(jl*(TI + 1) + il)*5 + v] = F[v];
-                    if (CURV) { face_metric(DY, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true, SGS>(acc, P, gs, F, area); }
-                    else face_flux<CONV, DISS, VISC, 1, false, SGS>(acc, P, invdx, F);
+                    double h4[4], s4[4];
+                    if (PRE)
+                    {
+                        #pragma unroll
+                        for (int i = 0; i < 4; ++i) { h4[i] = pubh[pown - 2 + i]; s4[i] = pubs[pown - 2 + i]; }
+                    }
+                    if (CURV) { face_metric(DX, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true, SGS, PRE>(acc, P, gs, F, area, h4, s4); }
+                    else face_flux<CONV, DISS, VISC, 0, false, SGS, PRE>(acc, P, invdx, F, 1.0, h4, s4);
+                    if (PRE)
+                    {
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v) Fxo[v] = F[v];
+                    }
+                    else
+                    {
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v) Fx[(jl*(TI + 1) + il)*5 + v] = F[v];
+                    }
+                    if (PRE)
+                    {
+                        #pragma unroll
+                        for (int i = 0; i < 4; ++i) { h4[i] = pubh[pown + (i - 2)*S::PW]; s4[i] = pubs[pown + (i - 2)*S::PW]; }
+                    }
+                    if (CURV) { face_metric(DY, ipc, jpc, k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true, SGS, PRE>(acc, P, gs, F, area, h4, s4); }
+                    else face_flux<CONV, DISS, VISC, 1, false, SGS, PRE>(acc, P, invdx, F, 1.0, h4, s4);
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) Fy[(jl*TI + il)*5 + v] = F[v];
+                }
+                if (PRE)
+                {
+                    // the x-flux of the right neighbour comes by shuffle (all 32 lanes take part; a warp is one tile row)
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) dFxy[v] = Fxo[v] - __shfl_down_sync(0xffffffffu, Fxo[v], 1);
+                    if (il == ni_t - 1)
+                    {
+                        #pragma unroll
+                        for (int v = 0; v < 5; ++v) dFxy[v] = Fxo[v];      // minus the edge flux after the barrier
+                    }
                 }
                 // faces on the upper edge of the tile
                 if (tid < nj_t)                      // warp 0: x-face i = ni_t of row tid
@@ -299,18 +375,32 @@ namespace spb
                     TileAcc<H> e = acc;
                     e.cell = ((tid + H)*S::TIp + (ni_t + H + ash))*5;
                     double F[5], gs[3], area;
-                    if (CURV) { face_metric(DX, i0 + ni_t + G.ng[0], j0 + tid + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true, SGS>(e, P, gs, F, area); }
-                    else face_flux<CONV, DISS, VISC, 0, false, SGS>(e, P, invdx, F);
+                    double h4[4], s4[4];
+                    if (PRE)
+                    {
+                        const int pe = (tid + 2)*S::PW + (ni_t + 2);
+                        #pragma unroll
+                        for (int i = 0; i < 4; ++i) { h4[i] = pubh[pe - 2 + i]; s4[i] = pubs[pe - 2 + i]; }
+                    }
+                    if (CURV) { face_metric(DX, i0 + ni_t + G.ng[0], j0 + tid + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 0, true, SGS, PRE>(e, P, gs, F, area, h4, s4); }
+                    else face_flux<CONV, DISS, VISC, 0, false, SGS, PRE>(e, P, invdx, F, 1.0, h4, s4);
                     #pragma unroll
-                    for (int v = 0; v < 5; ++v) Fx[(tid*(TI + 1) + ni_t)*5 + v] = F[v];
+                    for (int v = 0; v < 5; ++v) Fx[PRE ? tid*5 + v : (tid*(TI + 1) + ni_t)*5 + v] = F[v];
                 }
                 if (tid >= 32 && tid < 32 + ni_t)    // warp 1: y-face j = nj_t of column tid-32
                 {
                     TileAcc<H> e = acc;
                     e.cell = ((nj_t + H)*S::TIp + (tid - 32 + H + ash))*5;
                     double F[5], gs[3], area;
-                    if (CURV) { face_metric(DY, i0 + tid - 32 + G.ng[0], j0 + nj_t + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true, SGS>(e, P, gs, F, area); }
-                    else face_flux<CONV, DISS, VISC, 1, false, SGS>(e, P, invdx, F);
+                    double h4[4], s4[4];
+                    if (PRE)
+                    {
+                        const int pe = (nj_t + 2)*S::PW + (tid - 32 + 2);
+                        #pragma unroll
+                        for (int i = 0; i < 4; ++i) { h4[i] = pubh[pe + (i - 2)*S::PW]; s4[i] = pubs[pe + (i - 2)*S::PW]; }
+                    }
+                    if (CURV) { face_metric(DY, i0 + tid - 32 + G.ng[0], j0 + nj_t + G.ng[1], k + G.ng[2], gs, area); face_flux<CONV, DISS, VISC, 1, true, SGS, PRE>(e, P, gs, F, area, h4, s4); }
+                    else face_flux<CONV, DISS, VISC, 1, false, SGS, PRE>(e, P, invdx, F, 1.0, h4, s4);
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) Fy[(nj_t*TI + (tid - 32))*5 + v] = F[v];
                 }
@@ -321,12 +411,21 @@ namespace spb
                 #pragma unroll
                 for (int v = 0; v < 5; ++v)
                 {
-                    const double dFx = Fx[(jl*(TI + 1) + il)*5 + v] - Fx[(jl*(TI + 1) + il + 1)*5 + v];
+                    double dFx;
+                    if (PRE) dFx = (il == ni_t - 1) ? dFxy[v] - Fx[jl*5 + v] : dFxy[v];
+                    else     dFx = Fx[(jl*(TI + 1) + il)*5 + v] - Fx[(jl*(TI + 1) + il + 1)*5 + v];
                     const double dFy = Fy[(jl*TI + il)*5 + v] - Fy[((jl + 1)*TI + il)*5 + v];
                     rprev[v] = fma(dFx, invdx[0], fma(dFy, invdx[1], Fz[v]*invdx[2]));
                 }
             }
+            // PRE: the x / y faces of this step have read the published plane (barrier above): publish plane k+1 for the next step
+            if (PRE && k + 1 < nz) publish(1, zh[3], zs[3]);
             __syncthreads();
+            if (PRE)
+            {
+                #pragma unroll
+                for (int d = 0; d < 3; ++d) { zh[d] = zh[d + 1]; zs[d] = zs[d + 1]; }
+            }
             // slot of plane p = k (dk = -H) is free now: refill it with plane p + NP
             if (tid == 0)
             {
@@ -386,8 +485,10 @@ namespace spb
         auto kern = flux_div_kernel<CONV, DISS, VISC, FUSED, CURV, SGS>;
         StageParams SP{};
         if (stage) SP = *stage;
-        SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-        kern<<<(unsigned)nblk, S::NT, S::BYTES, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP, g->metric_dev, nbr_tab);
+        constexpr bool PRE = (CONV == SPB_CONV_FWENO) || (DISS == SPB_DISS_FWENO);
+        constexpr int SMEM = PRE ? S::BYTES_PRE : S::BYTES;
+        SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        kern<<<(unsigned)nblk, S::NT, SMEM, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP, g->metric_dev, nbr_tab);
         SPB_LAUNCH_CHECK();
         return 0;
     }
