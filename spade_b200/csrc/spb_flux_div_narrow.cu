@@ -17,6 +17,7 @@
 //    to the neighbour through shared memory, the z flux stays in registers.
 //  * The finished rhs plane is staged in shared memory and written with one TMA tensor store
 //    (hardware clips ragged tiles to the interior), so global stores are fully coalesced.
+#include <cstdlib>
 #include "spb_common.cuh"
 #include "spb_tma.cuh"
 #include "spb_flux.cuh"
@@ -44,7 +45,8 @@ namespace spb
         constexpr int NPUB = 7;                         // rho, cX, Dy.u, Dz.u, cY, Dz.v, Dx.v
         template <int TI_, int TJ_> struct Lay
         {
-            static_assert(TI_*TJ_ == NCOMPUTE && TI_ <= 32 && 2*TJ_ <= 32, "tile = 256 cells, rows within a warp, 2 TJ edge lanes");
+            static_assert((TI_*TJ_) % 32 == 0 && TI_ <= 32 && 2*TJ_ <= 32, "whole compute warps, rows within a warp, 2 TJ edge lanes");
+            static constexpr int NCOMP = TI_*TJ_;                  // compute threads: one cell column each (256, or 512 for the 32 x 16 tile)
             static constexpr int TI = TI_, TJ = TJ_;
             static constexpr int TIp = TI + 2 + 2;                 // halo + 16-byte TMA start alignment slack
             static constexpr int TJp = TJ + 2;
@@ -187,7 +189,7 @@ namespace spb
         // divergence of a cell by J = 1/(m0 m1 m2). Row 0 of a table = m (as info::metric sees it), row 1 = 1/m at the cell
         // centres, row 2 = 1/m at the faces.
         template <int CONV, int VISC, bool UNIF, bool FUSED, int TI, int TJ, bool CURV = false, bool GHOSTW = false>
-        __global__ void __launch_bounds__(GHOSTW ? NTHREADS : NTHREADS_NOGHOST, 2)
+        __global__ void __launch_bounds__(TI*TJ + (GHOSTW ? 64 : 32), (TI*TJ > 256) ? 1 : 2)
         flux_div_narrow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_rhs,
                                const __grid_constant__ CUtensorMap tmap_qout, const __grid_constant__ CUtensorMap tmap_in0,
                                const __grid_constant__ CUtensorMap tmap_in1, double* __restrict__ rhs,
@@ -197,6 +199,7 @@ namespace spb
                                double* __restrict__ qout_raw, const double* __restrict__ met)
         {
             using L = Lay<TI, TJ>;
+            constexpr int NCOMPUTE = L::NCOMP, NCW = NCOMPUTE/32;       // shadow the 256-thread defaults of the namespace
             constexpr int TIp = L::TIp, PLANE_BYTES = L::PLANE_BYTES, PLANE_STRIDE = L::PLANE_STRIDE, PW = L::PW, PSZ = L::PSZ;
             constexpr int STAGE_DOUBLES = L::STAGE_DOUBLES, OFF_P = L::OFF_P, OFF_STAGE_K = L::OFF_STAGE_K, OFF_STAGE_Q = L::OFF_STAGE_Q;
             constexpr int OFF_FX = L::OFF_FX, OFF_FY = L::OFF_FY, OFF_BAR = L::OFF_BAR, OFF_NBR = L::OFF_NBR;
@@ -910,7 +913,8 @@ namespace spb
         for (int d = 0; d < 3; ++d) { G.idx[d] = g->inv_dx_host[3*lb_begin + d]; G.cdx[d] = 0.25*G.idx[d]; }
         Stage S{};
         if (stage) S = *stage;
-        auto go = [&](auto kern, const int nthreads = NTHREADS_NOGHOST) -> int
+        constexpr int NTHREADS = L::NCOMP + 64, NTHREADS_NOGHOST = L::NCOMP + 32;
+        auto go = [&](auto kern, const int nthreads = L::NCOMP + 32) -> int
         {
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -938,6 +942,9 @@ namespace spb
     {
         // blocks of up to 16 cells along i (16^3 blocks: BASELINE configs 1 and 5) would fill half of a 32-wide tile row
         if (g->nx[0] <= 16) return launch_fdiv_narrow_tile<CONV, VISC, 16, 16>(g, q, rhs, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
+        // experiment: 32 x 16 tiles, 16 compute warps, one CTA per SM (less halo traffic, one edge warp per 16 rows)
+        static const bool tile16 = std::getenv("SPB_TILE_32x16") != nullptr;
+        if (tile16 && g->nx[1] % 16 == 0) return launch_fdiv_narrow_tile<CONV, VISC, 32, 16>(g, q, rhs, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
         return launch_fdiv_narrow_tile<CONV, VISC, 32, 8>(g, q, rhs, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
     }
 

@@ -65,8 +65,10 @@ def main():
     from oracle import port
     pool = sp.pool_t.from_torch()
 
-    for nb, n, periodic in (((2, 2, 4), (32, 16, 8), (1, 1, 1)), ((3, 1, 2), (16, 16, 16), (1, 0, 1))):
+    for nb, n, periodic in (((2, 2, 4), (32, 16, 8), (1, 1, 1)), ((3, 1, 2), (16, 16, 16), (1, 0, 1)), ((2, 3, 4), (16, 8, 8), (1, 0, 1))):
         ng = 2
+        if nb[0] * nb[1] * nb[2] < world:
+            continue                      # every rank must own a block (SPADE's partition gives the first nblocks % size ranks one extra)
         blocks = sp.cartesian_blocks_t(nb, [0.0, 2 * np.pi] * 3)
         grid = sp.cartesian_grid_t(n, blocks, sp.identity(), pool)
         lo, nloc = grid.first_block, grid.num_local_blocks

@@ -19,7 +19,7 @@ def free_port():
 
 
 @pytest.mark.parametrize("p2p", ["1", "0"])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_nccl_ranks(world, p2p):
     """p2p = 1: ghost messages through peer memory (CUDA IPC, pack kernel storing into the neighbour's buffer, arrival flags);
     p2p = 0: NCCL send/recv. Same results either way: exchange bit-exact, trajectories to 1e-12 against the oracle."""
