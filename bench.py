@@ -444,10 +444,19 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+    phases = None
+    if getattr(w.ti, "phase_events", None):
+        # diagnosis (SPB_PHASE_EVENTS=1): mean device times of a stage on this rank: start -> boundary kernel done -> packs and flags
+        # issued -> interior kernel done -> messages unpacked
+        pes = w.ti.phase_events[-4 * steps:]
+        mean = lambda f: sum(f(p) for p in pes) / len(pes)
+        phases = {"boundary_done_ms": mean(lambda p: p[0].elapsed_time(p[1])), "packs_done_ms": mean(lambda p: p[0].elapsed_time(p[2])),
+                  "interior_done_ms": mean(lambda p: p[0].elapsed_time(p[3])), "unpacked_ms": mean(lambda p: p[0].elapsed_time(p[4])), "stages": len(pes)}
+        w.ti.phase_events.clear()
     umax_end = sp.transform_reduce(w.q, sp.FN_WAVESPEED, sp.RED_MAX, w.gas)
     if not (umax_end == umax_end) or umax_end > 10 * w.umax0:
         raise SystemExit(f"bench.py: solution diverged (umax {umax_end})")
-    return {"ms": ms, "launches": int(launches), "clocks": clocks, "kern_ms": kern_ms, "kern_bpc": kern_bpc, "n_events": len(ev),
+    return {"ms": ms, "launches": int(launches), "clocks": clocks, "phases": phases, "kern_ms": kern_ms, "kern_bpc": kern_bpc, "n_events": len(ev),
             "value": w.cells_total * STAGES * steps / (ms * 1e-3)}
 
 
@@ -739,6 +748,8 @@ def ours(args):
                 "config": workload_config(args, n), "cell_steps_per_s": m["value"] / STAGES,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": m["launches"],
                 "clocks": m["clocks"], "parity_check": parity}
+        if m.get("phases"):
+            line["phases"] = m["phases"]
         if configs:
             line["configs"] = configs
         if ref_gpu is not None:

@@ -1045,6 +1045,7 @@ class integrator_t:
         self._two_streams = os.environ.get("SPB_TWO_STREAMS", "1") != "0"
         self._side = None
         self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
+        self.phase_events = [] if os.environ.get("SPB_PHASE_EVENTS") else None   # diagnosis: per-phase CUDA events of every stage
         if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
             if lib().spb_flux_div_rk_stage_supported(C.byref(rhs_calc.flux)):
                 self._plan = self._fused_plan(scheme)
@@ -1116,11 +1117,20 @@ class integrator_t:
                 if self._side is None:
                     self._side = torch.cuda.Stream(priority=-1)
                 main, side = torch.cuda.current_stream(), self._side
+                pe = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.phase_events is not None else None
+                if pe:
+                    pe[0].record(main)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     launch(_lib.SPB_PART_BOUNDARY)
+                    if pe:
+                        pe[1].record(side)
                     ex.begin(nxt)
+                    if pe:
+                        pe[2].record(side)
                 launch(_lib.SPB_PART_INTERIOR)
+                if pe:
+                    pe[3].record(main)
                 main.wait_stream(side)
             elif overlap:
                 launch(_lib.SPB_PART_BOUNDARY)
@@ -1144,6 +1154,9 @@ class integrator_t:
             if ex is not None:
                 ex.finish(cur, local=not self._fuse_exchange)
                 self.boundary_cond.after(cur)
+                if self.phase_events is not None and overlap and self._two_streams:
+                    pe[4].record(torch.cuda.current_stream())
+                    self.phase_events.append(pe)
             else:
                 self.boundary_cond(cur, tnext)
         if cur is not d.solution(0):                       # odd number of stages: the result sits in the scratch buffer

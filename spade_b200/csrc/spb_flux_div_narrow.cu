@@ -942,9 +942,9 @@ namespace spb
     {
         // blocks of up to 16 cells along i (16^3 blocks: BASELINE configs 1 and 5) would fill half of a 32-wide tile row
         if (g->nx[0] <= 16) return launch_fdiv_narrow_tile<CONV, VISC, 16, 16>(g, q, rhs, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
-        // experiment: 32 x 16 tiles, 16 compute warps, one CTA per SM (less halo traffic, one edge warp per 16 rows)
-        static const bool tile16 = std::getenv("SPB_TILE_32x16") != nullptr;
-        if (tile16 && g->nx[1] % 16 == 0) return launch_fdiv_narrow_tile<CONV, VISC, 32, 16>(g, q, rhs, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
+        // A 32 x 16 tile (16 compute warps, one CTA per SM: less halo traffic, one edge warp per 16 rows) was measured in round 2 and
+        // is slower: flux_div 0.393 vs 0.372 ms at 256^3, sustained 512^3 step 21.0 vs 20.1 ms (profiles/r02_tile_32x16.log) — with a
+        // single CTA per SM nothing fills the barrier bubbles. The kernel is written on Lay<TI, TJ>::NCOMP, so the variant is one line.
         return launch_fdiv_narrow_tile<CONV, VISC, 32, 8>(g, q, rhs, P, increment, lb_begin, lb_end, stream, q_out, stage, exch);
     }
 

@@ -25,16 +25,25 @@ namespace spb
     __global__ void __launch_bounds__(256) reduce_kernel(const double* __restrict__ q, const RedDims G, int ivar, double gamma, double R,
                                                          double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ result)
     {
-        double acc = red_identity<OP>();
+        // four cells per thread and trip with independent accumulators: 20 loads in flight instead of 5 (the fold order is fixed by the
+        // launch shape, so sums stay deterministic)
+        double a4[4] = {red_identity<OP>(), red_identity<OP>(), red_identity<OP>(), red_identity<OP>()};
         const long long stride = (long long)gridDim.x*blockDim.x;
-        for (long long cell = (long long)blockIdx.x*blockDim.x + threadIdx.x; cell < G.ncells; cell += stride)
+        auto offset = [&](const long long cell)
         {
             const int i = (int)(cell % G.nx[0]); long long t = cell / G.nx[0];
             const int j = (int)(t % G.nx[1]); t /= G.nx[1];
             const int k = (int)(t % G.nx[2]); const long long lb = t / G.nx[2];
-            const long long o = 5ll*((i + G.ng[0]) + (long long)G.np[0]*((j + G.ng[1]) + (long long)G.np[1]*((k + G.ng[2]) + (long long)G.np[2]*lb)));
-            acc = red_op<OP>(acc, red_fn<FN>(q + o, ivar, gamma, R));
+            return 5ll*((i + G.ng[0]) + (long long)G.np[0]*((j + G.ng[1]) + (long long)G.np[1]*((k + G.ng[2]) + (long long)G.np[2]*lb)));
+        };
+        long long cell = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+        for (; cell + 3*stride < G.ncells; cell += 4*stride)
+        {
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) a4[u] = red_op<OP>(a4[u], red_fn<FN>(q + offset(cell + u*stride), ivar, gamma, R));
         }
+        for (; cell < G.ncells; cell += stride) a4[0] = red_op<OP>(a4[0], red_fn<FN>(q + offset(cell), ivar, gamma, R));
+        double acc = red_op<OP>(red_op<OP>(a4[0], a4[1]), red_op<OP>(a4[2], a4[3]));
         #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc = red_op<OP>(acc, __shfl_down_sync(0xffffffffu, acc, s));
         __shared__ double warp_part[8];
