@@ -453,6 +453,11 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
         phases = {"boundary_done_ms": mean(lambda p: p[0].elapsed_time(p[1])), "packs_done_ms": mean(lambda p: p[0].elapsed_time(p[2])),
                   "interior_done_ms": mean(lambda p: p[0].elapsed_time(p[3])), "unpacked_ms": mean(lambda p: p[0].elapsed_time(p[4])), "stages": len(pes)}
         w.ti.phase_events.clear()
+        phases["stage_kernel_ms"] = sum(a.elapsed_time(b) for a, b, _ in ev) / max(1, len(ev))
+        if world > 1:
+            allp = [None] * world
+            dist.all_gather_object(allp, phases)
+            phases = {"per_rank": allp}
     umax_end = sp.transform_reduce(w.q, sp.FN_WAVESPEED, sp.RED_MAX, w.gas)
     if not (umax_end == umax_end) or umax_end > 10 * w.umax0:
         raise SystemExit(f"bench.py: solution diverged (umax {umax_end})")

@@ -723,6 +723,14 @@ class arr_exchange_t:
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pool.group)
         if int(flag.item()) == 0:
+            # some rank could not allocate, export or map: every rank takes the NCCL path; give back what was set up here
+            for bufs, f in remote.values():
+                for b in list(bufs) + [f]:
+                    lib().spb_ipc_close(b)
+            dist.barrier(group=self.pool.group)             # no peer still maps the buffers freed below
+            for bufs, f in own.values():
+                for b in list(bufs) + [f]:
+                    lib().spb_dev_free(b)
             return False
         self._own, self._remote, self._seq, self._p2p = own, remote, 0, True
         return True
@@ -1043,6 +1051,7 @@ class integrator_t:
         self._scratch = None
         self._fuse_exchange = bool(fuse_exchange)
         self._two_streams = os.environ.get("SPB_TWO_STREAMS", "1") != "0"
+        self._block_runs = os.environ.get("SPB_BLOCK_RUNS", "0") == "1"
         self._side = None
         self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
         self.phase_events = [] if os.environ.get("SPB_PHASE_EVENTS") else None   # diagnosis: per-phase CUDA events of every stage
@@ -1096,7 +1105,16 @@ class integrator_t:
             ex = self.boundary_cond.handle if isinstance(self.boundary_cond, exchange_bc_t) else None
             overlap = ex is not None and ex.pool.size() > 1
 
+            def launch_runs(part):
+                # development A/B (SPB_BLOCK_RUNS=1): the round-1 form, one launch per contiguous run of blocks
+                first, second = ex.boundary_block_runs()
+                for b0, b1 in (first if part == _lib.SPB_PART_BOUNDARY else second):
+                    check(lib().spb_flux_div_rk_stage_exchange(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd),
+                                                               ex._h if self._fuse_exchange else None, b0, b1, _stream_ptr()))
+
             def launch(part):
+                if self._block_runs and part != _lib.SPB_PART_ALL:
+                    return launch_runs(part)
                 # one launch per part of the local blocks (spb_flux_div_rk_stage_part: boundary / interior / all), whatever their
                 # order in memory; with a recognised exchange handle the kernel also fills the same-rank injection ghosts of q_out
                 exh = ex._h if ex is not None else None

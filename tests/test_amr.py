@@ -84,6 +84,36 @@ def test_plan_from_tables_message_layout(gold, case, nranks):
         lib().spb_exchange_destroy(h)
 
 
+@pytest.mark.parametrize("pre,nranks", [("p", 2), ("p", 4), ("b", 4), ("b", 8)])
+def test_boundary_blocks_include_the_donors_of_off_rank_interpolation_sends(pre, nranks):
+    """Host side of the overlapped schedule (no GPU): spb_exchange_boundary_blocks must mark the source block of EVERY off-rank
+    send transaction, injection and patch_fill_t alike — a donor block that only feeds an off-rank interpolation would otherwise
+    be advanced while its message is being packed. Tables: the reference's, for the parity grid (p) and the bench
+    grid (b) of config 5; p on 2 ranks and b on 4 / 8 ranks hold such interpolation-only donors (15 / 152 / 168 blocks)."""
+    from spade_b200._lib import lib, check, int3
+    fix = np.load(os.path.join(HERE, "golden", "config5_amr.npz"))
+    n = tuple(int(x) for x in fix[f"{pre}_cells"])
+    nblocks = len(fix[f"{pre}_boxes"])
+    i64 = C.POINTER(C.c_int64)
+    seen_interp_only = False
+    for rank in range(nranks):
+        t = {k: np.ascontiguousarray(fix[f"{pre}_{k}_{nranks}_{rank}"], dtype=np.int64) for k in ("send", "recv", "isend", "irecv")}
+        per, extra = divmod(nblocks, nranks)
+        nloc = per + (1 if rank < extra else 0)
+        h = C.c_void_p()
+        check(lib().spb_exchange_create_from_tables(C.byref(h), int3(n), int3((NG,) * 3), rank, nranks, t["send"].ctypes.data_as(i64),
+                                                    len(t["send"]), t["recv"].ctypes.data_as(i64), len(t["recv"])))
+        check(lib().spb_exchange_add_interp(h, t["isend"].ctypes.data_as(i64), len(t["isend"]), t["irecv"].ctypes.data_as(i64), len(t["irecv"])))
+        mask = np.zeros(max(nloc, 1), dtype=np.uint8)
+        check(lib().spb_exchange_boundary_blocks(h, nloc, mask.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        inj = {int(r[8]) for r in t["send"] if r[2] != rank}
+        itp = {int(r[8]) for r in t["isend"] if r[2] != rank}
+        assert set(np.flatnonzero(mask[:nloc])) == inj | itp
+        seen_interp_only = seen_interp_only or bool(itp - inj)
+        lib().spb_exchange_destroy(h)
+    assert seen_interp_only == ((pre, nranks) != ("p", 4))
+
+
 # ---------------------------------------------------------------- GPU
 def _rank_slices(nblocks, nranks):
     from oracle import port
