@@ -424,6 +424,8 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
     launches0 = sp.launch_count()
     timing["events"] = ev = []
     timing["on"] = True
+    if os.environ.get("SPB_PHASE_EVENTS"):
+        w.handle.finish_trace = []
     if w.fused:
         w.ti.stage_events = ev
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -454,6 +456,10 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
                   "interior_done_ms": mean(lambda p: p[0].elapsed_time(p[3])), "unpacked_ms": mean(lambda p: p[0].elapsed_time(p[4])), "stages": len(pes)}
         w.ti.phase_events.clear()
         phases["stage_kernel_ms"] = sum(a.elapsed_time(b) for a, b, _ in ev) / max(1, len(ev))
+        tr = getattr(w.handle, "finish_trace", None)
+        if tr:
+            tr = tr[-4 * steps:]
+            phases["finish_ms"] = [round(sum(t[k].elapsed_time(t[k + 1]) for t in tr) / len(tr), 4) for k in range(len(tr[0]) - 1)]   # wait, unpack per peer
         if world > 1:
             allp = [None] * world
             dist.all_gather_object(allp, phases)

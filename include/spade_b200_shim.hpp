@@ -235,6 +235,7 @@ namespace spade::b200
     struct stream_pair_t
     {
         cudaStream_t side = nullptr; cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+        cudaEvent_t ev_b[2] = {nullptr, nullptr}, ev_i[2] = {nullptr, nullptr};      // boundary / interior kernel of stage s done (s & 1)
         void fork() { cudaEventRecord(ev_main, nullptr); cudaStreamWaitEvent(side, ev_main, 0); }      // side continues after main
         void join() { cudaEventRecord(ev_side, side);    cudaStreamWaitEvent(nullptr, ev_side, 0); }   // main continues after side
     };
@@ -247,7 +248,9 @@ namespace spade::b200
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
             if (cudaStreamCreateWithPriority(&sp.side, cudaStreamNonBlocking, hi) != cudaSuccess
                 || cudaEventCreateWithFlags(&sp.ev_main, cudaEventDisableTiming) != cudaSuccess
-                || cudaEventCreateWithFlags(&sp.ev_side, cudaEventDisableTiming) != cudaSuccess)
+                || cudaEventCreateWithFlags(&sp.ev_side, cudaEventDisableTiming) != cudaSuccess
+                || cudaEventCreateWithFlags(&sp.ev_b[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&sp.ev_b[1], cudaEventDisableTiming) != cudaSuccess
+                || cudaEventCreateWithFlags(&sp.ev_i[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&sp.ev_i[1], cudaEventDisableTiming) != cudaSuccess)
                 throw except::sp_exception("spade_b200: could not create the side stream of the overlapped schedule");
         }
         return sp;
@@ -879,6 +882,23 @@ namespace spade::time_integration
             overlap = boundary.group->size() > 1;
         }
         thread_local bool fuse_refused = false;
+        // Deferred unpack (several ranks, no AMR interpolation, no wall fill, every peer writable directly): the off-rank ghost
+        // cells of stage s are only read by the rank-boundary blocks of stage s+1, so their flag wait + unpack moves to the
+        // side stream in front of that boundary kernel and the rank-interior kernel of stage s+1 starts without waiting for any
+        // message — a neighbour GPU that runs late stalls the short chain unpack -> boundary kernel -> pack, which has the
+        // whole interior kernel to catch up. Same schedule as api.py::integrator_t._advance_fused.
+        bool defer = false;
+        if constexpr (known_bc)
+        {
+            if (overlap)
+            {
+                auto& h = *boundary.handle;
+                if (!h.wired) h.wire(*boundary.group);
+                defer = h.all_direct && !boundary.has_fill && !fuse_refused
+                        && spb_exchange_num_interp_send(h.plan) == 0 && spb_exchange_num_interp_recv(h.plan) == 0;
+            }
+        }
+        double* pending = nullptr;                   // buffer whose off-rank ghost cells still wait for their messages
         int cur = 0;
         for (int i = 0; i < n; ++i)
         {
@@ -900,9 +920,37 @@ namespace spade::time_integration
                 }
                 b200::check(spb_flux_div_rk_stage_part(gh, bufs[cur], bufs[1 - cur], &fd, &sd, fuse, 0, part, stream), "spb_flux_div_rk_stage_part");
             };
+            bool deferred_stage = false;
             if constexpr (known_bc)
             {
-                if (overlap)
+                if (overlap && defer)
+                {
+                    auto& sp = b200::streams();
+                    auto& h = *boundary.handle;
+                    if (i == 0) sp.fork();                                        // everything enqueued before this step
+                    if (pending) { h.finish(pending, *boundary.group, sp.side); pending = nullptr; }
+                    if (i > 0) cudaStreamWaitEvent(sp.side, sp.ev_i[(i - 1) & 1], 0);   // same-rank ghosts of the boundary blocks written by the previous interior kernel
+                    launch(SPB_PART_BOUNDARY, sp.side);
+                    if (ghosts_done)
+                    {
+                        cudaEventRecord(sp.ev_b[i & 1], sp.side);
+                        h.begin(bufs[1 - cur], *boundary.group, sp.side);
+                        if (i > 0) cudaStreamWaitEvent(nullptr, sp.ev_b[(i - 1) & 1], 0);   // ... and of the interior blocks by the previous boundary kernel
+                        launch(SPB_PART_INTERIOR, nullptr);
+                        cudaEventRecord(sp.ev_i[i & 1], nullptr);
+                        pending = bufs[1 - cur];
+                        deferred_stage = true;
+                    }
+                    else
+                    {
+                        // the plan refused the ghost fusion at the first launch: finish this stage the undeferred way
+                        sp.join();
+                        launch(SPB_PART_INTERIOR, nullptr);
+                        h.begin(bufs[1 - cur], *boundary.group, nullptr);
+                        defer = false;
+                    }
+                }
+                else if (overlap)
                 {
                     auto& sp = b200::streams();
                     auto& h = *boundary.handle;
@@ -919,12 +967,26 @@ namespace spade::time_integration
             axis.time() = t_start + tfrac[i]*dt;
             if constexpr (known_bc)
             {
-                // the callback's work on the raw stage buffer (the result may sit in the scratch buffer): same-rank ghosts unless the
-                // kernel wrote them, the ghost cells fed by other ranks, then the wall fills of a channel solver
-                if (!ghosts_done) b200::check(spb_exchange_local(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local");
-                else b200::check(spb_exchange_local_interp(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local_interp");   // AMR: what the kernel left
-                if (overlap) boundary.handle->finish(bufs[cur], *boundary.group, nullptr);
-                boundary.fill(q, bufs[cur]);
+                if (deferred_stage)
+                {
+                    if (i + 1 == n)
+                    {
+                        // end of the step: the last messages are unpacked and the main stream sees the whole state
+                        auto& sp = b200::streams();
+                        boundary.handle->finish(pending, *boundary.group, sp.side);
+                        pending = nullptr;
+                        sp.join();
+                    }
+                }
+                else
+                {
+                    // the callback's work on the raw stage buffer (the result may sit in the scratch buffer): same-rank ghosts unless the
+                    // kernel wrote them, the ghost cells fed by other ranks, then the wall fills of a channel solver
+                    if (!ghosts_done) b200::check(spb_exchange_local(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local");
+                    else b200::check(spb_exchange_local_interp(boundary.handle->plan, bufs[cur], nullptr), "spb_exchange_local_interp");   // AMR: what the kernel left
+                    if (overlap) boundary.handle->finish(bufs[cur], *boundary.group, nullptr);
+                    boundary.fill(q, bufs[cur]);
+                }
             }
             else
             {

@@ -620,6 +620,9 @@ class arr_exchange_t:
         check(lib().spb_exchange_tables(self._h, send.ctypes.data_as(i64), recv.ctypes.data_as(i64), offs.ctypes.data_as(i64)))
         return send, recv, offs
 
+    def num_interp(self):
+        return int(lib().spb_exchange_num_interp_send(self._h)) + int(lib().spb_exchange_num_interp_recv(self._h))
+
     def local_injection_cells(self):
         """cells of the same-rank injection transactions (the ghost cells the fused stage kernel writes itself)"""
         if getattr(self, "_linj", None) is None:
@@ -766,9 +769,19 @@ class arr_exchange_t:
             check(lib().spb_exchange_local_interp(self._h, _dptr(array.data), st))    # AMR: what the stage kernel left (no-op otherwise)
         if self.pool.size() > 1 and self._p2p:
             par = self._seq & 1
+            trace = getattr(self, "finish_trace", None)        # diagnosis: CUDA events around every wait and unpack
+            if trace is not None:
+                evs = [torch.cuda.Event(enable_timing=True)]
+                evs[0].record()
             for p, (bufs, flags) in self._own.items():
                 check(lib().spb_flag_wait(C.c_void_p(flags.value + 8 * par), self._seq, st))
+                if trace is not None:
+                    evs.append(torch.cuda.Event(enable_timing=True)); evs[-1].record()
                 check(lib().spb_exchange_unpack(self._h, _dptr(array.data), p, bufs[par], st))
+                if trace is not None:
+                    evs.append(torch.cuda.Event(enable_timing=True)); evs[-1].record()
+            if trace is not None:
+                trace.append(evs)
             return
         for r in self._reqs:
             r.wait()
@@ -1052,6 +1065,8 @@ class integrator_t:
         self._fuse_exchange = bool(fuse_exchange)
         self._two_streams = os.environ.get("SPB_TWO_STREAMS", "1") != "0"
         self._block_runs = os.environ.get("SPB_BLOCK_RUNS", "0") == "1"
+        self._defer = os.environ.get("SPB_DEFER_UNPACK", "1") != "0"
+        self._pending = self._ev_b = self._ev_i = None
         self._side = None
         self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
         self.phase_events = [] if os.environ.get("SPB_PHASE_EVENTS") else None   # diagnosis: per-phase CUDA events of every stage
@@ -1125,10 +1140,61 @@ class integrator_t:
                     self._fuse_exchange = False                  # plan not canonical: separate same-rank copy from now on
                 check(lib().spb_flux_div_rk_stage_part(cur.h, _dptr(cur.data), _dptr(nxt.data), C.byref(f), C.byref(sd), exh, 0, part, _stream_ptr()))
 
+            # Deferred unpack (periodic multi-rank runs without AMR interpolation or wall fills): the off-rank ghost cells of stage s
+            # are only read by the rank-boundary blocks of stage s+1, so their wait + unpack moves to the side stream in front of
+            # that boundary kernel, and the rank-interior kernel of stage s+1 starts on the main stream without waiting for any
+            # message: a neighbour that runs late (eight power-capped GPUs never run at the same pace) or a slow link stalls the
+            # short side-stream chain unpack -> boundary kernel -> pack, which has the whole interior kernel to catch up.
+            defer = (overlap and self._two_streams and self._defer and self._fuse_exchange and not self._block_runs
+                     and self.boundary_cond.boundaries is None and ex.num_interp() == 0)
             if self.stage_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            if overlap and self._two_streams:
+            if defer:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(priority=-1)
+                main, side = torch.cuda.current_stream(), self._side
+                if i == 0:
+                    side.wait_stream(main)                      # everything enqueued before this step
+                    self._ev_b = self._ev_i = None
+                pe = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.phase_events is not None else None
+                if pe:
+                    pe[0].record(main)
+                with torch.cuda.stream(side):
+                    if self._pending is not None:
+                        ex.finish(self._pending, local=False)   # messages of the previous stage -> off-rank ghost cells of `cur`
+                        self._pending = None
+                    if pe:
+                        pe[4].record(side)                      # (deferred schedule: the unpack of the PREVIOUS stage's messages)
+                    if self._ev_i is not None:
+                        side.wait_event(self._ev_i)             # the previous interior kernel wrote same-rank ghosts of the boundary blocks
+                    launch(_lib.SPB_PART_BOUNDARY)
+                    ev_b = torch.cuda.Event()
+                    ev_b.record(side)
+                    if pe:
+                        pe[1].record(side)
+                    if self._fuse_exchange:
+                        ex.begin(nxt)
+                    if pe:
+                        pe[2].record(side)
+                if self._ev_b is not None:
+                    main.wait_event(self._ev_b)                 # the previous boundary kernel wrote same-rank ghosts of the interior blocks
+                if self._fuse_exchange:
+                    launch(_lib.SPB_PART_INTERIOR)
+                    ev_i = torch.cuda.Event()
+                    ev_i.record(main)
+                    if pe:
+                        pe[3].record(main)
+                        self.phase_events.append(pe)
+                    self._ev_b, self._ev_i, self._pending = ev_b, ev_i, nxt
+                else:
+                    # the plan refused the ghost fusion at the first launch: finish this stage the undeferred way
+                    main.wait_stream(side)
+                    launch(_lib.SPB_PART_INTERIOR)
+                    ex.begin(nxt)
+                    self._ev_b = self._ev_i = None
+                    defer = False
+            elif overlap and self._two_streams:
                 # rank-boundary blocks on a high-priority side stream, their messages packed and posted from it; the rank-interior
                 # blocks run on the main stream AT THE SAME TIME (both read q_in only and write disjoint cells), so the small
                 # boundary launch leaves no partial wave behind and the messages fly under the interior kernel
@@ -1169,7 +1235,15 @@ class integrator_t:
             if i + 1 == s.rows():
                 ax.t += dt
                 tnext = ax.t
-            if ex is not None:
+            if defer:
+                if i + 1 == s.rows():
+                    # end of the step: the last messages are unpacked and the main stream sees the whole state
+                    main, side = torch.cuda.current_stream(), self._side
+                    with torch.cuda.stream(side):
+                        ex.finish(self._pending, local=False)
+                        self._pending = None
+                    main.wait_stream(side)
+            elif ex is not None:
                 ex.finish(cur, local=not self._fuse_exchange)
                 self.boundary_cond.after(cur)
                 if self.phase_events is not None and overlap and self._two_streams:
