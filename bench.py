@@ -431,8 +431,10 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
+    host_t0 = time.perf_counter()
     for _ in range(steps):
         w.ti.advance()
+    host_loop_ms = 1e3 * (time.perf_counter() - host_t0)      # diagnosis: far below the device time if the host runs ahead
     t1.record()
     barrier()
     timing["on"] = False
@@ -456,6 +458,7 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
                   "interior_done_ms": mean(lambda p: p[0].elapsed_time(p[3])), "unpacked_ms": mean(lambda p: p[0].elapsed_time(p[4])), "stages": len(pes)}
         w.ti.phase_events.clear()
         phases["stage_kernel_ms"] = sum(a.elapsed_time(b) for a, b, _ in ev) / max(1, len(ev))
+        phases["host_loop_ms_per_step"] = host_loop_ms / steps
         tr = getattr(w.handle, "finish_trace", None)
         if tr:
             tr = tr[-4 * steps:]
