@@ -39,32 +39,29 @@ namespace spb
         double gm1, inv_gm1, inv_R;
     };
 
-    // 1/a with a MUFU.RCP64H seed and two Newton steps: relative error ~1e-16, no slow-path call (div.rn.f64 is ~3x the
-    // instructions and keeps a subroutine alive that costs registers). Arguments here are densities, sound speeds and
-    // smoothness sums: positive and far from the denormal range.
+    // 1/a from a MUFU.RCP64H seed (the upper 20 mantissa bits of a: relative error e0 <~ 1e-6) with ONE third-order step
+    // x (1 + e + e^2), e = 1 - a x: the error becomes e0^3 ~ 1e-18, below the rounding of the last fma (round 1 / 2 used two
+    // Newton steps, one fma more). No slow-path call (div.rn.f64 is ~3x the instructions and keeps a subroutine alive that costs
+    // registers). Arguments here are densities, sound speeds and smoothness sums: positive and far from the denormal range.
     __device__ __forceinline__ double rcp_nr(const double a)
     {
         double x;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-        double e = fma(-a, x, 1.0);
-        x = fma(x, e, x);
-        e = fma(-a, x, 1.0);
-        x = fma(x, e, x);
-        return x;
+        const double e = fma(-a, x, 1.0);
+        return fma(x, fma(e, e, e), x);
     }
 
-    // sqrt(a) for a > 0 from a MUFU.RSQ64H seed: two Newton steps on 1/sqrt(a), then one correction of the root
-    // (relative error ~1e-16, no slow-path call).
+    // sqrt(a) for a > 0 from a MUFU.RSQ64H seed: one Newton step on y = 1/sqrt(a) (error ~1e-12), then the correction
+    // s + (y/2)(a - s^2) of the root s = a y, which squares the error again and only needs y to 1e-12 (relative error of the
+    // result ~1e-16, no slow-path call).
     __device__ __forceinline__ double sqrt_nr(const double a)
     {
         double y;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
         const double h = 0.5*a;
-        double t = fma(-h*y, y, 0.5);
+        const double t = fma(-h*y, y, 0.5);
         y = fma(y, t, y);
-        t = fma(-h*y, y, 0.5);
-        y = fma(y, t, y);
-        double s = a*y;
+        const double s = a*y;
         const double r = fma(-s, s, a);
         return fma(0.5*y, r, s);
     }
@@ -93,10 +90,9 @@ namespace spb
 
     // ---- convective::totani_lr -------------------------------------------------------------
     template <int D>
-    __device__ __forceinline__ void flux_totani(const FluxParams& P, const double (&qL)[5], const double (&qR)[5], double (&F)[5])
+    __device__ __forceinline__ void flux_totani(const FluxParams& P, const double (&qL)[5], const double (&qR)[5], double (&F)[5],
+                                                const double rhoL, const double rhoR)
     {
-        const double rhoL = qL[0]*rcp_nr(P.R*qL[1]);
-        const double rhoR = qR[0]*rcp_nr(P.R*qR[1]);
         const double unL = qL[2+D], unR = qR[2+D];
         const double C = (rhoL + rhoR)*(unL + unR);                 // 4c
         double S = P.cv*(qL[1] + qR[1]);                            // e_L + e_R
@@ -182,27 +178,23 @@ namespace spb
     }
 
     // ---- convective::fweno_t ---------------------------------------------------------------------
+    // Two 2-cell candidate reconstructions per side with the weights a1/(2a0 + a1) (convective.h:380-400). In the reference's
+    // form r1 + w0 (r0 - r1) + r2 + w3 (r3 - r2) the candidates satisfy r0 - r1 = (b1 - b0)/2, r3 - r2 = (b3 - b2)/2 with the
+    // differences b the smoothness indicators are built from, and r1 + r2 = f1 + f2: 34 fp64 instructions instead of 47.
     __device__ __forceinline__ double fweno_apply(const double (&f)[4], const double (&d)[4], const int linear)
     {
         const double f0u = f[0] + d[0];
         const double f1u = f[1] + d[1], f1d = f[1] - d[1];
         const double f2u = f[2] + d[2], f2d = f[2] - d[2];
         const double f3d = f[3] - d[3];
-        const double r0 = fma(1.5, f1u, -0.5*f0u);
-        const double r1 = 0.5*(f1u + f2u);
-        const double r2 = 0.5*(f1d + f2d);
-        const double r3 = fma(1.5, f2d, -0.5*f3d);
+        const double b0 = f0u - f1u, b1 = f1u - f2u, b2 = f1d - f2d, b3 = f2d - f3d;
         const double eps = 1e-16;
-        double a0 = f0u - f1u, a1 = f1u - f2u, a2 = f1d - f2d, a3 = f2d - f3d;
-        a0 = fma(a0, a0, eps); a0 *= a0;
-        a1 = fma(a1, a1, eps); a1 *= a1;
-        a2 = fma(a2, a2, eps); a2 *= a2;
-        a3 = fma(a3, a3, eps); a3 *= a3;
-        double w0 = a1*rcp_nr(a0 + a0 + a1);
-        double w3 = a2*rcp_nr(a3 + a3 + a2);
+        double a0 = fma(b0, b0, eps), a1 = fma(b1, b1, eps), a2 = fma(b2, b2, eps), a3 = fma(b3, b3, eps);
+        a0 *= a0; a1 *= a1; a2 *= a2; a3 *= a3;
+        double w0 = a1*rcp_nr(fma(2.0, a0, a1));
+        double w3 = a2*rcp_nr(fma(2.0, a3, a2));
         if (linear) { w0 = 1.0/3.0; w3 = 1.0/3.0; }      // disable_smooth: the linear weights (two selects, no control flow)
-        // w0 r0 + (1-w0) r1 + (1-w3) r2 + w3 r3
-        return fma(w0, r0 - r1, r1) + fma(w3, r3 - r2, r2);
+        return fma(0.5, fma(w3, b3 - b2, w0*(b1 - b0)), f[1] + f[2]);
     }
 
     // The direction-independent per-cell part of fweno_t (convective.h:355-378): hr = rho/2 and hs = (rho/2)(|u| + c). One
@@ -350,14 +342,19 @@ namespace spb
         #pragma unroll
         for (int v = 0; v < 5; ++v) F[v] = 0.0;
 
-        if (CONV == SPB_CONV_TOTANI)     flux_totani<D>(P, qL, qR, F);
-        if (CONV == SPB_CONV_CENT_KEEP4) flux_cent_keep4<D>(P, qLL, qL, qR, qRR, F);
         double hrv[4] = {0.0, 0.0, 0.0, 0.0}, hsv[4] = {0.0, 0.0, 0.0, 0.0};
         if (PRE)
         {
             #pragma unroll
             for (int i = 0; i < 4; ++i) { hrv[i] = hr4[i]; hsv[i] = hs4[i]; }
         }
+        if (CONV == SPB_CONV_TOTANI)
+        {
+            // PRE: the prepared cells carry rho/2 = (p rcp(R T))/2, so 2 hr is the density bit for bit
+            if (PRE) flux_totani<D>(P, qL, qR, F, 2.0*hrv[1], 2.0*hrv[2]);
+            else     flux_totani<D>(P, qL, qR, F, qL[0]*rcp_nr(P.R*qL[1]), qR[0]*rcp_nr(P.R*qR[1]));
+        }
+        if (CONV == SPB_CONV_CENT_KEEP4) flux_cent_keep4<D>(P, qLL, qL, qR, qRR, F);
         if (CONV == SPB_CONV_FWENO)
         {
             if (PRE) flux_fweno_pre<D, CURV>(P, qLL, qL, qR, qRR, hrv, hsv, F, area);

@@ -92,18 +92,11 @@ namespace spb
 
         using Stage = spb::StageParams;
 
-        // rho = p/(R T) (reference convective.h:70, fluid_state.h:105) with a Newton-refined hardware reciprocal:
-        // MUFU.RCP64H seed (>= 20 bits) + 2 iterations -> relative error ~1e-16, no slow-path branch.
+        // rho = p/(R T) (reference convective.h:70, fluid_state.h:105) with the hardware reciprocal seed (MUFU.RCP64H, >= 20 bits)
+        // and one third-order step (spb_flux.cuh: rcp_nr) -> relative error ~1e-16, no slow-path branch.
         __device__ __forceinline__ double density(const double R, const double p, const double T)
         {
-            const double a = R*T;
-            double x;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-            double e = fma(-a, x, 1.0);
-            x = fma(x, e, x);
-            e = fma(-a, x, 1.0);
-            x = fma(x, e, x);
-            return p*x;
+            return p*rcp_nr(R*T);
         }
 
         template <int CONV, int VISC, int D>
@@ -148,16 +141,7 @@ namespace spb
             }
         }
 
-        __device__ __forceinline__ double fast_rcp(const double a)
-        {
-            double x;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-            double e = fma(-a, x, 1.0);
-            x = fma(x, e, x);
-            e = fma(-a, x, 1.0);
-            x = fma(x, e, x);
-            return x;
-        }
+        __device__ __forceinline__ double fast_rcp(const double a) { return rcp_nr(a); }
 
         __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
         {
