@@ -459,6 +459,12 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
         w.ti.phase_events.clear()
         phases["stage_kernel_ms"] = sum(a.elapsed_time(b) for a, b, _ in ev) / max(1, len(ev))
         phases["host_loop_ms_per_step"] = host_loop_ms / steps
+        je = getattr(w.ti, "join_events", None)
+        if je:
+            je = je[-steps:]
+            phases["join_ms"] = sum(a.elapsed_time(b) for a, b in je) / len(je)                 # end-of-step join (deferred schedule)
+            phases["step_ms"] = sum(je[i][1].elapsed_time(je[i + 1][1]) for i in range(len(je) - 1)) / max(1, len(je) - 1)
+            w.ti.join_events.clear()
         tr = getattr(w.handle, "finish_trace", None)
         if tr:
             tr = tr[-4 * steps:]

@@ -1070,6 +1070,7 @@ class integrator_t:
         self._side = None
         self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
         self.phase_events = [] if os.environ.get("SPB_PHASE_EVENTS") else None   # diagnosis: per-phase CUDA events of every stage
+        self.join_events = []
         if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
             if lib().spb_flux_div_rk_stage_supported(C.byref(rhs_calc.flux)):
                 self._plan = self._fused_plan(scheme)
@@ -1242,7 +1243,15 @@ class integrator_t:
                     with torch.cuda.stream(side):
                         ex.finish(self._pending, local=False)
                         self._pending = None
-                    main.wait_stream(side)
+                    if self.phase_events is not None:
+                        # diagnosis: the join of a step (last interior kernel done -> last messages unpacked on the side stream)
+                        ej = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                        ej[0].record(main)
+                        main.wait_stream(side)
+                        ej[1].record(main)
+                        self.join_events.append(ej)
+                    else:
+                        main.wait_stream(side)
             elif ex is not None:
                 ex.finish(cur, local=not self._fuse_exchange)
                 self.boundary_cond.after(cur)

@@ -173,32 +173,41 @@ namespace spb
         // 2-cell halo ring (176 cells) evaluated by the first 176 threads
         double zh[4] = {0.0, 0.0, 0.0, 0.0}, zs[4] = {0.0, 0.0, 0.0, 0.0};
         const int pown = (jl + 2)*S::PW + (il + 2);
+        // The halo cells belong to the threads of warps 2 .. 7 (warps 0 and 1 carry the faces on the tile's upper edge, a fourth
+        // face pass per step: everything else that can be taken off them is), and a halo cell of plane k+1 is evaluated BEFORE the
+        // first barrier of step k, while its warp would otherwise wait for warps 0 and 1; only the two stores follow the barrier.
         int phalo = -1, chalo = 0;                   // published index and ring offset of this thread's halo cell
-        if (PRE && tid < S::PUB_CELLS - TI*TJ)
+        constexpr int HALO_T0 = (S::NT - 64 >= S::PUB_CELLS - TI*TJ) ? 64 : 0;
+        if (PRE && tid >= HALO_T0 && tid - HALO_T0 < S::PUB_CELLS - TI*TJ)
         {
+            const int ht = tid - HALO_T0;
             int pi, pj;
-            if (tid < 4*S::PW) { pj = tid / S::PW; pi = tid - pj*S::PW; if (pj >= 2) pj += TJ; }
-            else { const int r = tid - 4*S::PW; pj = 2 + r/4; const int c = r & 3; pi = (c < 2) ? c : TI + c; }
+            if (ht < 4*S::PW) { pj = ht / S::PW; pi = ht - pj*S::PW; if (pj >= 2) pj += TJ; }
+            else { const int r = ht - 4*S::PW; pj = 2 + r/4; const int c = r & 3; pi = (c < 2) ? c : TI + c; }
             phalo = pj*S::PW + pi;
             chalo = (pj*S::TIp + (pi + ash))*5;      // H = 2: tile-local cell (pi - 2, pj - 2) sits at box column pi - 2 + H + ash
         }
-        auto publish = [&](const int dk, const double hr_own, const double hs_own)
+        double hh = 0.0, hsh = 0.0;                  // weno_cell of this thread's halo cell, on its way to the published plane
+        auto halo_eval = [&](const int dk)
         {
-            pubh[pown] = hr_own; pubs[pown] = hs_own;
             if (phalo >= 0)
             {
                 const double* c = ring + acc.pl[dk + H] + chalo;
-                double hr, hs;
-                weno_cell(P, c[0], c[1], c[2], c[3], c[4], hr, hs);
-                pubh[phalo] = hr; pubs[phalo] = hs;
+                weno_cell(P, c[0], c[1], c[2], c[3], c[4], hh, hsh);
             }
+        };
+        auto publish = [&](const double hr_own, const double hs_own)
+        {
+            pubh[pown] = hr_own; pubs[pown] = hs_own;
+            if (phalo >= 0) { pubh[phalo] = hh; pubs[phalo] = hsh; }
         };
         if (PRE)
         {
             #pragma unroll
             for (int d = 0; d < 3; ++d)
                 weno_cell(P, acc(0, 0, 0, d - 2), acc(1, 0, 0, d - 2), acc(2, 0, 0, d - 2), acc(3, 0, 0, d - 2), acc(4, 0, 0, d - 2), zh[d], zs[d]);
-            publish(0, zh[2], zs[2]);
+            halo_eval(0);
+            publish(zh[2], zs[2]);
             __syncthreads();
         }
         double rprev[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // partial rhs of cell k-1 (x, y and lower-z parts)
@@ -217,7 +226,19 @@ namespace spb
             }
             acc.pl[AH] = slot_next*S::PLANE_STRIDE;
 
-            double Fz[5];
+            if (FUSED && active && k < nz)
+            {
+                // the stage inputs of cell k are read at the top of the next step (40 bytes per thread, AoS): start them towards L1 now
+                #pragma unroll
+                for (int a = 0; a < 2; ++a)
+                    if (a < ST.nin)
+                    {
+                        const double* pin = ST.in[a] + col0 + (long long)k*kstride;
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(pin));
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(pin + 4));
+                    }
+            }
+            double Fz[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             double jac_prev = 1.0;                   // Jacobian of cell k-1
             if (PRE && k + AH < nplanes)             // the cell entering the z-stencil (plane k+1)
                 weno_cell(P, acc(0, 0, 0, 1), acc(1, 0, 0, 1), acc(2, 0, 0, 1), acc(3, 0, 0, 1), acc(4, 0, 0, 1), zh[3], zs[3]);
@@ -323,7 +344,11 @@ namespace spb
                 }
             }
 
-            double dFxy[5] = {0.0, 0.0, 0.0, 0.0, 0.0};          // PRE: F_x(own) - F_x(il+1) for all but the tile's last column
+            // PRE: the z part of the divergence of cell k, then the x part as soon as the x pass is done (F_x(own) - F_x(il+1) by warp
+            // shuffle for all but the tile's last column), so that only five accumulators stay live through the y and edge passes
+            double rz[5];
+            #pragma unroll
+            for (int v = 0; v < 5; ++v) rz[v] = Fz[v]*invdx[2];
             if (k < nz)
             {
                 double Fxo[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -348,6 +373,22 @@ namespace spb
                         #pragma unroll
                         for (int v = 0; v < 5; ++v) Fx[(jl*(TI + 1) + il)*5 + v] = F[v];
                     }
+                }
+                if (PRE)
+                {
+                    // the x-flux of the right neighbour comes by shuffle (all 32 lanes take part; a warp is one tile row); the last
+                    // column subtracts the edge flux after the barrier
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v)
+                    {
+                        const double up = __shfl_down_sync(0xffffffffu, Fxo[v], 1);
+                        rz[v] = fma((il == ni_t - 1) ? Fxo[v] : Fxo[v] - up, invdx[0], rz[v]);
+                    }
+                }
+                if (active)
+                {
+                    double F[5], gs[3], area;
+                    double h4[4], s4[4];
                     if (PRE)
                     {
                         #pragma unroll
@@ -357,17 +398,6 @@ namespace spb
                     else face_flux<CONV, DISS, VISC, 1, false, SGS, PRE>(acc, P, invdx, F, 1.0, h4, s4);
                     #pragma unroll
                     for (int v = 0; v < 5; ++v) Fy[(jl*TI + il)*5 + v] = F[v];
-                }
-                if (PRE)
-                {
-                    // the x-flux of the right neighbour comes by shuffle (all 32 lanes take part; a warp is one tile row)
-                    #pragma unroll
-                    for (int v = 0; v < 5; ++v) dFxy[v] = Fxo[v] - __shfl_down_sync(0xffffffffu, Fxo[v], 1);
-                    if (il == ni_t - 1)
-                    {
-                        #pragma unroll
-                        for (int v = 0; v < 5; ++v) dFxy[v] = Fxo[v];      // minus the edge flux after the barrier
-                    }
                 }
                 // faces on the upper edge of the tile
                 if (tid < nj_t)                      // warp 0: x-face i = ni_t of row tid
@@ -405,21 +435,23 @@ namespace spb
                     for (int v = 0; v < 5; ++v) Fy[(nj_t*TI + (tid - 32))*5 + v] = F[v];
                 }
             }
+            // the halo cells of the plane published next (k+1), evaluated by warps 2 .. 7 while warps 0 and 1 finish the edge faces
+            if (PRE && k + 1 < nz) halo_eval(1);
             __syncthreads();
             if (k < nz && active)
             {
                 #pragma unroll
                 for (int v = 0; v < 5; ++v)
                 {
-                    double dFx;
-                    if (PRE) dFx = (il == ni_t - 1) ? dFxy[v] - Fx[jl*5 + v] : dFxy[v];
-                    else     dFx = Fx[(jl*(TI + 1) + il)*5 + v] - Fx[(jl*(TI + 1) + il + 1)*5 + v];
                     const double dFy = Fy[(jl*TI + il)*5 + v] - Fy[((jl + 1)*TI + il)*5 + v];
-                    rprev[v] = fma(dFx, invdx[0], fma(dFy, invdx[1], Fz[v]*invdx[2]));
+                    double r = fma(dFy, invdx[1], rz[v]);
+                    if (PRE) { if (il == ni_t - 1) r = fma(-Fx[jl*5 + v], invdx[0], r); }
+                    else     r = fma(Fx[(jl*(TI + 1) + il)*5 + v] - Fx[(jl*(TI + 1) + il + 1)*5 + v], invdx[0], r);
+                    rprev[v] = r;
                 }
             }
             // PRE: the x / y faces of this step have read the published plane (barrier above): publish plane k+1 for the next step
-            if (PRE && k + 1 < nz) publish(1, zh[3], zs[3]);
+            if (PRE && k + 1 < nz) publish(zh[3], zs[3]);
             __syncthreads();
             if (PRE)
             {
