@@ -97,6 +97,7 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop = threading.Event()
+        self._ready = threading.Event()
         self._thr = None
 
     def _run_nvml(self):
@@ -108,6 +109,7 @@ class ClockSampler:
         self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
         bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self._ready.set()
         while not self._stop.is_set():
             self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
             r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
@@ -124,6 +126,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self._ready.set()
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
@@ -138,8 +141,11 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def start(self):
+        """Returns once the sampler is initialised (module import, nvmlInit, device handle): that costs ~10 ms of driver and
+        interpreter time, which must not fall into the timed region that starts right after."""
         self._thr = threading.Thread(target=self._run, daemon=True)
         self._thr.start()
+        self._ready.wait(timeout=10)
 
     def stop(self):
         self._stop.set()
@@ -419,6 +425,7 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
         w.ti.advance()
     barrier()
     sampler = ClockSampler(local_rank)
+    sample_clocks = sample_clocks and not os.environ.get("SPB_NO_CLOCK_SAMPLER")     # development A/B only
     if rank == 0 and sample_clocks:
         sampler.start()
     launches0 = sp.launch_count()

@@ -267,6 +267,26 @@ namespace spb
         const int row = 5*tr.bx;                       // contiguous doubles along i
         const long long pitch_j = 5ll*np0, pitch_k = 5ll*np0*np1;
         const int end = min(it.begin + ITEM, nel);
+        // 16-byte path (uniform per work item): rows of an even number of doubles that start on even offsets — every box of a
+        // lattice with an even padded row (2 exchange cells, even block sizes). A pair (el, el+1) with el even never leaves its row.
+        const bool even = !tr.interp && ((row | (5*np0) | nel) & 1) == 0
+            && (MODE == 2 || ((tr.src_off & 1) == 0 && (reinterpret_cast<uintptr_t>(qsrc) & 15) == 0))
+            && (MODE == 1 || ((tr.dst_off & 1) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0))
+            && (MODE == 0 || ((tr.buf_off & 1) == 0 && (reinterpret_cast<uintptr_t>(MODE == 1 ? buf : bufsrc) & 15) == 0));
+        if (even)
+        {
+            for (int el = it.begin + 2*threadIdx.x; el < end; el += 512)
+            {
+                const int r = el / row, c = el - r*row;
+                const int iz = r / tr.by, iy = r - iz*tr.by;
+                const long long rel = c + iy*pitch_j + iz*pitch_k;
+                const double2 val = (MODE == 2) ? *reinterpret_cast<const double2*>(bufsrc + tr.buf_off + el)
+                                                : *reinterpret_cast<const double2*>(qsrc + tr.src_off + rel);
+                if (MODE == 1) *reinterpret_cast<double2*>(buf + tr.buf_off + el) = val;
+                else           *reinterpret_cast<double2*>(q + tr.dst_off + rel) = val;
+            }
+            return;
+        }
         for (int el = it.begin + threadIdx.x; el < end; el += 256)
         {
             const int r = el / row, c = el - r*row;

@@ -22,7 +22,7 @@
 #include "spb_tma.cuh"
 #include "spb_flux.cuh"
 
-// Timing-only experiment switches (tools/runs/r02_exp.sh builds libspade_b200_exp<N>.so with -DSPB_EXP=N; the results of
+// Timing-only experiment switches (`make -C spade_b200/csrc exp EXP=N` builds libspade_b200_exp<N>.so with -DSPB_EXP=N, `tools/gpu_visit.sh exp` times them; the results of
 // those builds are WRONG by construction, they bound what a restructuring could gain): bit 0 drops barrier (2), bit 1
 // drops the flux hand-off through shared memory, bit 2 drops the published differences.
 #ifndef SPB_EXP
