@@ -423,6 +423,11 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
 
     for _ in range(warmup):
         w.ti.advance()
+    # the byte count of a stage launch needs the plan's same-rank ghost cells: read from the tables on first use (~15 ms of host time
+    # for 4096 blocks, cached afterwards) — before the timed region, not inside its first step (rounds 1 and 2 paid it there:
+    # first step 28.7 ms against a median of 19.4 ms, `steps_detail` in the line)
+    if getattr(w, "handle", None) is not None and hasattr(w.handle, "local_injection_cells"):
+        w.handle.local_injection_cells()
     barrier()
     sampler = ClockSampler(local_rank)
     sample_clocks = sample_clocks and not os.environ.get("SPB_NO_CLOCK_SAMPLER")     # development A/B only
@@ -439,8 +444,13 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
     barrier()
     t0.record()
     host_t0 = time.perf_counter()
+    step_ev, host_ms = [], []
     for _ in range(steps):
+        h0 = time.perf_counter()
         w.ti.advance()
+        host_ms.append(1e3 * (time.perf_counter() - h0))
+        step_ev.append(torch.cuda.Event(enable_timing=True))
+        step_ev[-1].record()
     host_loop_ms = 1e3 * (time.perf_counter() - host_t0)      # diagnosis: far below the device time if the host runs ahead
     t1.record()
     barrier()
@@ -480,10 +490,16 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
             allp = [None] * world
             dist.all_gather_object(allp, phases)
             phases = {"per_rank": allp}
+    # device time of every step (events behind each advance()) and host time of every advance() call: the first step of the region
+    # starts on an idle GPU with an empty launch queue, the others are enqueued while their predecessor runs
+    per_step = [t0.elapsed_time(step_ev[0])] + [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(steps - 1)]
+    steps_detail = {"first_ms": per_step[0], "median_ms": statistics.median(per_step), "max_ms": max(per_step),
+                    "host_first_ms": host_ms[0], "host_median_ms": statistics.median(host_ms)}
     umax_end = sp.transform_reduce(w.q, sp.FN_WAVESPEED, sp.RED_MAX, w.gas)
     if not (umax_end == umax_end) or umax_end > 10 * w.umax0:
         raise SystemExit(f"bench.py: solution diverged (umax {umax_end})")
     return {"ms": ms, "launches": int(launches), "clocks": clocks, "phases": phases, "kern_ms": kern_ms, "kern_bpc": kern_bpc, "n_events": len(ev),
+            "steps_detail": steps_detail,
             "value": w.cells_total * STAGES * steps / (ms * 1e-3)}
 
 
@@ -775,6 +791,7 @@ def ours(args):
                 "config": workload_config(args, n), "cell_steps_per_s": m["value"] / STAGES,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": m["launches"],
                 "clocks": m["clocks"], "parity_check": parity}
+        line["steps_detail"] = m["steps_detail"]
         if m.get("phases"):
             line["phases"] = m["phases"]
         if configs:

@@ -52,6 +52,8 @@ namespace spb
         static constexpr int PW = TI + 4, PH = TJ + 4, PUB_CELLS = PW*PH;
         static constexpr int FXE_DOUBLES = TJ*5;
         static constexpr int BYTES_PRE = NP*PLANE_STRIDE_BYTES + (FXE_DOUBLES + FY_DOUBLES + 2*PUB_CELLS)*8 + NP*8 + 128;
+        // PRE kernels on general coordinates: the three metric rows of the tile's x and y range (cells and faces 0 .. TI / TJ)
+        static constexpr int METS_DOUBLES = 3*(TI + 1) + 3*(TJ + 1);
     };
 
     // accessor of the staged planes, centred on tile-local cell (il, jl) of the current plane
@@ -92,7 +94,12 @@ namespace spb
         double*   Fy   = Fx + (PRE ? S::FXE_DOUBLES : S::FX_DOUBLES);
         double*   pubh = Fy + S::FY_DOUBLES;                                     // PRE: rho/2 of the published plane
         double*   pubs = pubh + S::PUB_CELLS;                                    // PRE: (rho/2)(|u| + c)
-        uint64_t* bars = (uint64_t*)(PRE ? pubs + S::PUB_CELLS : Fy + S::FY_DOUBLES);
+        // PRE + CURV: the x / y metric rows of the tile live in shared memory. A thread's own entries are loop invariants: read
+        // through __ldg the compiler keeps them in registers for the whole k loop (12 registers, paid in spills); shared-memory
+        // loads are not moved across the barriers of a step, so they are simply re-read where a face needs them.
+        constexpr bool METS = PRE && CURV;
+        double*   mets = pubs + S::PUB_CELLS;
+        uint64_t* bars = (uint64_t*)(PRE ? pubs + S::PUB_CELLS + (METS ? S::METS_DOUBLES : 0) : Fy + S::FY_DOUBLES);
 
         const int tid = threadIdx.x;
         const int il = tid & 31, jl = tid >> 5;
@@ -111,15 +118,22 @@ namespace spb
         // metric rows of this block: M(d, row, idx)
         const double* mt = CURV ? met + lb*9*(long long)G.lm : nullptr;
         auto M = [&](const int d, const int row, const int idx) { return __ldg(mt + (d*3 + row)*G.lm + idx); };
+        // the same entry addressed by padded index; METS: x / y entries come from the staged rows (tile-local index)
+        auto MP = [&](const int d, const int row, const int idx)
+        {
+            if (METS && d == 0) return mets[row*(TI + 1) + (idx - i0 - G.ng[0])];
+            if (METS && d == 1) return mets[3*(TI + 1) + row*(TJ + 1) + (idx - j0 - G.ng[1])];
+            return M(d, row, idx);
+        };
         // gradient scales and area factor of the lower face of direction D of the padded cell (ip, jp, kp)
         auto face_metric = [&](auto Dc, const int ip, const int jp, const int kp, double (&gs)[3], double& area)
         {
             constexpr int D = decltype(Dc)::value, T1 = (D + 1) % 3, T2 = (D + 2) % 3;
             const int idx[3] = {ip, jp, kp};
-            area   = M(T1, 0, idx[T1])*M(T2, 0, idx[T2]);
-            gs[D]  = invdx[D]*M(D, 2, idx[D]);
-            gs[T1] = invdx[T1]*M(T1, 1, idx[T1]);
-            gs[T2] = invdx[T2]*M(T2, 1, idx[T2]);
+            area   = MP(T1, 0, idx[T1])*MP(T2, 0, idx[T2]);
+            gs[D]  = invdx[D]*MP(D, 2, idx[D]);
+            gs[T1] = invdx[T1]*MP(T1, 1, idx[T1]);
+            gs[T2] = invdx[T2]*MP(T2, 1, idx[T2]);
         };
         constexpr std::integral_constant<int, 0> DX{};
         constexpr std::integral_constant<int, 1> DY{};
@@ -139,6 +153,15 @@ namespace spb
             #pragma unroll
             for (int s = 0; s < S::NP; ++s) mbar_init(&bars[s], 1);
             fence_mbar_init();
+        }
+        if (METS && tid < S::METS_DOUBLES)
+        {
+            // entry (row, loc) of direction d: padded index origin + loc, clamped to the table (ragged tiles)
+            const bool isx = tid < 3*(TI + 1);
+            const int  e = isx ? tid : tid - 3*(TI + 1), len = isx ? TI + 1 : TJ + 1;
+            const int  row = e / len, loc = e - row*len;
+            const int  idx = min((isx ? i0 + G.ng[0] : j0 + G.ng[1]) + loc, G.lm - 1);
+            mets[tid] = M(isx ? 0 : 1, row, idx);
         }
         __syncthreads();
         if (tid == 0)
@@ -249,7 +272,7 @@ namespace spb
                     double gs[3], area;
                     face_metric(DZ, ipc, jpc, k + G.ng[2], gs, area);
                     face_flux<CONV, DISS, VISC, 2, true, SGS, PRE>(acc, P, gs, Fz, area, zh, zs);
-                    if (k >= 1) jac_prev = M(0, 1, ipc)*M(1, 1, jpc)*M(2, 1, k - 1 + G.ng[2]);
+                    if (k >= 1) jac_prev = MP(0, 1, ipc)*MP(1, 1, jpc)*M(2, 1, k - 1 + G.ng[2]);
                 }
                 else face_flux<CONV, DISS, VISC, 2, false, SGS, PRE>(acc, P, invdx, Fz, 1.0, zh, zs);
             }
@@ -518,7 +541,7 @@ namespace spb
         StageParams SP{};
         if (stage) SP = *stage;
         constexpr bool PRE = (CONV == SPB_CONV_FWENO) || (DISS == SPB_DISS_FWENO);
-        constexpr int SMEM = PRE ? S::BYTES_PRE : S::BYTES;
+        constexpr int SMEM = PRE ? S::BYTES_PRE + (CURV ? S::METS_DOUBLES*8 : 0) : S::BYTES;
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         kern<<<(unsigned)nblk, S::NT, SMEM, stream>>>(tq, rhs, P, G, g->inv_dx_dev, q_out, SP, g->metric_dev, nbr_tab);
         SPB_LAUNCH_CHECK();

@@ -28,7 +28,7 @@ try:
     out = {"value": d["value"], "ms_per_step": round(d["ms_per_step"], 3), "frac": round(r["frac"], 4), "stage_ms": r.get("ms_per_launch"), "share": r.get("step_share"),
            "rhs_only": (r.get("rhs_only") or {}).get("frac"), "launches": d["gpu_launches"], "e2e": (d.get("e2e") or {}).get("value"), "clocks": d.get("clocks"),
            "parity": {k: (d.get("parity_check") or {}).get(k) for k in ("ok", "exchange_bit_exact", "trajectory_rel_l2", "error")},
-           "cfg4": ((d.get("configs") or {}).get("config4") or {}).get("value")}
+           "steps_detail": d.get("steps_detail"), "cfg4": ((d.get("configs") or {}).get("config4") or {}).get("value")}
     print(json.dumps(out))
     for p in ((d.get("phases") or {}).get("per_rank") or ([d["phases"]] if d.get("phases") else [])):
         print("   ", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()})
