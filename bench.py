@@ -95,7 +95,7 @@ class ClockSampler:
     """SM clock / throttle reasons during the timed region (nvidia-smi, B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.reasons, self.max_mhz, self.power = index, [], set(), None, []
         self._stop = threading.Event()
         self._ready = threading.Event()
         self._thr = None
@@ -112,6 +112,10 @@ class ClockSampler:
         self._ready.set()
         while not self._stop.is_set():
             self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            try:
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
             r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             for n, b in bits.items():
                 if r & b:
@@ -152,7 +156,10 @@ class ClockSampler:
         if self._thr:
             self._thr.join(timeout=6)
         med = statistics.median(self.samples) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        out = {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.power:
+            out["power_w"] = statistics.median(self.power)
+        return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -429,9 +436,12 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
     if getattr(w, "handle", None) is not None and hasattr(w.handle, "local_injection_cells"):
         w.handle.local_injection_cells()
     barrier()
-    sampler = ClockSampler(local_rank)
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = int(vis.split(",")[local_rank]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else local_rank   # NVML counts physical GPUs
+    sampler = ClockSampler(phys)
     sample_clocks = sample_clocks and not os.environ.get("SPB_NO_CLOCK_SAMPLER")     # development A/B only
-    if rank == 0 and sample_clocks:
+    all_sample = bool(os.environ.get("SPB_PHASE_EVENTS"))                            # diagnosis: every rank samples its own GPU
+    if (rank == 0 or all_sample) and sample_clocks:
         sampler.start()
     launches0 = sp.launch_count()
     timing["events"] = ev = []
@@ -442,6 +452,8 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
         w.ti.stage_events = ev
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if os.environ.get("SPB_DIAG_DELAY_RANK") == str(rank):
+        time.sleep(0.03)                     # diagnosis: this rank enters the timed region late (who runs ahead of whom?)
     t0.record()
     host_t0 = time.perf_counter()
     step_ev, host_ms = [], []
@@ -458,7 +470,7 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
     w.ti.stage_events = None
     ms = t0.elapsed_time(t1)
     launches = sp.launch_count() - launches0
-    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+    clocks = sampler.stop() if ((rank == 0 or all_sample) and sample_clocks) else None
     kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / max(1, len(ev))
     kern_bpc = sum(c for _, _, c in ev) / max(1, len(ev))      # algorithmic bytes per cell, mean over launches
     if world > 1:
@@ -466,23 +478,27 @@ def measure(w, steps, warmup, sp, torch, dist, world, rank, local_rank, timing, 
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     phases = None
-    if getattr(w.ti, "phase_events", None):
-        # diagnosis (SPB_PHASE_EVENTS=1): mean device times of a stage on this rank: start -> boundary kernel done -> packs and flags
-        # issued -> interior kernel done -> messages unpacked
-        pes = w.ti.phase_events[-4 * steps:]
-        mean = lambda f: sum(f(p) for p in pes) / len(pes)
-        phases = {"boundary_done_ms": mean(lambda p: p[0].elapsed_time(p[1])), "packs_done_ms": mean(lambda p: p[0].elapsed_time(p[2])),
-                  "interior_done_ms": mean(lambda p: p[0].elapsed_time(p[3])), "unpacked_ms": mean(lambda p: p[0].elapsed_time(p[4])), "stages": len(pes)}
-        w.ti.phase_events.clear()
-        phases["stage_kernel_ms"] = sum(a.elapsed_time(b) for a, b, _ in ev) / max(1, len(ev))
-        phases["host_loop_ms_per_step"] = host_loop_ms / steps
+    if os.environ.get("SPB_PHASE_EVENTS"):
+        # diagnosis (SPB_PHASE_EVENTS=1), per rank: stage kernel time, own step time, clocks of the own GPU; with the overlapped multi-rank
+        # schedule also the mean device times of a stage: start -> boundary kernel done -> packs and flags issued -> interior kernel
+        # done -> messages unpacked, the end-of-step join and the [flag wait, unpack] pairs
+        props = torch.cuda.get_device_properties(torch.cuda.current_device())
+        phases = {"stage_kernel_ms": sum(x.elapsed_time(y) for x, y, _ in ev) / max(1, len(ev)), "ms_per_step_own": t0.elapsed_time(t1) / steps,
+                  "host_loop_ms_per_step": host_loop_ms / steps, "clocks": clocks,
+                  "gpu": {"local_rank": local_rank, "nvml_index": phys, "uuid": str(getattr(props, "uuid", ""))[-8:]}}
+        pes = (getattr(w.ti, "phase_events", None) or [])[-4 * steps:]
+        if pes:
+            mean = lambda f: sum(f(p) for p in pes) / len(pes)
+            phases.update({"boundary_done_ms": mean(lambda p: p[0].elapsed_time(p[1])), "packs_done_ms": mean(lambda p: p[0].elapsed_time(p[2])),
+                           "interior_done_ms": mean(lambda p: p[0].elapsed_time(p[3])), "unpacked_ms": mean(lambda p: p[0].elapsed_time(p[4])), "stages": len(pes)})
+            w.ti.phase_events.clear()
         je = getattr(w.ti, "join_events", None)
         if je:
             je = je[-steps:]
-            phases["join_ms"] = sum(a.elapsed_time(b) for a, b in je) / len(je)                 # end-of-step join (deferred schedule)
+            phases["join_ms"] = sum(x.elapsed_time(y) for x, y in je) / len(je)                 # end-of-step join (deferred schedule)
             phases["step_ms"] = sum(je[i][1].elapsed_time(je[i + 1][1]) for i in range(len(je) - 1)) / max(1, len(je) - 1)
             w.ti.join_events.clear()
-        tr = getattr(w.handle, "finish_trace", None)
+        tr = getattr(getattr(w, "handle", None), "finish_trace", None)
         if tr:
             tr = tr[-4 * steps:]
             phases["finish_ms"] = [round(sum(t[k].elapsed_time(t[k + 1]) for t in tr) / len(tr), 4) for k in range(len(tr[0]) - 1)]   # wait, unpack per peer
@@ -720,6 +736,8 @@ def ours(args):
         opts.is_high_priority_stream = os.environ.get("SPB_NCCL_HIGH_PRIO", "1") != "0"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     pool = sp.pool_t.from_torch()
+    if os.environ.get("SPB_DIAG_SOLO"):
+        pool = sp.pool_t()                   # diagnosis: every rank runs the 1-GPU workload on its own (process group initialised, no exchange)
     n = max(world, 1)
     timing = {"on": False, "events": []}
 
