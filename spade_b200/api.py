@@ -1071,6 +1071,7 @@ class integrator_t:
         self.stage_events = None        # bench.py: a list collects (start, stop, algorithmic bytes per cell) per stage kernel
         self.phase_events = [] if os.environ.get("SPB_PHASE_EVENTS") else None   # diagnosis: per-phase CUDA events of every stage
         self.join_events = []
+        self._boundary_delay = int(float(os.environ.get("SPB_BOUNDARY_DELAY_US", "0")) * 1900)   # development A/B (SM cycles)
         if fused and isinstance(rhs_calc, flux_div_rhs_t) and rhs_calc.traits == overwrite and isinstance(scheme, rk_t):
             if lib().spb_flux_div_rk_stage_supported(C.byref(rhs_calc.flux)):
                 self._plan = self._fused_plan(scheme)
@@ -1169,6 +1170,8 @@ class integrator_t:
                         pe[4].record(side)                      # (deferred schedule: the unpack of the PREVIOUS stage's messages)
                     if self._ev_i is not None:
                         side.wait_event(self._ev_i)             # the previous interior kernel wrote same-rank ghosts of the boundary blocks
+                    if self._boundary_delay:
+                        torch.cuda._sleep(self._boundary_delay)     # development A/B: let the interior kernel fill the SMs first
                     launch(_lib.SPB_PART_BOUNDARY)
                     ev_b = torch.cuda.Event()
                     ev_b.record(side)

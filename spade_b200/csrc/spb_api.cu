@@ -66,6 +66,17 @@ extern "C"
                 g->dx_host[3*lb+d] = dx;
                 g->inv_dx_host[3*lb+d] = 1.0/dx;
             }
+        for (int d = 0; d < 3; ++d)
+        {
+            double xmax = 0.0, smin = 0.0;
+            for (int64_t lb = 0; lb < nlb; ++lb)
+            {
+                const double lo = bbox_host[6*lb + 2*d], hi = bbox_host[6*lb + 2*d + 1];
+                xmax = fmax(xmax, fmax(fabs(lo), fabs(hi)));
+                smin = (lb == 0) ? fabs(hi - lo) : fmin(smin, fabs(hi - lo));
+            }
+            g->spacing_round_tol[d] = (smin > 0.0) ? 4.0*2.220446049250313e-16*xmax/smin : 0.0;
+        }
         g->inv_dx_dev = nullptr;
         cudaError_t e = cudaGetDevice(&g->device);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);

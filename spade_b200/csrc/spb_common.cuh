@@ -60,6 +60,9 @@ struct spb_grid
     std::vector<double> dx_host;      // [nlb][3]
     std::vector<double> inv_dx_host;  // [nlb][3]
     double* inv_dx_dev;               // [nlb][3]
+    // relative spread of the spacings of a direction that the rounding of the block bounds alone explains: a block's size is
+    // formed as (lo + bsize) - lo (cartesian_blocks.h:66-71), exact to 2 ulp of the COORDINATE, i.e. 2 eps |x|/size relative
+    double  spacing_round_tol[3] = {0.0, 0.0, 0.0};
     int     num_sms;
     // general coordinates (spb_grid_set_metric): [nlb][3 directions][3 rows][metric_lm] doubles, rows = area metric,
     // 1/jacobian metric, 1/face metric; null for coords::identity

@@ -885,14 +885,18 @@ namespace spb
         if (bl.dev) { lb_begin = 0; lb_end = g->nlb; }                  // the spacing check below then covers every block
         const int64_t nblk = (bl.dev ? bl.count : lb_end - lb_begin)*G.tiles_i*G.tiles_j;
         if (nblk <= 0) return 0;
-        // A lattice counts as uniform when the per-block spacings agree to 8 ulp: box.size/num_cell formed block by block
-        // (cartesian_grid.h:134-135) wobbles in the last bit with the block origin, which is 1e-16 relative in the rhs.
+        // A lattice counts as uniform when the per-block spacings agree up to what the rounding of the block bounds explains:
+        // box.size/num_cell formed block by block (cartesian_grid.h:134-135) wobbles with the block origin by 2 ulp of the
+        // COORDINATE — 10 and 20 ulp of the spacing on ranks 1 and 2 of a weak-scaled box whose z runs to 2 pi N. A fixed 8-ulp
+        // test (rounds 1 and 2) sent exactly those ranks to the per-block-table variant, which is 6 % slower, and every other
+        // rank waited for them (profiles/r02_pair_diagnosis.log). The common spacing changes the rhs by < 1e-13 relative.
         bool uniform = true;
         for (int64_t b = lb_begin; b < lb_end && uniform; ++b)
             for (int d = 0; d < 3; ++d)
             {
                 const double a = g->inv_dx_host[3*b + d], r = g->inv_dx_host[3*lb_begin + d];
-                uniform = uniform && (fabs(a - r) <= 8.0*2.220446049250313e-16*fabs(r));
+                const double tol = fmin(fmax(8.0*2.220446049250313e-16, g->spacing_round_tol[d]), 1e-13);
+                uniform = uniform && (fabs(a - r) <= tol*fabs(r));
             }
         for (int d = 0; d < 3; ++d) { G.idx[d] = g->inv_dx_host[3*lb_begin + d]; G.cdx[d] = 0.25*G.idx[d]; }
         Stage S{};

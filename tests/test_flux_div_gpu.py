@@ -54,6 +54,26 @@ def test_anisotropic_spacing_and_one_ghost():
     assert rel_l2(got, want) < TOL
 
 
+def test_lattice_far_from_the_origin_keeps_the_uniform_kernel_and_the_gate():
+    """A rank of a weak-scaled box sits far from the origin (z up to 2 pi N): box.size/num_cell formed from the rounded block
+    bounds (cartesian_grid.h:134-135) then wobbles by 10-80 ulp from block to block. The narrow kernel treats such a lattice
+    as uniform (one spacing from the constant bank: the fast variant; spb_grid::spacing_round_tol) and must stay inside
+    the 1e-12 gate against the oracle, which uses the reference's per-block spacings."""
+    from oracle import port
+    nb, n, ng = (1, 1, 16), (16, 8, 8), 2
+    L = 2 * np.pi
+    bounds = [0.0, L, 0.0, L, 2 * L, 3 * L]                  # the z-slab of rank 2 of a weak-scaled TGV box: 20 ulp of wobble
+    bsize = (bounds[5] - bounds[4]) / nb[2]
+    dz = np.array([((bounds[4] + b * bsize + bsize) - (bounds[4] + b * bsize)) / n[2] for b in range(nb[2])])
+    assert np.ptp(dz) / dz[0] > 8 * 2.220446049250313e-16    # the case the old 8-ulp test sent to the slow per-block variant
+    for scheme in (0, 3, 4):
+        q = make_state(nb, n, ng, seed=5, bounds=bounds)
+        cfg = oracle_cfg(nb, n, ng, scheme=scheme, bounds=bounds)
+        want = port.flux_div(cfg, q.ravel()).reshape(q.shape)
+        got = run_product(nb, n, ng, q, scheme, bounds=bounds)
+        assert rel_l2(got, want) < TOL
+
+
 def test_increment_trait():
     from oracle import port
     nb, n, ng = (1, 1, 2), (32, 8, 8), 2
