@@ -77,11 +77,29 @@ extern "C"
             }
             g->spacing_round_tol[d] = (smin > 0.0) ? 4.0*2.220446049250313e-16*xmax/smin : 0.0;
         }
+        // refinement levels per direction (an AMR grid has a handful; a uniform lattice one)
+        std::vector<int> lev(nlb > 0 ? nlb : 0, 0);
+        for (int d = 0; d < 3; ++d)
+        {
+            const double tol = fmin(fmax(8.0*2.220446049250313e-16, g->spacing_round_tol[d]), 1e-13);
+            int n = 0;
+            for (int64_t lb = 0; lb < nlb && n >= 0; ++lb)
+            {
+                const double a = g->inv_dx_host[3*lb + d];
+                int l = 0;
+                while (l < n && !(fabs(a - g->lev_inv[d][l]) <= tol*fabs(a))) ++l;
+                if (l == n) { if (n == 16) { n = -1; break; } g->lev_inv[d][n++] = a; }
+                lev[lb] |= l << (8*d);
+            }
+            g->lev_n[d] = n;
+        }
         g->inv_dx_dev = nullptr;
         cudaError_t e = cudaGetDevice(&g->device);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);
         if (e == cudaSuccess && nlb > 0) e = cudaMalloc(&g->inv_dx_dev, sizeof(double)*3*nlb);
         if (e == cudaSuccess && nlb > 0) e = cudaMemcpy(g->inv_dx_dev, g->inv_dx_host.data(), sizeof(double)*3*nlb, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && nlb > 0) e = cudaMalloc((void**)&g->lev_dev, sizeof(int)*nlb);
+        if (e == cudaSuccess && nlb > 0) e = cudaMemcpy(g->lev_dev, lev.data(), sizeof(int)*nlb, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { delete g; return spb::cuda_fail(e, "spb_grid_create", __FILE__, __LINE__); }
         *out = g;
         return 0;
@@ -164,6 +182,7 @@ extern "C"
         if (!g) return;
         if (g->metric_dev) cudaFree(g->metric_dev);
         if (g->inv_dx_dev) cudaFree(g->inv_dx_dev);
+        if (g->lev_dev) cudaFree(g->lev_dev);
         if (g->red_scratch) cudaFree(g->red_scratch);
         for (int i = 0; i < 6; ++i) if (g->bnd_blocks_dev[i]) cudaFree(g->bnd_blocks_dev[i]);
         delete g;

@@ -63,6 +63,12 @@ struct spb_grid
     // relative spread of the spacings of a direction that the rounding of the block bounds alone explains: a block's size is
     // formed as (lo + bsize) - lo (cartesian_blocks.h:66-71), exact to 2 ulp of the COORDINATE, i.e. 2 eps |x|/size relative
     double  spacing_round_tol[3] = {0.0, 0.0, 0.0};
+    // refinement levels: the distinct inverse spacings of each direction (values that differ by no more than the rounding
+    // tolerance above are one level) and, per block, the packed level indices l0 | l1 << 8 | l2 << 16. lev_n[d] = -1: more
+    // than SPB_MAX_LEVELS distinct spacings in direction d (the narrow kernel then refuses a non-uniform launch)
+    int     lev_n[3] = {0, 0, 0};
+    double  lev_inv[3][16] = {};
+    int*    lev_dev = nullptr;
     int     num_sms;
     // general coordinates (spb_grid_set_metric): [nlb][3 directions][3 rows][metric_lm] doubles, rows = area metric,
     // 1/jacobian metric, 1/face metric; null for coords::identity

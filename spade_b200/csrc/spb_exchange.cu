@@ -287,29 +287,45 @@ namespace spb
             }
             return;
         }
+        if (MODE != 2 && tr.interp)
+        {
+            // patch_fill_t (make_exchange.h:233-256, transactions.h:176-201), one destination CELL per thread: donor offset
+            // ((ix << (i_coeff+1)) >> 1) + d*i_incr; per variable the 2^3 donors are added in the order d0 fastest and the sum is
+            // multiplied by 1/8 (bit-identical to the reference). The index arithmetic is done once per cell, the 8 x 5 loads are
+            // independent. A cell that straddles two work items is completed by both (each stores its own variables).
+            for (int cell = it.begin/5 + threadIdx.x; 5*cell < end; cell += 256)
+            {
+                const int r = cell / tr.bx, ix = cell - r*tr.bx;
+                const int iz = r / tr.by, iy = r - iz*tr.by;
+                const int i0 = (ix << (tr.ic[0] + 1)) >> 1, j0 = (iy << (tr.ic[1] + 1)) >> 1, k0 = (iz << (tr.ic[2] + 1)) >> 1;
+                const double* d0p = qsrc + tr.src_off + 5ll*i0 + j0*pitch_j + k0*pitch_k;
+                const long long si = 5ll*tr.inc[0], sj = tr.inc[1]*pitch_j, sk = tr.inc[2]*pitch_k;
+                double sum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                #pragma unroll
+                for (int iv = 0; iv < 8; ++iv)
+                {
+                    const double* dp = d0p + (iv & 1)*si + ((iv >> 1) & 1)*sj + ((iv >> 2) & 1)*sk;
+                    #pragma unroll
+                    for (int v = 0; v < 5; ++v) sum[v] = __dadd_rn(sum[v], dp[v]);
+                }
+                const long long rel = 5ll*ix + iy*pitch_j + iz*pitch_k;
+                #pragma unroll
+                for (int v = 0; v < 5; ++v)
+                {
+                    const int el = 5*cell + v;
+                    if (el < it.begin || el >= end) continue;
+                    if (MODE == 1) buf[tr.buf_off + el] = sum[v]*0.125;
+                    else           q[tr.dst_off + rel + v] = sum[v]*0.125;
+                }
+            }
+            return;
+        }
         for (int el = it.begin + threadIdx.x; el < end; el += 256)
         {
             const int r = el / row, c = el - r*row;
             const int iz = r / tr.by, iy = r - iz*tr.by;
             const long long rel = c + iy*pitch_j + iz*pitch_k;
-            double val;
-            if (MODE == 2) val = bufsrc[tr.buf_off + el];
-            else if (!tr.interp) val = qsrc[tr.src_off + rel];
-            else
-            {
-                // patch_fill_t (make_exchange.h:233-256, transactions.h:176-201): donor offset ((ix << (i_coeff+1)) >> 1) + d*i_incr,
-                // the 2^3 donors are added in the order d0 fastest and the sum is multiplied by 1/8
-                const int ix = c / 5, v = c - 5*ix;
-                const int i0 = (ix << (tr.ic[0] + 1)) >> 1, j0 = (iy << (tr.ic[1] + 1)) >> 1, k0 = (iz << (tr.ic[2] + 1)) >> 1;
-                double sum = 0.0;
-                #pragma unroll
-                for (int iv = 0; iv < 8; ++iv)
-                {
-                    const int d0 = iv & 1, d1 = (iv >> 1) & 1, d2 = (iv >> 2) & 1;
-                    sum = __dadd_rn(sum, qsrc[tr.src_off + 5ll*(i0 + d0*tr.inc[0]) + (j0 + d1*tr.inc[1])*pitch_j + (k0 + d2*tr.inc[2])*pitch_k + v]);
-                }
-                val = sum*0.125;
-            }
+            const double val = (MODE == 2) ? bufsrc[tr.buf_off + el] : qsrc[tr.src_off + rel];
             if (MODE == 1) buf[tr.buf_off + el] = val;
             else q[tr.dst_off + rel] = val;
         }

@@ -81,6 +81,9 @@ namespace spb
             int tma_store;
             int ghost;                      // fused stage: also store the finished q planes into the same-rank neighbours' ghost cells
             double idx[3], cdx[3];          // uniform lattice: 1/dx and 0.25/dx
+            double lev_inv[3][16];          // non-uniform lattice (AMR): the distinct 1/dx of each direction (spb_grid::lev_inv)
+            double lev_cinv[3][16];         // ... and 0.25/dx
+            const int* lev;                 // ... and the packed level indices of every block (spb_grid::lev_dev)
             int lm;                         // general coordinates: row length of the metric tables (spb_grid::metric_lm)
             const int* blist;               // local block of CTA group t (a scattered block set in one launch), or null: lb0 + t
         };
@@ -151,7 +154,10 @@ namespace spb
         __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
         // Inverse spacings: for a uniform lattice (all blocks the same dx) they come from the kernel-parameter constant
-        // bank and cost no registers; otherwise (AMR: per-block dx) they are read from the per-block table.
+        // bank and cost no registers. An AMR grid has a handful of distinct spacings per direction (its refinement levels):
+        // they sit in the constant bank too, and the block's level indices are made warp-uniform FOR THE COMPILER by a
+        // warp reduction (REDUX writes a uniform register), so the six values live in uniform registers instead of twelve
+        // vector registers per thread (the per-block table of rounds 1 and 2 cost the kernel 9 % through spills).
         template <bool UNIF> struct Spacing
         {
             double i0, i1, i2, c0, c1, c2;
@@ -160,8 +166,9 @@ namespace spb
                 if (UNIF) { i0 = G.idx[0]; i1 = G.idx[1]; i2 = G.idx[2]; c0 = G.cdx[0]; c1 = G.cdx[1]; c2 = G.cdx[2]; }
                 else
                 {
-                    i0 = tab[3*lb + 0]; i1 = tab[3*lb + 1]; i2 = tab[3*lb + 2];
-                    c0 = 0.25*i0; c1 = 0.25*i1; c2 = 0.25*i2;
+                    const unsigned pk = __reduce_max_sync(0xffffffffu, (unsigned)__ldg(G.lev + lb));
+                    i0 = G.lev_inv[0][pk & 15u]; i1 = G.lev_inv[1][(pk >> 8) & 15u]; i2 = G.lev_inv[2][(pk >> 16) & 15u];
+                    c0 = G.lev_cinv[0][pk & 15u]; c1 = G.lev_cinv[1][(pk >> 8) & 15u]; c2 = G.lev_cinv[2][(pk >> 16) & 15u];
                 }
             }
         };
@@ -899,6 +906,11 @@ namespace spb
                 uniform = uniform && (fabs(a - r) <= tol*fabs(r));
             }
         for (int d = 0; d < 3; ++d) { G.idx[d] = g->inv_dx_host[3*lb_begin + d]; G.cdx[d] = 0.25*G.idx[d]; }
+        G.lev = g->lev_dev;
+        for (int d = 0; d < 3; ++d)
+            for (int l = 0; l < 16; ++l) { G.lev_inv[d][l] = g->lev_inv[d][l]; G.lev_cinv[d][l] = 0.25*g->lev_inv[d][l]; }
+        if (!uniform && (g->lev_n[0] < 0 || g->lev_n[1] < 0 || g->lev_n[2] < 0))
+        { set_error("spb_flux_div: more than 16 distinct block spacings along one direction"); return SPB_ERR_UNSUPPORTED; }
         Stage S{};
         if (stage) S = *stage;
         constexpr int NTHREADS = L::NCOMP + 64, NTHREADS_NOGHOST = L::NCOMP + 32;

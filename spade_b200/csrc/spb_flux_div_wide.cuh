@@ -27,6 +27,10 @@ namespace spb
         int increment;
         int lm;                     // general coordinates: length of one metric table row (spb_grid::metric_lm)
         const int* blist;           // local block of CTA group t (a scattered block set in one launch), or null: lb0 + t
+        // the distinct 1/dx of each direction (refinement levels, spb_grid::lev_inv) and the packed level indices of every block:
+        // read through a warp-uniform index (REDUX) they live in uniform registers, not in six vector registers per thread
+        double lev_inv[3][16];
+        const int* lev;
     };
 
     template <int H> struct FdivSmem
@@ -53,7 +57,8 @@ namespace spb
         static constexpr int FXE_DOUBLES = TJ*5;
         static constexpr int BYTES_PRE = NP*PLANE_STRIDE_BYTES + (FXE_DOUBLES + FY_DOUBLES + 2*PUB_CELLS)*8 + NP*8 + 128;
         // PRE kernels on general coordinates: the three metric rows of the tile's x and y range (cells and faces 0 .. TI / TJ)
-        static constexpr int METS_DOUBLES = 3*(TI + 1) + 3*(TJ + 1);
+        static constexpr int METS_ZCAP = 65;                           // staged z entries per row (blocks of up to 64 cells along k)
+        static constexpr int METS_DOUBLES = 3*(TI + 1) + 3*(TJ + 1) + 3*METS_ZCAP;
     };
 
     // accessor of the staged planes, centred on tile-local cell (il, jl) of the current plane
@@ -94,9 +99,11 @@ namespace spb
         double*   Fy   = Fx + (PRE ? S::FXE_DOUBLES : S::FX_DOUBLES);
         double*   pubh = Fy + S::FY_DOUBLES;                                     // PRE: rho/2 of the published plane
         double*   pubs = pubh + S::PUB_CELLS;                                    // PRE: (rho/2)(|u| + c)
-        // PRE + CURV: the x / y metric rows of the tile live in shared memory. A thread's own entries are loop invariants: read
-        // through __ldg the compiler keeps them in registers for the whole k loop (12 registers, paid in spills); shared-memory
-        // loads are not moved across the barriers of a step, so they are simply re-read where a face needs them.
+        // PRE + CURV: the metric rows of the tile (x, y range of the tile, z range of the block) live in shared memory. A thread's
+        // own x / y entries are loop invariants: read through __ldg the compiler keeps them in registers for the whole k loop
+        // (12 registers, paid in spills); shared-memory loads are not moved across the barriers of a step, so they are simply
+        // re-read where a face needs them. The z entries change every step: as global loads they sat at the top of the step in
+        // front of the z-face (long-scoreboard stalls 1.31 per issue against 0.47 on identity coordinates).
         constexpr bool METS = PRE && CURV;
         double*   mets = pubs + S::PUB_CELLS;
         uint64_t* bars = (uint64_t*)(PRE ? pubs + S::PUB_CELLS + (METS ? S::METS_DOUBLES : 0) : Fy + S::FY_DOUBLES);
@@ -114,7 +121,8 @@ namespace spb
         const int nj_t = min(TJ, G.nx[1] - j0);
         const bool active = (il < ni_t) && (jl < nj_t);
 
-        const double invdx[3] = {inv_dx_tab[3*lb + 0], inv_dx_tab[3*lb + 1], inv_dx_tab[3*lb + 2]};
+        const unsigned lpk = __reduce_max_sync(0xffffffffu, (unsigned)__ldg(G.lev + lb));
+        const double invdx[3] = {G.lev_inv[0][lpk & 15u], G.lev_inv[1][(lpk >> 8) & 15u], G.lev_inv[2][(lpk >> 16) & 15u]};
         // metric rows of this block: M(d, row, idx)
         const double* mt = CURV ? met + lb*9*(long long)G.lm : nullptr;
         auto M = [&](const int d, const int row, const int idx) { return __ldg(mt + (d*3 + row)*G.lm + idx); };
@@ -123,6 +131,7 @@ namespace spb
         {
             if (METS && d == 0) return mets[row*(TI + 1) + (idx - i0 - G.ng[0])];
             if (METS && d == 1) return mets[3*(TI + 1) + row*(TJ + 1) + (idx - j0 - G.ng[1])];
+            if (METS && d == 2 && idx - G.ng[2] < S::METS_ZCAP) return mets[3*(TI + 1) + 3*(TJ + 1) + row*S::METS_ZCAP + (idx - G.ng[2])];
             return M(d, row, idx);
         };
         // gradient scales and area factor of the lower face of direction D of the padded cell (ip, jp, kp)
@@ -154,14 +163,18 @@ namespace spb
             for (int s = 0; s < S::NP; ++s) mbar_init(&bars[s], 1);
             fence_mbar_init();
         }
-        if (METS && tid < S::METS_DOUBLES)
+        if (METS)
         {
-            // entry (row, loc) of direction d: padded index origin + loc, clamped to the table (ragged tiles)
-            const bool isx = tid < 3*(TI + 1);
-            const int  e = isx ? tid : tid - 3*(TI + 1), len = isx ? TI + 1 : TJ + 1;
-            const int  row = e / len, loc = e - row*len;
-            const int  idx = min((isx ? i0 + G.ng[0] : j0 + G.ng[1]) + loc, G.lm - 1);
-            mets[tid] = M(isx ? 0 : 1, row, idx);
+            // entry (row, loc) of direction d: padded index origin + loc, clamped to the table (ragged tiles, short blocks)
+            for (int e0 = tid; e0 < S::METS_DOUBLES; e0 += blockDim.x)
+            {
+                const int d = e0 < 3*(TI + 1) ? 0 : (e0 < 3*(TI + 1) + 3*(TJ + 1) ? 1 : 2);
+                const int e = e0 - (d == 0 ? 0 : (d == 1 ? 3*(TI + 1) : 3*(TI + 1) + 3*(TJ + 1)));
+                const int len = d == 0 ? TI + 1 : (d == 1 ? TJ + 1 : S::METS_ZCAP);
+                const int row = e / len, loc = e - row*len;
+                const int org = d == 0 ? i0 + G.ng[0] : (d == 1 ? j0 + G.ng[1] : G.ng[2]);
+                mets[e0] = M(d, row, min(org + loc, G.lm - 1));
+            }
         }
         __syncthreads();
         if (tid == 0)
@@ -272,7 +285,7 @@ namespace spb
                     double gs[3], area;
                     face_metric(DZ, ipc, jpc, k + G.ng[2], gs, area);
                     face_flux<CONV, DISS, VISC, 2, true, SGS, PRE>(acc, P, gs, Fz, area, zh, zs);
-                    if (k >= 1) jac_prev = MP(0, 1, ipc)*MP(1, 1, jpc)*M(2, 1, k - 1 + G.ng[2]);
+                    if (k >= 1) jac_prev = MP(0, 1, ipc)*MP(1, 1, jpc)*MP(2, 1, k - 1 + G.ng[2]);
                 }
                 else face_flux<CONV, DISS, VISC, 2, false, SGS, PRE>(acc, P, invdx, Fz, 1.0, zh, zs);
             }
@@ -529,6 +542,11 @@ namespace spb
         G.lb0 = lb_begin;
         G.increment = increment;
         G.lm = g->metric_lm;
+        if (g->lev_n[0] < 0 || g->lev_n[1] < 0 || g->lev_n[2] < 0)
+        { set_error("spb_flux_div: more than 16 distinct block spacings along one direction"); return SPB_ERR_UNSUPPORTED; }
+        G.lev = g->lev_dev;
+        for (int d = 0; d < 3; ++d)
+            for (int l = 0; l < 16; ++l) G.lev_inv[d][l] = g->lev_inv[d][l];
         // fused same-rank ghost exchange: the neighbour table of the plan (refused for plans with non-canonical transactions)
         const int* nbr_tab = nullptr;
         if (FUSED && exch) { int rc = exchange_fuse_table(exch, g->nx, g->ng, g->nlb, &nbr_tab); if (rc) return rc; }
