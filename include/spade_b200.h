@@ -79,7 +79,10 @@ typedef struct spb_flux_desc
  * Local (per-rank) block geometry, replacing the device image of grid_geometry_t
  * (reference src/grid/grid_geometry.h:16-100, src/grid/cartesian_grid.h:114-165).
  * bbox: host array [nlb][6] = xmin,xmax,ymin,ymax,zmin,zmax of each local block in computational
- * coordinates; dx = (max-min)/nx and inv_dx = 1.0/dx are formed exactly as the reference does. */
+ * coordinates; dx = (max-min)/nx and inv_dx = 1.0/dx are formed exactly as the reference does.
+ * The RHS kernels read the spacings of a block as refinement LEVELS: per direction the distinct values of inv_dx (values that
+ * differ by no more than the rounding of the block bounds explains, 4 eps |x|max / block size, are one level; at most 16 per
+ * direction, else the RHS calls return SPB_ERR_UNSUPPORTED). A lattice with one level per direction is "uniform". */
 typedef struct spb_grid spb_grid;
 int  spb_grid_create(spb_grid** out, const int nx[3], const int ng[3], int64_t nlb, const double* bbox_host);
 void spb_grid_destroy(spb_grid* g);
