@@ -87,6 +87,11 @@ typedef struct spb_grid spb_grid;
 int  spb_grid_create(spb_grid** out, const int nx[3], const int ng[3], int64_t nlb, const double* bbox_host);
 void spb_grid_destroy(spb_grid* g);
 int64_t spb_grid_array_size(const spb_grid* g);                    /* doubles in one 5-variable array */
+/* Host-only (no device needed): the refinement levels spb_grid_create derives from the block boxes. lev_n[d] = number of
+ * distinct inv_dx along d (-1: more than 16), lev_inv = [3][16] doubles, lev_of_block (may be null) = [nlb] packed indices
+ * l0 | l1 << 8 | l2 << 16, round_tol (may be null) = [3] relative spread that the rounding of the block bounds explains. */
+int  spb_grid_spacing_levels(const int nx[3], int64_t nlb, const double* bbox_host, int lev_n[3], double* lev_inv,
+                             int* lev_of_block, double* round_tol);
 int64_t spb_grid_offset(const spb_grid* g, int v, int i, int j, int k, int64_t lb);
 
 /* ---- general coordinates: replaces the geometry of coords::diagonal_coords ---------------------

@@ -64,6 +64,7 @@ _ip = C.POINTER(C.c_int)
 # name -> (restype, argtypes); every symbol include/spade_b200.h declares
 SYMBOLS = {
     "spb_grid_create": (C.c_int, [C.POINTER(C.c_void_p), _ip, _ip, C.c_int64, _dp]),
+    "spb_grid_spacing_levels": (C.c_int, [_ip, C.c_int64, _dp, _ip, _dp, _ip, _dp]),
     "spb_grid_destroy": (None, [C.c_void_p]),
     "spb_grid_array_size": (C.c_int64, [C.c_void_p]),
     "spb_grid_offset": (C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]),

@@ -47,6 +47,43 @@ extern "C"
         return 0;
     }
 
+    // Host-only: the distinct inverse spacings of each direction. The reference forms dx = box.size/num_cell block by block from
+    // the rounded block bounds (cartesian_blocks.h:66-71, cartesian_grid.h:134-135), exact to 2 ulp of the COORDINATE: spacings
+    // that differ by no more than 4 eps |x|max / (smallest block size) (at least 8 eps, at most 1e-13) are one level.
+    int spb_grid_spacing_levels(const int nx[3], int64_t nlb, const double* bbox_host, int lev_n[3], double* lev_inv,
+                                int* lev_of_block, double* round_tol)
+    {
+        if (!nx || nlb < 0 || (nlb > 0 && !bbox_host) || !lev_n || !lev_inv) { spb::set_error("spb_grid_spacing_levels: bad argument"); return SPB_ERR_BAD_ARG; }
+        const double eps = 2.220446049250313e-16;
+        for (int64_t lb = 0; lb < nlb && lev_of_block; ++lb) lev_of_block[lb] = 0;
+        for (int d = 0; d < 3; ++d)
+        {
+            if (nx[d] < 1) { spb::set_error("spb_grid_spacing_levels: bad extents"); return SPB_ERR_BAD_ARG; }
+            double xmax = 0.0, smin = 0.0;
+            for (int64_t lb = 0; lb < nlb; ++lb)
+            {
+                const double lo = bbox_host[6*lb + 2*d], hi = bbox_host[6*lb + 2*d + 1];
+                xmax = fmax(xmax, fmax(fabs(lo), fabs(hi)));
+                smin = (lb == 0) ? fabs(hi - lo) : fmin(smin, fabs(hi - lo));
+            }
+            const double rt = (smin > 0.0) ? 4.0*eps*xmax/smin : 0.0;
+            if (round_tol) round_tol[d] = rt;
+            const double tol = fmin(fmax(8.0*eps, rt), 1e-13);
+            int n = 0;
+            for (int l = 0; l < 16; ++l) lev_inv[16*d + l] = 0.0;
+            for (int64_t lb = 0; lb < nlb && n >= 0; ++lb)
+            {
+                const double a = 1.0/((bbox_host[6*lb + 2*d + 1] - bbox_host[6*lb + 2*d])/nx[d]);     // inv_dx as the reference forms it
+                int l = 0;
+                while (l < n && !(fabs(a - lev_inv[16*d + l]) <= tol*fabs(a))) ++l;
+                if (l == n) { if (n == 16) { n = -1; break; } lev_inv[16*d + n++] = a; }
+                if (lev_of_block) lev_of_block[lb] |= l << (8*d);
+            }
+            lev_n[d] = n;
+        }
+        return 0;
+    }
+
     // reference: src/grid/cartesian_grid.h:114-136 (dx = box.size/num_cell; inv_dx = 1.0/dx)
     int spb_grid_create(spb_grid** out, const int nx[3], const int ng[3], int64_t nlb, const double* bbox_host)
     {
@@ -66,33 +103,9 @@ extern "C"
                 g->dx_host[3*lb+d] = dx;
                 g->inv_dx_host[3*lb+d] = 1.0/dx;
             }
-        for (int d = 0; d < 3; ++d)
-        {
-            double xmax = 0.0, smin = 0.0;
-            for (int64_t lb = 0; lb < nlb; ++lb)
-            {
-                const double lo = bbox_host[6*lb + 2*d], hi = bbox_host[6*lb + 2*d + 1];
-                xmax = fmax(xmax, fmax(fabs(lo), fabs(hi)));
-                smin = (lb == 0) ? fabs(hi - lo) : fmin(smin, fabs(hi - lo));
-            }
-            g->spacing_round_tol[d] = (smin > 0.0) ? 4.0*2.220446049250313e-16*xmax/smin : 0.0;
-        }
         // refinement levels per direction (an AMR grid has a handful; a uniform lattice one)
         std::vector<int> lev(nlb > 0 ? nlb : 0, 0);
-        for (int d = 0; d < 3; ++d)
-        {
-            const double tol = fmin(fmax(8.0*2.220446049250313e-16, g->spacing_round_tol[d]), 1e-13);
-            int n = 0;
-            for (int64_t lb = 0; lb < nlb && n >= 0; ++lb)
-            {
-                const double a = g->inv_dx_host[3*lb + d];
-                int l = 0;
-                while (l < n && !(fabs(a - g->lev_inv[d][l]) <= tol*fabs(a))) ++l;
-                if (l == n) { if (n == 16) { n = -1; break; } g->lev_inv[d][n++] = a; }
-                lev[lb] |= l << (8*d);
-            }
-            g->lev_n[d] = n;
-        }
+        spb_grid_spacing_levels(nx, nlb, bbox_host, g->lev_n, &g->lev_inv[0][0], nlb > 0 ? lev.data() : nullptr, g->spacing_round_tol);
         g->inv_dx_dev = nullptr;
         cudaError_t e = cudaGetDevice(&g->device);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);

@@ -135,3 +135,56 @@ def test_fused_stage_plans_reproduce_every_rk_table():
             w = new_w
         assert abs(w - want) < 1e-14 * abs(want), alg.name
     assert sp.integrator_t._fused_plan(sp.rk4_t) is not None and sp.integrator_t._fused_plan(sp.ssprk3_t) is not None
+
+
+def _levels(nx, boxes):
+    from spade_b200 import _lib
+    lib = _lib.lib()
+    boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+    nlb = boxes.shape[0]
+    lev_n = (C.c_int * 3)()
+    lev_inv = np.zeros((3, 16))
+    lev = np.zeros(nlb, dtype=np.int32)
+    tol = np.zeros(3)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    _lib.check(lib.spb_grid_spacing_levels(_lib.int3(nx), nlb, dp(boxes), lev_n, dp(lev_inv), lev.ctypes.data_as(C.POINTER(C.c_int)), dp(tol)))
+    return list(lev_n), lev_inv, lev, tol
+
+
+def test_spacing_levels_of_weak_scaled_slabs_amr_grids_and_exotic_lattices():
+    """spb_grid_spacing_levels (host-only): every rank of a weak-scaled TGV box is ONE level per direction although the reference's
+    box.size/num_cell (cartesian_grid.h:134-135) wobbles by 10-20 ulp on the ranks away from the origin — the case that sent
+    ranks 1 and 2 to a slower kernel variant in rounds 1 and 2; an AMR grid has one level per refinement; more than 16 distinct
+    spacings along a direction are reported as -1 (the RHS calls then refuse the grid)."""
+    import spade_b200.api as sp
+    L, eps = 2 * np.pi, 2.220446049250313e-16
+    n = 8
+    blocks = sp.cartesian_blocks_t((2, 2, 16 * n), [0.0, L, 0.0, L, 0.0, L * n])
+    wobble = []
+    for r in range(n):
+        boxes = np.array([blocks.get_block_box(lb) for lb in range(r * 64, (r + 1) * 64)])
+        inv = 1.0 / ((boxes[:, 5] - boxes[:, 4]) / 32)
+        wobble.append(np.ptp(inv) / inv[0] / eps)
+        lev_n, lev_inv, lev, tol = _levels((32, 32, 32), boxes)
+        assert lev_n == [1, 1, 1] and not lev.any()
+        assert lev_inv[2, 0] == inv[0] and tol[2] >= wobble[-1] * eps
+    assert max(wobble) > 8                                   # the old fixed 8-ulp test failed on such ranks
+    # three refinement levels along x and z, two along y, blocks far from the origin
+    rng = np.random.default_rng(0)
+    boxes, want = [], []
+    for _ in range(200):
+        l = rng.integers(0, 3, size=3) % np.array([3, 2, 3])
+        lo = rng.uniform(-40.0, 40.0, size=3)
+        size = 1.0 / 2.0 ** l
+        boxes.append([lo[0], lo[0] + size[0], lo[1], lo[1] + size[1], lo[2], lo[2] + size[2]])
+        want.append(l)
+    lev_n, lev_inv, lev, tol = _levels((16, 16, 16), np.array(boxes))
+    assert lev_n == [3, 2, 3]
+    for b, l in zip(range(200), want):
+        for d in range(3):
+            got = lev_inv[d, (lev[b] >> (8 * d)) & 255]
+            assert abs(got - 16.0 * 2.0 ** l[d]) <= 1e-13 * got
+    # 17 distinct block sizes along y
+    boxes = np.array([[0.0, 1.0, 0.0, 1.0 + 0.1 * k, 0.0, 1.0] for k in range(17)])
+    lev_n, _, _, _ = _levels((8, 8, 8), boxes)
+    assert lev_n == [1, -1, 1]
