@@ -778,17 +778,38 @@ def ours(args):
     if not args.no_e2e:
         e2e = e2e_leg(w, args, sp, torch, dist, world, args.steps)
 
-    # config 4 (256^3 per GPU, the weak-scaling sweep BASELINE names) in the same line of the default run
+    # The other BASELINE configurations in the same line of the default run, so that the driver's records carry them at every N:
+    # config 4 (256^3 per GPU, the weak-scaling sweep BASELINE names), config 3 (stretched channel, hybrid WENO + Ducros + viscous,
+    # a 1024 x 512 x 64 slab per GPU: N = 8 is the 1024 x 512 x 512 grid) and config 5 (the AMR grid, strong scaling), each with
+    # its own parity check through the same code path. A sub-record that fails reports the error; the main line stands.
     configs = None
     if args.config == 2 and not args.no_configs and not args.lattice:
-        w4 = build_workload(4, args, sp, pool, torch, timing)
-        m4 = measure(w4, max(args.steps, 20), max(args.warmup, 3), sp, torch, dist, world, rank, local_rank, timing, False)
-        r4 = roofline_of(w4, m4, max(args.steps, 20))
-        configs = {"config4": {"workload": workload_config(argparse.Namespace(**{**vars(args), "config": 4}), n)["workload"],
-                               "value": m4["value"], "unit": UNIT, "ms_per_step": m4["ms"] / max(args.steps, 20), "steps": max(args.steps, 20),
-                               "gpu_launches": m4["launches"], "scaling": "weak",
-                               "roofline": {k: r4[k] for k in ("bound", "achieved", "peak", "unit", "frac", "ms_per_launch", "alg_bytes_per_cell", "step_share")}}}
-        del w4
+        configs = {}
+        for cid in (4, 3, 5):
+            try:
+                sub_scheme = "hybrid" if cid == 3 else "central"
+                sub_args = argparse.Namespace(**{**vars(args), "config": cid, "scheme": sub_scheme})
+                ksteps = max(args.steps, 20) if cid == 4 else max(5, min(args.steps, 10))
+                par = None
+                if cid != 4 and not args.no_parity:          # config 4 runs the functor set and code path the main line has checked
+                    try:
+                        par = parity_check(cid, sub_scheme, sp, pool, torch)
+                    except Exception as exc:
+                        par = {"ok": False, "error": repr(exc)[:300]}
+                wc = build_workload(cid, sub_args, sp, pool, torch, timing)
+                mc = measure(wc, ksteps, max(args.warmup, 3), sp, torch, dist, world, rank, local_rank, timing, False)
+                rc = roofline_of(wc, mc, ksteps)
+                keys = ("bound", "achieved", "peak", "unit", "frac", "ms_per_launch", "alg_bytes_per_cell", "step_share", "frac_of_measured_dfma_rate", "hbm")
+                configs[f"config{cid}"] = {"workload": workload_config(sub_args, n)["workload"],
+                                           "value": mc["value"], "unit": UNIT, "ms_per_step": mc["ms"] / ksteps, "steps": ksteps,
+                                           "gpu_launches": mc["launches"], "scaling": wc.scaling,
+                                           "roofline": {k: rc[k] for k in keys if k in rc}}
+                if par is not None:
+                    configs[f"config{cid}"]["parity_check"] = par
+                del wc
+            except Exception as exc:                         # never take the headline down with a sub-record
+                configs[f"config{cid}"] = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
 
     cpu_baseline, ref_gpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
