@@ -6,8 +6,8 @@
 Workloads (BASELINE.json `configs`, numbered from 1):
   2 (default, the configuration the metric is quoted on): Taylor-Green vortex, 512^3 cells per GPU in 32^3 blocks
     (16 x 16 x 16N blocks, 2 exchange cells), totani_lr + visc_lr, rk4_t with the fused prim/cons update, periodic.
-  4: the weak-scaling sweep, 256^3 cells per GPU (8 x 8 x 8N blocks), same solver. The default run also measures it
-    briefly and reports it in the `configs` sub-record of the same JSON line.
+  4: the weak-scaling sweep, 256^3 cells per GPU (8 x 8 x 8N blocks), same solver. The default run also measures
+    configs 4, 3 and 5 briefly and reports them in the `configs` sub-records of the same JSON line.
   3: compressible channel, 1024 x 512 x 64N cells (32 x 16 x 2N blocks; N = 8 is the 1024 x 512 x 512 grid), y stretched
     with integrated_tanh_1D, isothermal no-slip walls, hybrid(totani_lr, fweno_t, ducros_t) + visc_lr. FP64-bound:
     `roofline.bound` = "fp64".
