@@ -20,6 +20,13 @@ metric: cell-stage-updates/s = cells x stages x steps / time (a cell advanced th
 Before the timed region every run advances a small lattice of the same functor set through the same code path
 (fused stage kernel, two-stream overlap, peer-memory or NCCL messages) and compares it with the oracle
 (`parity_check` in the line: exchange bit-exact, 2 RK4 steps to 1e-12). Prints ONE JSON line.
+
+Development switches (environment; none of them changes what the default line measures): SPB_PHASE_EVENTS=1 adds per-rank
+stage phases, join / step times, clocks and GPU identity (`phases`); SPB_DEFER_UNPACK=0, SPB_P2P=0, SPB_BLOCK_RUNS=1 select the
+undeferred schedule, NCCL send/recv, one launch per contiguous block run; SPB_DIAG_SOLO=1 lets every rank run the 1-GPU
+workload under torchrun; SPB_DIAG_DELAY_RANK=r delays rank r by 30 ms at the head of the timed region; SPB_BOUNDARY_DELAY_US
+delays the boundary kernel on the side stream; SPB_NO_CLOCK_SAMPLER=1 switches the NVML sampler off (tools/gpu_visit.sh phases /
+solo2 / steps use them; the findings are in DESIGN section 6).
 """
 import argparse
 import json
